@@ -1,0 +1,180 @@
+/*
+ * m3pc.h -- C-ABI of the B200-native (sm_100a) M^3PC test-time-planning hot path.
+ *
+ * The reference (wkh923/m3pc) is pure Python/PyTorch and has NO FFI; this header is the boundary a
+ * maintainer would bind from Python (ctypes / cffi / a torch extension shim).
+ * Every entry point cites the reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain pointers + sizes + a CUDA stream (passed as void*, i.e. cudaStream_t); no torch types.
+ *   - every function returns 0 on success, <0 on error (never throws across the ABI);
+ *     m3pc_last_error() returns a thread-local message for the last failing call.
+ *   - the caller allocates and owns all I/O buffers ("device" = device pointer, "host" = host pointer);
+ *     the library owns only what hangs off the handle (packed weights, workspaces).
+ *   - all work is enqueued on the caller's stream; no internal host synchronisation except in
+ *     m3pc_create / m3pc_finalize_params / m3pc_destroy.
+ *   - one handle per (process, device); calls on one handle must be externally serialised.
+ *   - there is no CPU fallback: without a sm_100 device every compute call fails with M3PC_ERR_CUDA.
+ *
+ * Activation layout inside the library is token-major: row = token * B + b (B = batch of candidates or
+ * environments).  It is never exposed: all I/O tensors below use the reference's (B, T, d) layout.
+ */
+#ifndef M3PC_H_
+#define M3PC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define M3PC_OK 0
+#define M3PC_ERR_INVALID (-1) /* bad argument / unsupported configuration */
+#define M3PC_ERR_CUDA (-2)    /* CUDA runtime / driver error, or no sm_100 device */
+#define M3PC_ERR_STATE (-3)   /* call order violated (e.g. forward before finalize_params) */
+#define M3PC_ERR_NOMEM (-4)
+
+#define M3PC_PREC_BF16 0 /* bf16 operands on tcgen05 tensor cores, fp32 accumulate, fp32 residual stream */
+#define M3PC_PREC_FP32 1 /* fp32 operands and accumulate on CUDA cores (reference-grade, 1e-5) */
+
+/* modality order everywhere: the reference's dict order, finetune_omtm/learner.py:361-366 */
+#define M3PC_STATES 0
+#define M3PC_ACTIONS 1
+#define M3PC_REWARDS 2
+#define M3PC_RETURNS 3
+
+#define M3PC_MAX_T 16    /* traj_length limit (tokens = 4*T <= 64) */
+#define M3PC_MAX_ACT 32  /* action dim limit */
+#define M3PC_MAX_OBS 128 /* observation dim limit */
+
+/* plan_guidance values, finetune_omtm/learner.py:388-412 */
+#define M3PC_GUIDE_RTG 0          /* rtg_guiding            learner.py:271-327 */
+#define M3PC_GUIDE_CRITIC 1       /* critic_lambda_guiding  learner.py:211-268 */
+#define M3PC_GUIDE_NOISE_CRITIC 2 /* noise_adding_lambda    learner.py:142-208 */
+#define M3PC_GUIDE_SAMPLING 3     /* plan=False: mtm_sampling learner.py:103-115 */
+
+typedef struct m3pc_engine* m3pc_handle_t;
+
+/* Replaces omtmConfig + data_shapes + traj_length (omtm/models/mtm_model.py:200-221, 324-437). */
+typedef struct {
+  int32_t n_embd;      /* multiple of 128; head_dim must be 128 */
+  int32_t n_head;      /* n_embd / 128 */
+  int32_t n_enc_layer;
+  int32_t n_dec_layer;
+  int32_t traj_length; /* T <= M3PC_MAX_T */
+  int32_t obs_dim;
+  int32_t act_dim;
+  int32_t precision;     /* M3PC_PREC_* */
+  int32_t max_batch;     /* largest B (candidates or envs) a call will pass */
+  int32_t chunk;         /* B rows per kernel sequence (L2 blocking); 0 = library default */
+  int32_t critic_hidden; /* TwinQ hidden width (256 in the reference); 0 = no critic */
+  int32_t reserved[5];
+} m3pc_config_t;
+
+const char* m3pc_last_error(void);
+const char* m3pc_version(void);
+
+/* Learner.__init__ model construction (finetune_omtm/learner.py:30-36). */
+int m3pc_create(m3pc_handle_t* out, const m3pc_config_t* cfg);
+int m3pc_destroy(m3pc_handle_t h);
+
+/*
+ * omtm.load_state_dict (learner.py:33-35), TwinQ weights (finetune_omtm/model.py:146-160) and tokenizer
+ * statistics (omtm/tokenizers/continuous.py:32-62), by NAME:
+ *   - every key of the reference's omtm.state_dict(), verbatim ("encoder.layers.0.linear1.weight", ...);
+ *   - "critic.q1.net.0.weight" ... "critic.q2.net.4.bias", "critic.obs_mean", "critic.obs_std";
+ *   - "tokenizer.<modality>.mean" / ".std" for states, rewards, returns (actions are not normalised).
+ * `data` is a HOST pointer to `count` fp32 values in the tensor's row-major order.
+ */
+int m3pc_set_param(m3pc_handle_t h, const char* name, const float* data, size_t count);
+/* Packs weights for the device (bf16 K-major copies, fused constants). Must follow the last m3pc_set_param. */
+int m3pc_finalize_params(m3pc_handle_t h);
+
+/*
+ * omtm.forward(trajectories, masks)  (mtm_model.py:593-607), P = 1 token per time step.
+ *   tok_*   device fp32, tokenised inputs (B,T,d) (what TokenizerManager.encode returns, squeezed)
+ *   masks   HOST, 4*T bytes of {0,1}, modality-major (states, actions, rewards, returns)
+ *   out_*   device fp32 (B,T,d) raw head outputs (before TokenizerManager.decode); any may be NULL.
+ *           out_act_mu / out_act_std are the parameters of the reference's SquashedNormal
+ *           (mtm_model.py:313-321): mean = tanh(mu), sample = tanh(mu + std*eps).
+ */
+int m3pc_forward(m3pc_handle_t h, int32_t batch, const float* tok_states, const float* tok_actions,
+                 const float* tok_rewards, const float* tok_returns, const uint8_t* masks, float* out_states,
+                 float* out_act_mu, float* out_act_std, float* out_rewards, float* out_returns, void* stream);
+
+/* Per-shard record for the multi-GPU combine. Floats, in this order:
+ *   [0] m = max_n J_n   [1] Z = sum exp(tau (J_n - m))   [2] best J   [3] best global idx (as float bits of int32)
+ *   [4] best sample key p_n/q_n (relative to local m)   [5] its global idx (int32 bits)   [6] n_cand
+ *   [7] reserved   [8 .. 8+A) U = sum exp(tau (J_n - m)) * a0_n   [8+A .. 8+2A) a0 of best key   */
+#define M3PC_PARTIAL_FLOATS (8 + 2 * M3PC_MAX_ACT)
+
+/* Learner.rtg_guiding / critic_lambda_guiding / noise_adding_lambda / mtm_sampling on one window
+ * (finetune_omtm/learner.py:103-327), after Learner.action_sample built the window (learner.py:342-385). */
+typedef struct {
+  int32_t guidance;     /* M3PC_GUIDE_* */
+  int32_t horizon;      /* h: the planner conditions on tokens < T-h and plans tokens >= T-h */
+  int32_t n_cand;       /* candidates evaluated by THIS call (cfg.action_samples, or this rank's shard) */
+  int32_t cand_offset;  /* global id of local candidate 0 (noise / index bookkeeping under sharding) */
+  float discount;       /* cfg.discount */
+  float temperature;    /* cfg.temperature */
+  float lmbda;          /* cfg.lmbda (rtg_guiding: the reference hard-codes 0.6, learner.py:272,405-407) */
+  int32_t reserved0;
+  const float* win_states;      /* device (T,obs) RAW window (zero padded), learner.py:348-366 */
+  const float* win_actions;     /* device (T,act) RAW */
+  const float* win_rewards;     /* device (T) RAW */
+  const float* win_returns_tok; /* device (T) TOKENISED returns: the host evaluates (rtg-mean)/std in
+                                   float64 and rounds to fp32 exactly as the reference does (learner.py:368-385,
+                                   continuous.py:74-79) */
+  const float* eps;   /* device: injected N(0,1) noise, (n_cand,h,A) for guidance 0/1/2, (A) for 3; NULL = Philox */
+  const float* expq;  /* device (n_cand): injected Exp(1) draws of torch.multinomial; NULL = Philox */
+  uint64_t seed;      /* Philox key when eps/expq are NULL; counter = global candidate id */
+  float* out_eval_action;   /* device (A)  learner.py:323  (mtm_sampling: tanh(mu)) */
+  float* out_sample_action; /* device (A)  learner.py:324-325 */
+  float* out_partials;      /* device (M3PC_PARTIAL_FLOATS) or NULL */
+  float* dbg_expect_return; /* device (n_cand) or NULL: J_n before the max subtraction */
+  float* dbg_candidates;    /* device (n_cand,h,A) or NULL */
+  int32_t* dbg_indices;     /* device (2) or NULL: [argmax_n J_n, sampled idx] (global ids) */
+  void* reserved1[4];
+} m3pc_plan_args_t;
+
+int m3pc_plan(m3pc_handle_t h, const m3pc_plan_args_t* args, void* stream);
+
+/* Combine `n_shards` records (device, n_shards*M3PC_PARTIAL_FLOATS, e.g. the output of an NCCL all-gather)
+ * into the global eval / sample action: log-sum-exp merge of the per-shard softmax partials. */
+int m3pc_merge_partials(m3pc_handle_t h, const float* partials, int32_t n_shards, float temperature,
+                        float* out_eval_action, float* out_sample_action, int32_t* out_indices, void* stream);
+
+/* Zero-shot backward planners on E lock-step environments (zeroshot_omtm/learner.py:60-261).
+ *   mode 0 = action_id_sample (one pass, gid mask); 1 = action_piid_sample (pi mask -> fill states -> fid mask).
+ *   win_* as in m3pc_plan_args_t but with a leading E axis: (E,T,obs) etc.; eps (E,A) or NULL (mean only).
+ *   out_eval_action / out_sample_action: device (E,A). */
+int m3pc_backward_plan(m3pc_handle_t h, int32_t mode, int32_t n_env, int32_t horizon, const float* win_states,
+                       const float* win_actions, const float* win_rewards, const float* win_returns_tok,
+                       const float* eps, float* out_eval_action, float* out_sample_action, float* dbg_states_filled,
+                       void* stream);
+
+/* ---- kernel-level entry points (unit parity tests and profiling; same kernels the calls above launch) ---- */
+
+/* C[M,N] = epilogue(A[M,K] * W[N,K]^T): flags bit0 = GELU(erf), bit1 = C += residual (fp32 in place, C is fp32),
+ * bit2 = ReLU. bias (N) fp32 or NULL.  bf16 variant: A, W are bf16 (device), C is bf16 unless bit1 (then fp32). */
+int m3pc_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int32_t M, int32_t N, int32_t K,
+                   int32_t flags, void* stream);
+int m3pc_gemm_fp32(const float* A, const float* W, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
+                   int32_t flags, void* stream);
+/* y = LayerNorm(x) over the last dim (eps 1e-5); x fp32 (M,D); y bf16 (out_bf16=1) or fp32. */
+int m3pc_layernorm(const float* x, const float* gamma, const float* beta, void* y, int32_t M, int32_t D,
+                   int32_t out_bf16, void* stream);
+/* Bidirectional attention over token-major qkv (S*B rows, 3*D cols), head_dim 128; out (S*B, D). */
+int m3pc_attention(const void* qkv, void* out, int32_t B, int32_t S, int32_t n_head, int32_t is_bf16, void* stream);
+
+/* Device-side time (ms) spent between the first and last kernel of the most recent m3pc_plan / m3pc_forward
+ * on this handle, measured with CUDA events on the caller's stream (valid after the stream is synchronised). */
+int m3pc_last_device_ms(m3pc_handle_t h, float* ms);
+/* Number of kernels the most recent m3pc_plan / m3pc_forward call launched. */
+int m3pc_last_launch_count(m3pc_handle_t h, int32_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* M3PC_H_ */

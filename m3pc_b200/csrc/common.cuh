@@ -1,0 +1,120 @@
+// Shared helpers for the m3pc sm_100a kernels: error plumbing, activation-type traits, warp reductions.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <string>
+
+#include "../../include/m3pc.h"
+
+namespace m3pc {
+
+void set_error(const std::string& msg);
+
+#define M3PC_CHECK_CUDA(expr)                                                                              \
+  do {                                                                                                     \
+    cudaError_t _e = (expr);                                                                               \
+    if (_e != cudaSuccess) {                                                                               \
+      ::m3pc::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
+                        std::to_string(__LINE__) + ")");                                                   \
+      return M3PC_ERR_CUDA;                                                                                \
+    }                                                                                                      \
+  } while (0)
+
+#define M3PC_REQUIRE(cond, msg)                                                                  \
+  do {                                                                                           \
+    if (!(cond)) {                                                                               \
+      ::m3pc::set_error(std::string(msg) + " [" #cond "] (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+      return M3PC_ERR_INVALID;                                                                   \
+    }                                                                                            \
+  } while (0)
+
+#define M3PC_TRY(expr)          \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc != M3PC_OK) return _rc; \
+  } while (0)
+
+// Check the launch that was just issued (cheap: no sync) and count it (m3pc_last_launch_count).
+extern thread_local int g_launch_count;
+#define M3PC_CHECK_LAUNCH()                \
+  do {                                     \
+    ++::m3pc::g_launch_count;              \
+    M3PC_CHECK_CUDA(cudaGetLastError());   \
+  } while (0)
+
+// epilogue flags (public ABI: m3pc_gemm_*)
+constexpr int EPI_GELU = 1;
+constexpr int EPI_RESIDUAL = 2;  // C (fp32) += result, in place
+constexpr int EPI_RELU = 4;
+// internal-only
+constexpr int EPI_ROWTABLE = 8;  // add table[(row / rows_per_group) * N + col]
+constexpr int EPI_OUT_F32 = 16;  // write fp32 even without residual
+
+struct GemmEpilogue {
+  const float* bias = nullptr;    // (N) or null
+  const float* table = nullptr;   // (groups, N) or null; group = row / rows_per_group
+  int rows_per_group = 1;
+  int flags = 0;
+};
+
+// ---- activation element traits -------------------------------------------------------------------
+template <typename T>
+struct Act;
+template <>
+struct Act<float> {
+  static __device__ __forceinline__ float ld(const float* p) { return *p; }
+  static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+};
+template <>
+struct Act<__nv_bfloat16> {
+  static __device__ __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+// 4 consecutive activations <-> float4
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// nn.GELU() (erf form), evaluated in fp32.
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- kernel launchers implemented across the .cu files -----------------------------------------------
+// gemm_tcgen05.cu
+int gemm_bf16_tcgen05(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, int M, int N, int K,
+                      const GemmEpilogue& epi, cudaStream_t st);
+int gemm_init_driver_api();
+// sgemm.cu
+int gemm_fp32(const float* A, const float* W, float* C, int M, int N, int K, const GemmEpilogue& epi, cudaStream_t st);
+
+}  // namespace m3pc

@@ -1,0 +1,903 @@
+// Engine: the handle behind include/m3pc.h -- parameter packing, workspaces, and the launch sequences of
+// omtm.forward (mtm_model.py:593-607) and of the M^3PC planners (finetune_omtm/learner.py:103-327,
+// zeroshot_omtm/learner.py:60-261).  Host code only; every kernel lives in the sibling .cu files.
+//
+// HBM layout: all activations are token-major matrices, row = token * Bc + b for the Bc batch rows (candidates
+// or environments) of the current chunk.  A chunk is run through the whole network before the next one starts,
+// so its working set (<= ~80 bytes/feature/row) stays L2-resident; weights (22.7 MB bf16) stay L2-resident too.
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace m3pc {
+
+thread_local int g_launch_count = 0;
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+
+namespace {
+
+const char* kMod[4] = {"states", "actions", "rewards", "returns"};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int alloc(size_t n) {
+    free();
+    if (n == 0) n = 16;
+    M3PC_CHECK_CUDA(cudaMalloc(&p, n));
+    bytes = n;
+    return M3PC_OK;
+  }
+  void free() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  ~DevBuf() { free(); }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct LayerW {
+  const float *in_w, *in_b, *out_w, *out_b, *l1_w, *l1_b, *l2_w, *l2_b, *n1_w, *n1_b, *n2_w, *n2_b;
+  const __nv_bfloat16 *in_w16, *out_w16, *l1_w16, *l2_w16;
+};
+struct StackW {
+  std::vector<LayerW> layers;
+  const float *norm_w, *norm_b;
+};
+
+// source of one modality's tokens for the embedding kernel
+struct ModSrc {
+  const float* base = nullptr;  // token t of batch row b at base + b*bstride + t*d
+  long bstride = 0;
+  bool normalize = false;       // apply the tokenizer's (x-mean)/std
+  const float* base2 = nullptr; // tokens t >= t_split come from base2 + b*bstride2 + (t-t_split)*d
+  long bstride2 = 0;
+  int t_split = 1 << 30;
+};
+
+struct FwdIO {
+  ModSrc src[4];
+  uint8_t mask[4 * M3PC_MAX_T];
+  float* out_states = nullptr;
+  float* out_mu = nullptr;
+  float* out_std = nullptr;
+  float* out_rewards = nullptr;
+  float* out_returns = nullptr;
+};
+
+}  // namespace
+}  // namespace m3pc
+
+using namespace m3pc;
+
+struct m3pc_engine {
+  m3pc_config_t cfg{};
+  int D = 0, H = 0, T = 0, F = 0, obs = 0, act = 0, Le = 0, Ld = 0, QH = 0;
+  int dims[4] = {0, 0, 0, 0};
+  bool bf16 = true;
+  int chunk = 0;
+  bool finalized = false;
+  std::map<std::string, std::vector<float>> staged;
+
+  DevBuf arena_f32, arena_bf16;            // packed parameters
+  std::map<std::string, size_t> off_f32;   // name -> float offset in arena_f32
+  std::map<std::string, size_t> off_bf16;  // name -> element offset in arena_bf16
+
+  // derived device pointers
+  const float* enc_wt[4] = {};    // W_enc^T (d, D)
+  const float* enc_cvec = nullptr;  // (4, T, D) bias + perdim + pos
+  const float* dec_cvec = nullptr;  // (4T, D)   bias + perdim + pos
+  const float* dec_maskrow = nullptr;  // (4T, D) W_dec mask_token + dec_cvec
+  const float* dec_w[4] = {};
+  const __nv_bfloat16* dec_w16[4] = {};
+  StackW enc, dec;
+  const float *head_ln_w[4] = {}, *head_ln_b[4] = {}, *head_w1[4] = {}, *head_b1[4] = {}, *head_w3[4] = {}, *head_b3[4] = {};
+  const __nv_bfloat16* head_w1_16[4] = {};
+  const float *mu_w = nullptr, *mu_b = nullptr, *ls_w = nullptr, *ls_b = nullptr;
+  const float *tok_mean[4] = {}, *tok_std[4] = {};
+  float h_tok_mean[4] = {0, 0, 0, 0}, h_tok_std[4] = {1, 1, 1, 1};  // scalar modalities (rewards, returns) on host
+  bool has_critic = false;
+  const float *q_w[2][3] = {}, *q_b[2][3] = {}, *obs_mean = nullptr, *obs_std = nullptr;
+
+  // workspaces (per chunk)
+  DevBuf X, Y, Y2, QKV, ATT, HID, ENC;
+  // planner buffers
+  DevBuf p1_mu, p1_std, cand, pred_states, pred_rewards, pred_returns, sa, qa, qb1, qb2, qvals, J, filled, e_mu, e_std;
+
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int last_launches = 0;
+
+  ~m3pc_engine() {
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+  }
+};
+
+namespace m3pc {
+namespace {
+
+size_t act_bytes(const m3pc_engine* e) { return e->bf16 ? 2 : 4; }
+
+// ------------------------------------------------------------------------------------------------ params
+int need(m3pc_engine* e, const std::string& name, size_t count, const std::vector<float>** out) {
+  auto it = e->staged.find(name);
+  if (it == e->staged.end()) {
+    set_error("missing parameter '" + name + "'");
+    return M3PC_ERR_STATE;
+  }
+  if (it->second.size() != count) {
+    set_error("parameter '" + name + "' has " + std::to_string(it->second.size()) + " values, expected " + std::to_string(count));
+    return M3PC_ERR_INVALID;
+  }
+  *out = &it->second;
+  return M3PC_OK;
+}
+
+struct Packer {
+  std::vector<float> f32;
+  std::vector<std::pair<size_t, size_t>> bf16_src;  // (offset in f32, count) of tensors that also get a bf16 copy
+  std::map<std::string, size_t>* off;
+  std::map<std::string, size_t>* off16;
+  size_t n16 = 0;
+  size_t add(const std::string& name, const float* data, size_t n, bool also_bf16 = false) {
+    // 64-float (256 B) alignment keeps every tensor TMA/float4 friendly
+    while (f32.size() % 64) f32.push_back(0.f);
+    const size_t o = f32.size();
+    f32.insert(f32.end(), data, data + n);
+    (*off)[name] = o;
+    if (also_bf16) {
+      while (n16 % 128) ++n16;
+      (*off16)[name] = n16;
+      bf16_src.push_back({o, n});
+      n16 += n;
+    }
+    return o;
+  }
+};
+
+int pack_stack(m3pc_engine* e, Packer& pk, const std::string& prefix, int n_layer) {
+  const size_t D = e->D, F = e->F;
+  const std::vector<float>* v;
+  for (int l = 0; l < n_layer; ++l) {
+    const std::string p = prefix + ".layers." + std::to_string(l);
+    struct Item { const char* suffix; size_t n; bool mat; } items[] = {
+        {".self_attn.in_proj_weight", 3 * D * D, true}, {".self_attn.in_proj_bias", 3 * D, false},
+        {".self_attn.out_proj.weight", D * D, true},    {".self_attn.out_proj.bias", D, false},
+        {".linear1.weight", F * D, true},               {".linear1.bias", F, false},
+        {".linear2.weight", D * F, true},               {".linear2.bias", D, false},
+        {".norm1.weight", D, false},                    {".norm1.bias", D, false},
+        {".norm2.weight", D, false},                    {".norm2.bias", D, false}};
+    for (auto& it : items) {
+      M3PC_TRY(need(e, p + it.suffix, it.n, &v));
+      pk.add(p + it.suffix, v->data(), it.n, it.mat && e->bf16);
+    }
+  }
+  M3PC_TRY(need(e, prefix + ".norm.weight", D, &v));
+  pk.add(prefix + ".norm.weight", v->data(), D);
+  M3PC_TRY(need(e, prefix + ".norm.bias", D, &v));
+  pk.add(prefix + ".norm.bias", v->data(), D);
+  return M3PC_OK;
+}
+
+void bind_stack(m3pc_engine* e, StackW& s, const std::string& prefix, int n_layer) {
+  const float* base = e->arena_f32.as<float>();
+  const __nv_bfloat16* base16 = e->arena_bf16.as<__nv_bfloat16>();
+  auto f = [&](const std::string& n) { return base + e->off_f32.at(n); };
+  auto h = [&](const std::string& n) -> const __nv_bfloat16* { return e->bf16 ? base16 + e->off_bf16.at(n) : nullptr; };
+  s.layers.resize(n_layer);
+  for (int l = 0; l < n_layer; ++l) {
+    const std::string p = prefix + ".layers." + std::to_string(l);
+    LayerW& w = s.layers[l];
+    w.in_w = f(p + ".self_attn.in_proj_weight"); w.in_b = f(p + ".self_attn.in_proj_bias");
+    w.out_w = f(p + ".self_attn.out_proj.weight"); w.out_b = f(p + ".self_attn.out_proj.bias");
+    w.l1_w = f(p + ".linear1.weight"); w.l1_b = f(p + ".linear1.bias");
+    w.l2_w = f(p + ".linear2.weight"); w.l2_b = f(p + ".linear2.bias");
+    w.n1_w = f(p + ".norm1.weight"); w.n1_b = f(p + ".norm1.bias");
+    w.n2_w = f(p + ".norm2.weight"); w.n2_b = f(p + ".norm2.bias");
+    w.in_w16 = h(p + ".self_attn.in_proj_weight"); w.out_w16 = h(p + ".self_attn.out_proj.weight");
+    w.l1_w16 = h(p + ".linear1.weight"); w.l2_w16 = h(p + ".linear2.weight");
+  }
+  s.norm_w = f(prefix + ".norm.weight");
+  s.norm_b = f(prefix + ".norm.bias");
+}
+
+int finalize(m3pc_engine* e) {
+  const size_t D = e->D, T = e->T;
+  Packer pk;
+  pk.off = &e->off_f32;
+  pk.off16 = &e->off_bf16;
+  e->off_f32.clear();
+  e->off_bf16.clear();
+  const std::vector<float>* v;
+  const std::vector<float>* pos;
+  M3PC_TRY(need(e, "pos_embed", T * D, &pos));
+
+  std::vector<float> enc_cvec(4 * T * D), dec_cvec(4 * T * D), dec_maskrow(4 * T * D);
+  for (int k = 0; k < 4; ++k) {
+    const size_t d = e->dims[k];
+    const std::string m = kMod[k];
+    const std::vector<float>*ew, *eb, *epd, *dw, *db, *dpd, *mt;
+    M3PC_TRY(need(e, "encoder_embed_dict." + m + ".weight", D * d, &ew));
+    M3PC_TRY(need(e, "encoder_embed_dict." + m + ".bias", D, &eb));
+    M3PC_TRY(need(e, "encoder_per_dim_encoding." + m, D, &epd));
+    M3PC_TRY(need(e, "decoder_embed_dict." + m + ".weight", D * D, &dw));
+    M3PC_TRY(need(e, "decoder_embed_dict." + m + ".bias", D, &db));
+    M3PC_TRY(need(e, "decoder_per_dim_encoding." + m, D, &dpd));
+    M3PC_TRY(need(e, "mask_token_dict." + m, D, &mt));
+    // W_enc^T (d, D): lanes of the embedding kernel read it coalesced along D
+    std::vector<float> wt(d * D);
+    for (size_t c = 0; c < D; ++c)
+      for (size_t i = 0; i < d; ++i) wt[i * D + c] = (*ew)[c * d + i];
+    pk.add("enc_wt." + m, wt.data(), wt.size());
+    pk.add("decoder_embed_dict." + m + ".weight", dw->data(), D * D, e->bf16);
+    // W_dec mask_token (fp64 accumulate, rounded once)
+    std::vector<float> wm(D);
+    for (size_t c = 0; c < D; ++c) {
+      double s = 0.0;
+      for (size_t i = 0; i < D; ++i) s += static_cast<double>((*dw)[c * D + i]) * static_cast<double>((*mt)[i]);
+      wm[c] = static_cast<float>(s);
+    }
+    for (size_t t = 0; t < T; ++t)
+      for (size_t c = 0; c < D; ++c) {
+        const size_t o = (k * T + t) * D + c;
+        enc_cvec[o] = ((*eb)[c] + (*epd)[c]) + (*pos)[t * D + c];
+        dec_cvec[o] = ((*db)[c] + (*dpd)[c]) + (*pos)[t * D + c];
+        dec_maskrow[o] = ((wm[c] + (*db)[c]) + (*dpd)[c]) + (*pos)[t * D + c];
+      }
+  }
+  pk.add("enc_cvec", enc_cvec.data(), enc_cvec.size());
+  pk.add("dec_cvec", dec_cvec.data(), dec_cvec.size());
+  pk.add("dec_maskrow", dec_maskrow.data(), dec_maskrow.size());
+  M3PC_TRY(pack_stack(e, pk, "encoder", e->Le));
+  M3PC_TRY(pack_stack(e, pk, "decoder", e->Ld));
+  for (int k = 0; k < 4; ++k) {
+    const std::string m = kMod[k];
+    const size_t d = e->dims[k];
+    if (k == M3PC_ACTIONS) {
+      const char* names[4] = {"output_head_dict.actions.mu.weight", "output_head_dict.actions.mu.bias",
+                              "output_head_dict.actions.log_std.weight", "output_head_dict.actions.log_std.bias"};
+      const size_t counts[4] = {d * D, d, d * D, d};
+      for (int i = 0; i < 4; ++i) {
+        M3PC_TRY(need(e, names[i], counts[i], &v));
+        pk.add(names[i], v->data(), counts[i]);
+      }
+    } else {
+      const std::string p = "output_head_dict." + m;
+      struct Item { const char* suffix; size_t n; bool mat; } items[] = {{".0.weight", D, false}, {".0.bias", D, false},
+                                                                       {".1.weight", D * D, true}, {".1.bias", D, false},
+                                                                       {".3.weight", d * D, false}, {".3.bias", d, false}};
+      for (auto& it : items) {
+        M3PC_TRY(need(e, p + it.suffix, it.n, &v));
+        pk.add(p + it.suffix, v->data(), it.n, it.mat && e->bf16);
+      }
+      // tokenizer statistics (decode needs them for all three; encode for states/rewards)
+      M3PC_TRY(need(e, "tokenizer." + m + ".mean", d, &v));
+      pk.add("tokenizer." + m + ".mean", v->data(), d);
+      if (d == 1) e->h_tok_mean[k] = (*v)[0];
+      M3PC_TRY(need(e, "tokenizer." + m + ".std", d, &v));
+      pk.add("tokenizer." + m + ".std", v->data(), d);
+      if (d == 1) e->h_tok_std[k] = (*v)[0];
+    }
+  }
+  e->has_critic = false;
+  if (e->QH > 0 && e->staged.count("critic.q1.net.0.weight")) {
+    const size_t in = e->obs + e->act, Hq = e->QH;
+    const size_t wn[3] = {Hq * in, Hq * Hq, Hq}, bn[3] = {Hq, Hq, 1};
+    for (int q = 0; q < 2; ++q)
+      for (int l = 0; l < 3; ++l) {
+        const std::string p = "critic.q" + std::to_string(q + 1) + ".net." + std::to_string(2 * l);
+        M3PC_TRY(need(e, p + ".weight", wn[l], &v));
+        pk.add(p + ".weight", v->data(), wn[l]);
+        M3PC_TRY(need(e, p + ".bias", bn[l], &v));
+        pk.add(p + ".bias", v->data(), bn[l]);
+      }
+    M3PC_TRY(need(e, "critic.obs_mean", e->obs, &v));
+    pk.add("critic.obs_mean", v->data(), e->obs);
+    M3PC_TRY(need(e, "critic.obs_std", e->obs, &v));
+    pk.add("critic.obs_std", v->data(), e->obs);
+    e->has_critic = true;
+  }
+
+  // upload
+  M3PC_TRY(e->arena_f32.alloc(pk.f32.size() * sizeof(float)));
+  M3PC_CHECK_CUDA(cudaMemcpy(e->arena_f32.p, pk.f32.data(), pk.f32.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (e->bf16) {
+    M3PC_TRY(e->arena_bf16.alloc((pk.n16 + 128) * sizeof(__nv_bfloat16)));
+    M3PC_CHECK_CUDA(cudaMemset(e->arena_bf16.p, 0, e->arena_bf16.bytes));
+    size_t o16 = 0;
+    for (auto& pr : pk.bf16_src) {
+      while (o16 % 128) ++o16;
+      M3PC_TRY(launch_f32_to_bf16(e->arena_f32.as<float>() + pr.first, e->arena_bf16.as<__nv_bfloat16>() + o16, pr.second, 0));
+      o16 += pr.second;
+    }
+    M3PC_CHECK_CUDA(cudaDeviceSynchronize());
+  }
+
+  // bind
+  const float* base = e->arena_f32.as<float>();
+  const __nv_bfloat16* base16 = e->arena_bf16.as<__nv_bfloat16>();
+  auto f = [&](const std::string& n) { return base + e->off_f32.at(n); };
+  auto h16 = [&](const std::string& n) -> const __nv_bfloat16* { return e->bf16 ? base16 + e->off_bf16.at(n) : nullptr; };
+  e->enc_cvec = f("enc_cvec");
+  e->dec_cvec = f("dec_cvec");
+  e->dec_maskrow = f("dec_maskrow");
+  for (int k = 0; k < 4; ++k) {
+    const std::string m = kMod[k];
+    e->enc_wt[k] = f("enc_wt." + m);
+    e->dec_w[k] = f("decoder_embed_dict." + m + ".weight");
+    e->dec_w16[k] = h16("decoder_embed_dict." + m + ".weight");
+    if (k != M3PC_ACTIONS) {
+      const std::string p = "output_head_dict." + m;
+      e->head_ln_w[k] = f(p + ".0.weight"); e->head_ln_b[k] = f(p + ".0.bias");
+      e->head_w1[k] = f(p + ".1.weight"); e->head_b1[k] = f(p + ".1.bias");
+      e->head_w1_16[k] = h16(p + ".1.weight");
+      e->head_w3[k] = f(p + ".3.weight"); e->head_b3[k] = f(p + ".3.bias");
+      e->tok_mean[k] = f("tokenizer." + m + ".mean");
+      e->tok_std[k] = f("tokenizer." + m + ".std");
+    }
+  }
+  e->mu_w = f("output_head_dict.actions.mu.weight"); e->mu_b = f("output_head_dict.actions.mu.bias");
+  e->ls_w = f("output_head_dict.actions.log_std.weight"); e->ls_b = f("output_head_dict.actions.log_std.bias");
+  bind_stack(e, e->enc, "encoder", e->Le);
+  bind_stack(e, e->dec, "decoder", e->Ld);
+  if (e->has_critic) {
+    for (int q = 0; q < 2; ++q)
+      for (int l = 0; l < 3; ++l) {
+        const std::string p = "critic.q" + std::to_string(q + 1) + ".net." + std::to_string(2 * l);
+        e->q_w[q][l] = f(p + ".weight");
+        e->q_b[q][l] = f(p + ".bias");
+      }
+    e->obs_mean = f("critic.obs_mean");
+    e->obs_std = f("critic.obs_std");
+  }
+  e->staged.clear();
+  e->finalized = true;
+  return M3PC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+int gemm(m3pc_engine* e, const void* A, const float* w32, const __nv_bfloat16* w16, void* C, int M, int N, int K, const GemmEpilogue& epi,
+         cudaStream_t st) {
+  if (e->bf16) return gemm_bf16_tcgen05(reinterpret_cast<const __nv_bfloat16*>(A), w16, C, M, N, K, epi, st);
+  return gemm_fp32(reinterpret_cast<const float*>(A), w32, reinterpret_cast<float*>(C), M, N, K, epi, st);
+}
+
+// one pre-LN transformer block on `rows` = S * Bc token-major rows; expects Y = LN1(X) on entry
+int block(m3pc_engine* e, const LayerW& w, int Bc, int S, cudaStream_t st) {
+  const int D = e->D, F = e->F, rows = S * Bc;
+  GemmEpilogue ep;
+  ep.bias = w.in_b;
+  M3PC_TRY(gemm(e, e->Y.p, w.in_w, w.in_w16, e->QKV.p, rows, 3 * D, D, ep, st));
+  M3PC_TRY(launch_attention(e->QKV.p, e->ATT.p, Bc, S, e->H, e->bf16, st));
+  ep = GemmEpilogue{};
+  ep.bias = w.out_b;
+  ep.flags = EPI_RESIDUAL;
+  M3PC_TRY(gemm(e, e->ATT.p, w.out_w, w.out_w16, e->X.p, rows, D, D, ep, st));
+  LnParams ln{};
+  ln.x = e->X.as<float>();
+  ln.rows = rows;
+  ln.g1 = w.n2_w;
+  ln.b1 = w.n2_b;
+  ln.y1 = e->Y.p;
+  ln.rows_per_group = 1;
+  M3PC_TRY(launch_layernorm(ln, D, e->bf16, st));
+  ep = GemmEpilogue{};
+  ep.bias = w.l1_b;
+  ep.flags = EPI_GELU;
+  M3PC_TRY(gemm(e, e->Y.p, w.l1_w, w.l1_w16, e->HID.p, rows, F, D, ep, st));
+  ep = GemmEpilogue{};
+  ep.bias = w.l2_b;
+  ep.flags = EPI_RESIDUAL;
+  M3PC_TRY(gemm(e, e->HID.p, w.l2_w, w.l2_w16, e->X.p, rows, D, F, ep, st));
+  return M3PC_OK;
+}
+
+int forward_chunk(m3pc_engine* e, const FwdIO& io, int b0, int Bc, cudaStream_t st) {
+  const int D = e->D, T = e->T;
+  const size_t ab = act_bytes(e);
+  // ---- token tables from the masks (mtm_model.py:534-544: kept tokens keep their order, modality-major) ----
+  int enc_mod[MAX_TOK], enc_t[MAX_TOK], dec_src[MAX_TOK];
+  int S = 0;
+  for (int k = 0; k < 4; ++k)
+    for (int t = 0; t < T; ++t) {
+      if (io.mask[k * T + t]) {
+        enc_mod[S] = k;
+        enc_t[S] = t;
+        dec_src[k * T + t] = S++;
+      } else {
+        dec_src[k * T + t] = -1;
+      }
+    }
+  M3PC_REQUIRE(S > 0, "forward: every token is masked");
+
+  // ---- K1: embed + gather + first LayerNorm ----
+  EmbedParams ep{};
+  ep.n_tok = S;
+  ep.B = Bc;
+  for (int s = 0; s < S; ++s) {
+    const int k = enc_mod[s], t = enc_t[s], d = e->dims[k];
+    const ModSrc& ms = io.src[k];
+    EmbedTok& tk = ep.tok[s];
+    if (ms.base2 != nullptr && t >= ms.t_split) {
+      tk.src = ms.base2 + static_cast<size_t>(b0) * ms.bstride2 + static_cast<size_t>(t - ms.t_split) * d;
+      tk.bstride = static_cast<int>(ms.bstride2);
+    } else {
+      tk.src = ms.base + static_cast<size_t>(b0) * ms.bstride + static_cast<size_t>(t) * d;
+      tk.bstride = static_cast<int>(ms.bstride);
+    }
+    tk.wt = e->enc_wt[k];
+    tk.cvec = e->enc_cvec + (static_cast<size_t>(k) * T + t) * D;
+    tk.nmean = ms.normalize ? e->tok_mean[k] : nullptr;
+    tk.nstd = ms.normalize ? e->tok_std[k] : nullptr;
+    tk.d = d;
+  }
+  const LayerW& first = e->Le > 0 ? e->enc.layers[0] : e->dec.layers[0];
+  M3PC_TRY(launch_embed(ep, D, e->X.as<float>(), e->Y.p, e->bf16, e->Le > 0 ? first.n1_w : e->enc.norm_w,
+                        e->Le > 0 ? first.n1_b : e->enc.norm_b, st));
+  void* enc_out = e->Le > 0 ? e->ENC.p : e->Y.p;
+
+  // ---- encoder stack (mtm_model.py:379-391, 619-644) ----
+  for (int l = 0; l < e->Le; ++l) {
+    M3PC_TRY(block(e, e->enc.layers[l], Bc, S, st));
+    LnParams ln{};
+    ln.x = e->X.as<float>();
+    ln.rows = S * Bc;
+    ln.rows_per_group = 1;
+    if (l + 1 < e->Le) {
+      ln.g1 = e->enc.layers[l + 1].n1_w;
+      ln.b1 = e->enc.layers[l + 1].n1_b;
+      ln.y1 = e->Y.p;
+    } else {
+      ln.g1 = e->enc.norm_w;
+      ln.b1 = e->enc.norm_b;
+      ln.y1 = e->ENC.p;
+    }
+    M3PC_TRY(launch_layernorm(ln, D, e->bf16, st));
+  }
+
+  // ---- K4: decoder input = decoder_embed(encoder output | mask token) + per-dim + pos (mtm_model.py:646-696) ----
+  FillParams fp{};
+  fp.B = Bc;
+  for (int j = 0; j < 4 * T; ++j)
+    if (dec_src[j] < 0) {
+      fp.row[fp.n] = e->dec_maskrow + static_cast<size_t>(j) * D;
+      fp.tok[fp.n] = j;
+      ++fp.n;
+    }
+  M3PC_TRY(launch_fill_rows(fp, D, e->X.as<float>(), st));
+  for (int j = 0; j < 4 * T;) {  // runs of kept tokens with one modality: one grouped GEMM each
+    if (dec_src[j] < 0) { ++j; continue; }
+    const int k = j / T;
+    int len = 1;
+    while (j + len < (k + 1) * T && dec_src[j + len] == dec_src[j] + len) ++len;
+    GemmEpilogue ge;
+    ge.table = e->dec_cvec + static_cast<size_t>(j) * D;
+    ge.rows_per_group = Bc;
+    ge.flags = EPI_OUT_F32 | EPI_ROWTABLE;
+    const char* a = reinterpret_cast<const char*>(enc_out) + static_cast<size_t>(dec_src[j]) * Bc * D * ab;
+    M3PC_TRY(gemm(e, a, e->dec_w[k], e->dec_w16[k], e->X.as<float>() + static_cast<size_t>(j) * Bc * D, len * Bc, D, D, ge, st));
+    j += len;
+  }
+  const int Sd = 4 * T, rows_d = Sd * Bc;
+  LnParams ln{};
+  ln.x = e->X.as<float>();
+  ln.rows = rows_d;
+  ln.rows_per_group = 1;
+  if (e->Ld > 0) {
+    ln.g1 = e->dec.layers[0].n1_w;
+    ln.b1 = e->dec.layers[0].n1_b;
+    ln.y1 = e->Y.p;
+    M3PC_TRY(launch_layernorm(ln, D, e->bf16, st));
+  }
+  // ---- decoder stack (mtm_model.py:397-409, 701-705) ----
+  for (int l = 0; l < e->Ld; ++l) {
+    M3PC_TRY(block(e, e->dec.layers[l], Bc, Sd, st));
+    if (l + 1 < e->Ld) {
+      ln.g1 = e->dec.layers[l + 1].n1_w;
+      ln.b1 = e->dec.layers[l + 1].n1_b;
+      ln.y1 = e->Y.p;
+      ln.y2 = nullptr;
+      M3PC_TRY(launch_layernorm(ln, D, e->bf16, st));
+    }
+  }
+  // final decoder norm (-> Y) chained with each head's own LayerNorm (-> Y2), mtm_model.py:428-433
+  ln.g1 = e->dec.norm_w;
+  ln.b1 = e->dec.norm_b;
+  ln.y1 = e->Y.p;
+  ln.y2 = e->Y2.p;
+  ln.rows_per_group = T * Bc;
+  for (int k = 0; k < 4; ++k) {
+    ln.g2[k] = e->head_ln_w[k];  // null for actions
+    ln.b2[k] = e->head_ln_b[k];
+  }
+  M3PC_TRY(launch_layernorm(ln, D, e->bf16, st));
+
+  // ---- K5: heads ----
+  float* outs[4] = {io.out_states, nullptr, io.out_rewards, io.out_returns};
+  for (int k = 0; k < 4; ++k) {
+    if (k == M3PC_ACTIONS || outs[k] == nullptr) continue;
+    const int d = e->dims[k];
+    GemmEpilogue ge;
+    ge.bias = e->head_b1[k];
+    ge.flags = EPI_GELU;
+    const char* a = reinterpret_cast<const char*>(e->Y2.p) + static_cast<size_t>(k) * T * Bc * D * ab;
+    M3PC_TRY(gemm(e, a, e->head_w1[k], e->head_w1_16[k], e->HID.p, T * Bc, D, D, ge, st));
+    RowDotParams rp{};
+    rp.y = e->HID.p;
+    rp.B = Bc; rp.tok0 = 0; rp.n_t = T; rp.t_out0 = 0; rp.T_out = T; rp.d_out = d;
+    rp.w = e->head_w3[k];
+    rp.b = e->head_b3[k];
+    rp.out = outs[k] + static_cast<size_t>(b0) * T * d;
+    M3PC_TRY(launch_rowdot(rp, D, e->bf16, st));
+  }
+  if (io.out_mu != nullptr) {
+    RowDotParams rp{};
+    rp.y = e->Y.p;
+    rp.B = Bc; rp.tok0 = M3PC_ACTIONS * T; rp.n_t = T; rp.t_out0 = 0; rp.T_out = T; rp.d_out = e->act;
+    rp.w = e->mu_w; rp.b = e->mu_b;
+    rp.out = io.out_mu + static_cast<size_t>(b0) * T * e->act;
+    rp.w2 = e->ls_w; rp.b2 = e->ls_b;
+    rp.out2 = io.out_std + static_cast<size_t>(b0) * T * e->act;
+    M3PC_TRY(launch_rowdot(rp, D, e->bf16, st));
+  }
+  return M3PC_OK;
+}
+
+int forward(m3pc_engine* e, const FwdIO& io, int B, cudaStream_t st) {
+  M3PC_REQUIRE(e->finalized, "forward before m3pc_finalize_params");
+  M3PC_REQUIRE(B >= 1 && B <= e->cfg.max_batch, "batch exceeds cfg.max_batch");
+  M3PC_REQUIRE((io.out_mu == nullptr) == (io.out_std == nullptr), "out_act_mu and out_act_std go together");
+  for (int b0 = 0; b0 < B; b0 += e->chunk) M3PC_TRY(forward_chunk(e, io, b0, std::min(e->chunk, B - b0), st));
+  return M3PC_OK;
+}
+
+int critic(m3pc_engine* e, int N, int h, cudaStream_t st) {
+  const int rows = N * h, in = e->obs + e->act, Hq = e->QH;
+  CriticInParams ci{};
+  ci.states_pred = e->pred_states.as<float>();
+  ci.cand = e->cand.as<float>();
+  ci.tok_mean = e->tok_mean[M3PC_STATES];
+  ci.tok_std = e->tok_std[M3PC_STATES];
+  ci.obs_mean = e->obs_mean;
+  ci.obs_std = e->obs_std;
+  ci.sa = e->sa.as<float>();
+  ci.N = N; ci.h = h; ci.T = e->T; ci.obs = e->obs; ci.A = e->act;
+  M3PC_TRY(launch_critic_input(ci, st));
+  float* outs[2] = {e->qb1.as<float>(), e->qb2.as<float>()};
+  for (int q = 0; q < 2; ++q) {
+    GemmEpilogue ge;
+    ge.bias = e->q_b[q][0];
+    ge.flags = EPI_RELU;
+    M3PC_TRY(gemm_fp32(e->sa.as<float>(), e->q_w[q][0], e->qa.as<float>(), rows, Hq, in, ge, st));
+    ge.bias = e->q_b[q][1];
+    M3PC_TRY(gemm_fp32(e->qa.as<float>(), e->q_w[q][1], outs[q], rows, Hq, Hq, ge, st));
+  }
+  return launch_critic_out(outs[0], outs[1], e->q_w[0][2], e->q_b[0][2], e->q_w[1][2], e->q_b[1][2], e->qvals.as<float>(), rows, Hq, st);
+}
+
+void set_window_sources(m3pc_engine* e, FwdIO& io, const float* ws, const float* wa, const float* wr, const float* wrt, long stride_mul) {
+  const int T = e->T;
+  io.src[M3PC_STATES] = ModSrc{ws, stride_mul * T * e->obs, true};
+  io.src[M3PC_ACTIONS] = ModSrc{wa, stride_mul * T * e->act, false};
+  io.src[M3PC_REWARDS] = ModSrc{wr, stride_mul * T, true};
+  io.src[M3PC_RETURNS] = ModSrc{wrt, stride_mul * T, false};
+}
+
+int plan(m3pc_engine* e, const m3pc_plan_args_t* a, cudaStream_t st) {
+  M3PC_REQUIRE(e->finalized, "plan before m3pc_finalize_params");
+  const int T = e->T, h = a->horizon, N = a->n_cand, A = e->act, idx = T - h;
+  M3PC_REQUIRE(h >= 1 && h <= T, "horizon must be in [1, traj_length]");
+  M3PC_REQUIRE(a->guidance >= 0 && a->guidance <= 3, "unknown guidance");
+  M3PC_REQUIRE(a->win_states && a->win_actions && a->win_rewards && a->win_returns_tok, "window pointers must be set");
+  M3PC_REQUIRE(a->out_eval_action && a->out_sample_action, "output pointers must be set");
+  const bool needs_critic = a->guidance == M3PC_GUIDE_CRITIC || a->guidance == M3PC_GUIDE_NOISE_CRITIC;
+  M3PC_REQUIRE(!needs_critic || e->has_critic, "critic guidance requested but no critic parameters were loaded");
+  if (a->guidance != M3PC_GUIDE_SAMPLING) M3PC_REQUIRE(N >= 1 && N <= e->cfg.max_batch, "n_cand exceeds cfg.max_batch");
+
+  // ---- pass 1: B = 1, rcbc mask (finetune_omtm/masks.py:7-27) -> action distribution ----
+  FwdIO io{};
+  set_window_sources(e, io, a->win_states, a->win_actions, a->win_rewards, a->win_returns_tok, 0);
+  for (int t = 0; t < T; ++t) {
+    io.mask[M3PC_STATES * T + t] = t <= idx;
+    io.mask[M3PC_ACTIONS * T + t] = t < idx;
+    io.mask[M3PC_REWARDS * T + t] = 0;
+    io.mask[M3PC_RETURNS * T + t] = 1;
+  }
+  io.out_mu = e->p1_mu.as<float>();
+  io.out_std = e->p1_std.as<float>();
+  M3PC_TRY(forward(e, io, 1, st));
+  if (a->guidance == M3PC_GUIDE_SAMPLING)
+    return launch_sampling_tail(io.out_mu, io.out_std, a->eps, T, h, A, 1, a->out_eval_action, a->out_sample_action, a->seed, st);
+
+  // ---- K6: candidates ----
+  CandParams cp{};
+  cp.mu = io.out_mu; cp.std = io.out_std; cp.eps = a->eps; cp.cand = e->cand.as<float>();
+  cp.N = N; cp.h = h; cp.A = A; cp.T = T;
+  cp.noise_mode = a->guidance == M3PC_GUIDE_NOISE_CRITIC ? 1 : 0;
+  cp.seed = a->seed; cp.cand_offset = a->cand_offset;
+  M3PC_TRY(launch_candidates(cp, st));
+  if (a->dbg_candidates)
+    M3PC_CHECK_CUDA(cudaMemcpyAsync(a->dbg_candidates, cp.cand, sizeof(float) * N * h * A, cudaMemcpyDeviceToDevice, st));
+
+  // ---- pass 2: B = N, fd mask (finetune_omtm/masks.py:30-44); history shared, planned actions per candidate ----
+  FwdIO io2{};
+  set_window_sources(e, io2, a->win_states, a->win_actions, a->win_rewards, a->win_returns_tok, 0);
+  io2.src[M3PC_ACTIONS].base2 = cp.cand;
+  io2.src[M3PC_ACTIONS].bstride2 = static_cast<long>(h) * A;
+  io2.src[M3PC_ACTIONS].t_split = idx;
+  for (int t = 0; t < T; ++t) {
+    io2.mask[M3PC_STATES * T + t] = t <= idx;
+    io2.mask[M3PC_ACTIONS * T + t] = 1;
+    io2.mask[M3PC_REWARDS * T + t] = 0;
+    io2.mask[M3PC_RETURNS * T + t] = 0;
+  }
+  io2.out_rewards = e->pred_rewards.as<float>();
+  if (needs_critic)
+    io2.out_states = e->pred_states.as<float>();
+  else
+    io2.out_returns = e->pred_returns.as<float>();
+  M3PC_TRY(forward(e, io2, N, st));
+
+  // ---- K7 + K8 ----
+  if (needs_critic) M3PC_TRY(critic(e, N, h, st));
+  ScoreParams sp{};
+  sp.rewards_pred = io2.out_rewards;
+  sp.returns_pred = needs_critic ? nullptr : io2.out_returns;
+  sp.qvals = needs_critic ? e->qvals.as<float>() : nullptr;
+  sp.rw_mean = e->h_tok_mean[M3PC_REWARDS]; sp.rw_std = e->h_tok_std[M3PC_REWARDS];
+  sp.rt_mean = e->h_tok_mean[M3PC_RETURNS]; sp.rt_std = e->h_tok_std[M3PC_RETURNS];
+  sp.discount = a->discount; sp.lmbda = a->lmbda;
+  sp.N = N; sp.h = h; sp.T = T;
+  sp.J = e->J.as<float>();
+  M3PC_TRY(launch_score(sp, st));
+  if (a->dbg_expect_return) M3PC_CHECK_CUDA(cudaMemcpyAsync(a->dbg_expect_return, sp.J, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+  SelectParams sl{};
+  sl.J = sp.J; sl.cand = cp.cand; sl.expq = a->expq;
+  sl.N = N; sl.h = h; sl.A = A;
+  sl.temperature = a->temperature; sl.seed = a->seed; sl.cand_offset = a->cand_offset;
+  sl.eval_action = a->out_eval_action; sl.sample_action = a->out_sample_action;
+  sl.partials = a->out_partials; sl.indices = a->dbg_indices;
+  return launch_select(sl, st);
+}
+
+int backward_plan(m3pc_engine* e, int mode, int E, int h, const float* ws, const float* wa, const float* wr, const float* wrt,
+                  const float* eps, float* out_eval, float* out_sample, float* dbg_filled, cudaStream_t st) {
+  M3PC_REQUIRE(e->finalized, "backward_plan before m3pc_finalize_params");
+  const int T = e->T, idx = T - h, A = e->act;
+  M3PC_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (id) or 1 (piid)");
+  M3PC_REQUIRE(h >= 1 && h <= T && E >= 1 && E <= e->cfg.max_batch, "bad horizon / n_env");
+  FwdIO io{};
+  set_window_sources(e, io, ws, wa, wr, wrt, 1);
+  // gid == pi mask (zeroshot_omtm/masks.py:50-91): all states except (idx+1 .. T-2) when idx > 0; actions < idx
+  for (int t = 0; t < T; ++t) {
+    io.mask[M3PC_STATES * T + t] = !(idx > 0 && t >= idx + 1 && t < T - 1);
+    io.mask[M3PC_ACTIONS * T + t] = t < idx;
+    io.mask[M3PC_REWARDS * T + t] = 0;
+    io.mask[M3PC_RETURNS * T + t] = 0;
+  }
+  if (mode == 0) {
+    io.out_mu = e->e_mu.as<float>();
+    io.out_std = e->e_std.as<float>();
+    M3PC_TRY(forward(e, io, E, st));
+  } else {
+    io.out_states = e->pred_states.as<float>();
+    M3PC_TRY(forward(e, io, E, st));
+    M3PC_TRY(launch_piid_fill(ws, io.out_states, e->tok_mean[M3PC_STATES], e->tok_std[M3PC_STATES], e->filled.as<float>(), E, T, h, e->obs, st));
+    if (dbg_filled)
+      M3PC_CHECK_CUDA(cudaMemcpyAsync(dbg_filled, e->filled.p, sizeof(float) * E * T * e->obs, cudaMemcpyDeviceToDevice, st));
+    FwdIO io2{};
+    set_window_sources(e, io2, e->filled.as<float>(), wa, wr, wrt, 1);
+    // fid mask (zeroshot_omtm/masks.py:30-47): all states, actions < idx
+    for (int t = 0; t < T; ++t) {
+      io2.mask[M3PC_STATES * T + t] = 1;
+      io2.mask[M3PC_ACTIONS * T + t] = t < idx;
+    }
+    io2.out_mu = e->e_mu.as<float>();
+    io2.out_std = e->e_std.as<float>();
+    M3PC_TRY(forward(e, io2, E, st));
+  }
+  return launch_sampling_tail(e->e_mu.as<float>(), e->e_std.as<float>(), eps, T, h, A, E, out_eval, out_sample, 0ull, st);
+}
+
+int create(m3pc_handle_t* out, const m3pc_config_t* cfg) {
+  M3PC_REQUIRE(out != nullptr && cfg != nullptr, "null argument");
+  M3PC_REQUIRE(cfg->n_embd > 0 && cfg->n_embd % 128 == 0 && cfg->n_embd <= 1024, "n_embd must be a multiple of 128, <= 1024");
+  M3PC_REQUIRE(cfg->n_head * 128 == cfg->n_embd, "head_dim must be 128 (n_head == n_embd / 128)");
+  M3PC_REQUIRE(cfg->traj_length >= 1 && cfg->traj_length <= M3PC_MAX_T, "traj_length out of range");
+  M3PC_REQUIRE(cfg->obs_dim >= 1 && cfg->obs_dim <= M3PC_MAX_OBS && cfg->act_dim >= 1 && cfg->act_dim <= M3PC_MAX_ACT, "obs/act dim out of range");
+  M3PC_REQUIRE(cfg->n_enc_layer >= 1 && cfg->n_dec_layer >= 1, "need at least one encoder and one decoder layer");
+  M3PC_REQUIRE(cfg->precision == M3PC_PREC_BF16 || cfg->precision == M3PC_PREC_FP32, "unknown precision");
+  M3PC_REQUIRE(cfg->max_batch >= 1, "max_batch must be positive");
+  int dev = 0;
+  M3PC_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  M3PC_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_error(std::string("this library is built for sm_100a only; device is ") + prop.name + " (sm_" + std::to_string(prop.major) +
+              std::to_string(prop.minor) + ")");
+    return M3PC_ERR_CUDA;
+  }
+  std::unique_ptr<m3pc_engine> e(new m3pc_engine());
+  e->cfg = *cfg;
+  e->D = cfg->n_embd; e->H = cfg->n_head; e->T = cfg->traj_length; e->F = 4 * cfg->n_embd;
+  e->obs = cfg->obs_dim; e->act = cfg->act_dim; e->Le = cfg->n_enc_layer; e->Ld = cfg->n_dec_layer; e->QH = cfg->critic_hidden;
+  e->dims[0] = e->obs; e->dims[1] = e->act; e->dims[2] = 1; e->dims[3] = 1;
+  e->bf16 = cfg->precision == M3PC_PREC_BF16;
+  e->chunk = cfg->chunk > 0 ? cfg->chunk : 1024;
+  e->chunk = std::min(e->chunk, cfg->max_batch);
+  if (e->bf16) M3PC_TRY(gemm_init_driver_api());
+  const size_t rows = static_cast<size_t>(4) * e->T * e->chunk + 128;  // +128: slack rows for tile tails
+  const size_t ab = act_bytes(e.get()), D = e->D;
+  M3PC_TRY(e->X.alloc(rows * D * 4));
+  M3PC_TRY(e->Y.alloc(rows * D * ab));
+  M3PC_TRY(e->Y2.alloc(rows * D * ab));
+  M3PC_TRY(e->QKV.alloc(rows * 3 * D * ab));
+  M3PC_TRY(e->ATT.alloc(rows * D * ab));
+  M3PC_TRY(e->HID.alloc(rows * 4 * D * ab));
+  M3PC_TRY(e->ENC.alloc(rows * D * ab));
+  for (DevBuf* b : {&e->X, &e->Y, &e->Y2, &e->QKV, &e->ATT, &e->HID, &e->ENC}) M3PC_CHECK_CUDA(cudaMemset(b->p, 0, b->bytes));
+  const size_t N = cfg->max_batch, T = e->T;
+  M3PC_TRY(e->p1_mu.alloc(T * e->act * 4));
+  M3PC_TRY(e->p1_std.alloc(T * e->act * 4));
+  M3PC_TRY(e->cand.alloc(N * T * e->act * 4));
+  M3PC_TRY(e->pred_states.alloc(N * T * e->obs * 4));
+  M3PC_TRY(e->pred_rewards.alloc(N * T * 4));
+  M3PC_TRY(e->pred_returns.alloc(N * T * 4));
+  M3PC_TRY(e->J.alloc(N * 4));
+  M3PC_TRY(e->filled.alloc(N * T * e->obs * 4));
+  M3PC_TRY(e->e_mu.alloc(N * T * e->act * 4));
+  M3PC_TRY(e->e_std.alloc(N * T * e->act * 4));
+  if (e->QH > 0) {
+    M3PC_TRY(e->sa.alloc(N * T * (e->obs + e->act) * 4));
+    M3PC_TRY(e->qa.alloc(N * T * e->QH * 4));
+    M3PC_TRY(e->qb1.alloc(N * T * e->QH * 4));
+    M3PC_TRY(e->qb2.alloc(N * T * e->QH * 4));
+    M3PC_TRY(e->qvals.alloc(N * T * 4));
+  }
+  M3PC_CHECK_CUDA(cudaEventCreate(&e->ev0));
+  M3PC_CHECK_CUDA(cudaEventCreate(&e->ev1));
+  M3PC_CHECK_CUDA(cudaDeviceSynchronize());
+  *out = e.release();
+  return M3PC_OK;
+}
+
+template <typename Fn>
+int timed(m3pc_engine* e, cudaStream_t st, Fn&& fn) {
+  g_launch_count = 0;
+  M3PC_CHECK_CUDA(cudaEventRecord(e->ev0, st));
+  const int rc = fn();
+  e->last_launches = g_launch_count;
+  if (rc != M3PC_OK) return rc;
+  M3PC_CHECK_CUDA(cudaEventRecord(e->ev1, st));
+  return M3PC_OK;
+}
+
+}  // namespace
+}  // namespace m3pc
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* m3pc_last_error(void) { return m3pc::g_error.c_str(); }
+const char* m3pc_version(void) { return "m3pc-b200 0.1.0 (sm_100a)"; }
+
+int m3pc_create(m3pc_handle_t* out, const m3pc_config_t* cfg) { return m3pc::create(out, cfg); }
+
+int m3pc_destroy(m3pc_handle_t h) {
+  if (h == nullptr) return M3PC_OK;
+  cudaDeviceSynchronize();
+  delete h;
+  return M3PC_OK;
+}
+
+int m3pc_set_param(m3pc_handle_t h, const char* name, const float* data, size_t count) {
+  M3PC_REQUIRE(h != nullptr && name != nullptr && data != nullptr, "null argument");
+  h->finalized = false;
+  h->staged[name].assign(data, data + count);
+  return M3PC_OK;
+}
+
+int m3pc_finalize_params(m3pc_handle_t h) {
+  M3PC_REQUIRE(h != nullptr, "null handle");
+  return m3pc::finalize(h);
+}
+
+int m3pc_forward(m3pc_handle_t h, int32_t batch, const float* tok_states, const float* tok_actions, const float* tok_rewards,
+                 const float* tok_returns, const uint8_t* masks, float* out_states, float* out_act_mu, float* out_act_std,
+                 float* out_rewards, float* out_returns, void* stream) {
+  M3PC_REQUIRE(h != nullptr && masks != nullptr, "null argument");
+  M3PC_REQUIRE(tok_states && tok_actions && tok_rewards && tok_returns, "all four modalities must be given");
+  m3pc::FwdIO io{};
+  const int T = h->T;
+  io.src[M3PC_STATES] = m3pc::ModSrc{tok_states, static_cast<long>(T) * h->obs, false};
+  io.src[M3PC_ACTIONS] = m3pc::ModSrc{tok_actions, static_cast<long>(T) * h->act, false};
+  io.src[M3PC_REWARDS] = m3pc::ModSrc{tok_rewards, static_cast<long>(T), false};
+  io.src[M3PC_RETURNS] = m3pc::ModSrc{tok_returns, static_cast<long>(T), false};
+  for (int i = 0; i < 4 * T; ++i) {
+    M3PC_REQUIRE(masks[i] <= 1, "mask entries must be 0 or 1");
+    io.mask[i] = masks[i];
+  }
+  io.out_states = out_states; io.out_mu = out_act_mu; io.out_std = out_act_std;
+  io.out_rewards = out_rewards; io.out_returns = out_returns;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return m3pc::timed(h, st, [&] { return m3pc::forward(h, io, batch, st); });
+}
+
+int m3pc_plan(m3pc_handle_t h, const m3pc_plan_args_t* args, void* stream) {
+  M3PC_REQUIRE(h != nullptr && args != nullptr, "null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return m3pc::timed(h, st, [&] { return m3pc::plan(h, args, st); });
+}
+
+int m3pc_merge_partials(m3pc_handle_t h, const float* partials, int32_t n_shards, float temperature, float* out_eval_action,
+                        float* out_sample_action, int32_t* out_indices, void* stream) {
+  M3PC_REQUIRE(h != nullptr && partials && out_eval_action && out_sample_action && n_shards >= 1, "bad argument");
+  return m3pc::launch_merge(partials, n_shards, h->act, temperature, out_eval_action, out_sample_action, out_indices,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+
+int m3pc_backward_plan(m3pc_handle_t h, int32_t mode, int32_t n_env, int32_t horizon, const float* win_states, const float* win_actions,
+                       const float* win_rewards, const float* win_returns_tok, const float* eps, float* out_eval_action,
+                       float* out_sample_action, float* dbg_states_filled, void* stream) {
+  M3PC_REQUIRE(h != nullptr && win_states && win_actions && win_rewards && win_returns_tok && out_eval_action && out_sample_action,
+               "null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return m3pc::timed(h, st, [&] {
+    return m3pc::backward_plan(h, mode, n_env, horizon, win_states, win_actions, win_rewards, win_returns_tok, eps, out_eval_action,
+                               out_sample_action, dbg_states_filled, st);
+  });
+}
+
+int m3pc_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int32_t M, int32_t N, int32_t K, int32_t flags, void* stream) {
+  M3PC_REQUIRE(A && W && C, "null argument");
+  M3PC_REQUIRE((flags & ~7) == 0, "unknown flag");
+  m3pc::GemmEpilogue ep;
+  ep.bias = bias;
+  ep.flags = flags;
+  return m3pc::gemm_bf16_tcgen05(reinterpret_cast<const __nv_bfloat16*>(A), reinterpret_cast<const __nv_bfloat16*>(W), C, M, N, K, ep,
+                                 reinterpret_cast<cudaStream_t>(stream));
+}
+
+int m3pc_gemm_fp32(const float* A, const float* W, const float* bias, float* C, int32_t M, int32_t N, int32_t K, int32_t flags, void* stream) {
+  M3PC_REQUIRE(A && W && C, "null argument");
+  M3PC_REQUIRE((flags & ~7) == 0, "unknown flag");
+  m3pc::GemmEpilogue ep;
+  ep.bias = bias;
+  ep.flags = flags;
+  return m3pc::gemm_fp32(A, W, C, M, N, K, ep, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int m3pc_layernorm(const float* x, const float* gamma, const float* beta, void* y, int32_t M, int32_t D, int32_t out_bf16, void* stream) {
+  M3PC_REQUIRE(x && gamma && beta && y, "null argument");
+  m3pc::LnParams p{};
+  p.x = x; p.rows = M; p.g1 = gamma; p.b1 = beta; p.y1 = y; p.rows_per_group = 1;
+  return m3pc::launch_layernorm(p, D, out_bf16 != 0, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int m3pc_attention(const void* qkv, void* out, int32_t B, int32_t S, int32_t n_head, int32_t is_bf16, void* stream) {
+  M3PC_REQUIRE(qkv && out, "null argument");
+  return m3pc::launch_attention(qkv, out, B, S, n_head, is_bf16 != 0, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int m3pc_last_device_ms(m3pc_handle_t h, float* ms) {
+  M3PC_REQUIRE(h != nullptr && ms != nullptr, "null argument");
+  M3PC_CHECK_CUDA(cudaEventSynchronize(h->ev1));
+  M3PC_CHECK_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return M3PC_OK;
+}
+
+int m3pc_last_launch_count(m3pc_handle_t h, int32_t* n) {
+  M3PC_REQUIRE(h != nullptr && n != nullptr, "null argument");
+  *n = h->last_launches;
+  return M3PC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,137 @@
+// Launcher declarations for the memory-bound fused kernels of the MTM forward and the M^3PC candidate loop.
+#pragma once
+#include "common.cuh"
+
+namespace m3pc {
+
+constexpr int MAX_TOK = 64;  // 4 * traj_length, traj_length <= 16
+constexpr int LN_EPS_BITS = 0x3727c5ac;  // 1e-5f
+
+// ---- K1: tokenise + embed + positional/per-dim + unmasked gather (+ LayerNorm of the first block) -------
+struct EmbedTok {
+  const float* src;    // first element of this token's feature vector for batch row 0
+  const float* wt;     // W_enc^T of the token's modality, (d, D) row-major
+  const float* cvec;   // (D): bias + per-dim encoding + pos[t]
+  const float* nmean;  // (d) tokenizer mean or nullptr (already tokenised / un-normalised modality)
+  const float* nstd;   // (d)
+  int bstride;         // floats between consecutive batch rows (0 = shared by all rows)
+  int d;               // feature dim
+};
+struct EmbedParams {
+  EmbedTok tok[MAX_TOK];
+  int n_tok;
+  int B;
+};
+// x (n_tok*B, D) fp32 residual stream, y (n_tok*B, D) = LayerNorm(x; gamma, beta) in AT.
+int launch_embed(const EmbedParams& p, int D, float* x, void* y, bool y_bf16, const float* gamma, const float* beta, cudaStream_t st);
+
+// ---- LayerNorm family ---------------------------------------------------------------------------------
+// y1 = LN(x; g1, b1) (optional), y2 = LN(y1; g2[grp], b2[grp]) (optional, grp = row / rows_per_group, skipped where g2[grp]==0)
+struct LnParams {
+  const float* x;
+  int rows;
+  const float* g1;
+  const float* b1;
+  void* y1;  // may be null
+  const float* g2[4];
+  const float* b2[4];
+  int rows_per_group;
+  void* y2;  // may be null
+};
+int launch_layernorm(const LnParams& p, int D, bool out_bf16, cudaStream_t st);
+
+// ---- K4 helper: broadcast batch-constant decoder rows (mask tokens after decoder embedding) ------------
+struct FillParams {
+  const float* row[MAX_TOK];  // (D) constant row for each listed decoder token
+  int tok[MAX_TOK];           // decoder token index j (row block j*B .. j*B+B)
+  int n;
+  int B;
+};
+int launch_fill_rows(const FillParams& p, int D, float* x, cudaStream_t st);
+
+// ---- K5: skinny output projections (512 -> d) ----------------------------------------------------------
+// out[b, t, o] = dot(Y[(tok0 + t) * B + b, :], W[o, :]) + bias[o]     for t < n_t, o < d_out  (out is (B, T_out, d_out), t written at t + t_out0)
+// actor mode: second weight set gives std = exp(-5 + 3.5 (tanh(.) + 1))   (DiagGaussianActor, mtm_model.py:313-321)
+struct RowDotParams {
+  const void* y;   // (rows, D) AT
+  int B, tok0, n_t, t_out0, T_out, d_out;
+  const float* w;   // (d_out, D)
+  const float* b;   // (d_out)
+  float* out;       // (B, T_out, d_out)
+  const float* w2;  // actor log_std weights or null
+  const float* b2;
+  float* out2;      // std
+};
+int launch_rowdot(const RowDotParams& p, int D, bool y_bf16, cudaStream_t st);
+
+// ---- K3: small-sequence bidirectional attention ----------------------------------------------------------
+int launch_attention(const void* qkv, void* out, int B, int S, int n_head, bool bf16, cudaStream_t st);
+
+// ---- K6..K8: the candidate loop ---------------------------------------------------------------------------
+struct CandParams {
+  const float* mu;   // (T, A) action-head mu of pass 1 (B = 1)
+  const float* std;  // (T, A)
+  const float* eps;  // (N, h, A) injected noise or null (Philox)
+  float* cand;       // (N, h, A)
+  int N, h, A, T;
+  int noise_mode;    // 0: tanh(mu + std*eps) (learner.py:285-287); 1: clamp(tanh(mu) + 0.09*eps) (learner.py:156-167)
+  unsigned long long seed;
+  int cand_offset;
+};
+int launch_candidates(const CandParams& p, cudaStream_t st);
+
+struct CriticInParams {
+  const float* states_pred;  // (N, T, obs) raw head output (tokenised space)
+  const float* cand;         // (N, h, A)
+  const float* tok_mean;     // (obs) tokenizer stats of states
+  const float* tok_std;
+  const float* obs_mean;     // (obs) critic normaliser
+  const float* obs_std;
+  float* sa;                 // (N*h, obs+A), row = n*h + t
+  int N, h, T, obs, A;
+};
+int launch_critic_input(const CriticInParams& p, cudaStream_t st);
+// q = min(h1 . w1 + b1, h2 . w2 + b2) per row; h1, h2 (rows, H) fp32
+int launch_critic_out(const float* h1, const float* h2, const float* w1, const float* b1, const float* w2, const float* b2, float* q,
+                      int rows, int H, cudaStream_t st);
+
+struct ScoreParams {
+  const float* rewards_pred;  // (N, T) raw head output
+  const float* returns_pred;  // (N, T) raw head output (rtg_guiding) or null
+  const float* qvals;         // (N*h) critic values or null
+  float rw_mean, rw_std, rt_mean, rt_std;
+  float discount, lmbda;
+  int N, h, T;
+  float* J;  // (N)
+};
+int launch_score(const ScoreParams& p, cudaStream_t st);
+
+struct SelectParams {
+  const float* J;     // (N)
+  const float* cand;  // (N, h, A): a0 = cand[n, 0, :]
+  const float* expq;  // (N) or null
+  int N, h, A;
+  float temperature;
+  unsigned long long seed;
+  int cand_offset;
+  float* eval_action;    // (A)
+  float* sample_action;  // (A)
+  float* partials;       // (M3PC_PARTIAL_FLOATS) or null
+  int* indices;          // (2) or null
+};
+int launch_select(const SelectParams& p, cudaStream_t st);
+int launch_merge(const float* partials, int n_shards, int A, float temperature, float* eval_action, float* sample_action, int* indices,
+                 cudaStream_t st);
+
+// mtm_sampling tail (learner.py:103-115): eval = tanh(mu[T-h]), sample = tanh(mu[T-h] + std[T-h]*eps)
+int launch_sampling_tail(const float* mu, const float* std, const float* eps, int T, int h, int A, int E, float* eval_action,
+                         float* sample_action, unsigned long long seed, cudaStream_t st);
+
+// zero-shot piid fill (zeroshot_omtm/learner.py:240-246): states[:, T-h+2:-1] and states[:, :T-h+1] <- decode(pred)
+int launch_piid_fill(const float* win_states, const float* states_pred, const float* tok_mean, const float* tok_std, float* filled, int E,
+                     int T, int h, int obs, cudaStream_t st);
+
+// conversions
+int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t st);
+
+}  // namespace m3pc

@@ -1,0 +1,326 @@
+// K6..K8: the M^3PC candidate loop, kept on the device (no host round-trip inside a plan).
+//
+//   candidates_kernel   K6  sample N action sequences from the pass-1 tanh-Gaussian (learner.py:285-287) or add fixed
+//                           variance noise to its mean (learner.py:156-167); injected noise for parity, Philox otherwise.
+//   critic_input_kernel K7  decode predicted states, normalise for the critic, concatenate the action (model.py:163-168).
+//   critic_out_kernel   K7  last TwinQ layer + min(q1, q2) (model.py:170-171).
+//   score_kernel        K8  TD(lambda) return per candidate, written as the reference's loop (learner.py:301-316).
+//   select_kernel       K8  softmax over candidates, weighted-mean action, exponential-race sample == torch.multinomial
+//                           (learner.py:318-325); emits the per-shard record merged by merge_kernel under sharding.
+#include "kernels.cuh"
+
+namespace m3pc {
+namespace {
+
+// ---- Philox4x32-10 (counter-based: results do not depend on how candidates are sharded) -------------------
+struct U4 { unsigned x, y, z, w; };
+__device__ __forceinline__ U4 philox4x32(U4 c, unsigned k0, unsigned k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = U4{hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0};
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ float u01(unsigned u) { return (static_cast<float>(u >> 8) + 0.5f) * (1.0f / 16777216.0f); }  // (0,1)
+__device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned gid, unsigned elem, unsigned stream) {
+  const U4 r = philox4x32(U4{gid, elem >> 1, stream, 0u}, static_cast<unsigned>(seed), static_cast<unsigned>(seed >> 32));
+  const float rad = sqrtf(-2.0f * logf(u01(r.x)));
+  const float ang = 6.283185307179586f * u01(r.y);
+  return (elem & 1) ? rad * sinf(ang) : rad * cosf(ang);
+}
+__device__ __forceinline__ float philox_exp(unsigned long long seed, unsigned gid, unsigned stream) {
+  const U4 r = philox4x32(U4{gid, 0u, stream, 1u}, static_cast<unsigned>(seed), static_cast<unsigned>(seed >> 32));
+  return -logf(u01(r.x));
+}
+
+__global__ void candidates_kernel(const __grid_constant__ CandParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = p.h * p.A;
+  if (i >= p.N * per) return;
+  const int n = i / per, e = i - n * per, j = e / p.A, a = e - j * p.A;
+  const float eps = p.eps ? p.eps[i] : philox_normal(p.seed, static_cast<unsigned>(p.cand_offset + n), static_cast<unsigned>(e), 0u);
+  const int t = p.T - p.h + j;
+  const float mu = p.mu[t * p.A + a];
+  float v;
+  if (p.noise_mode == 0) {
+    v = tanhf(__fadd_rn(mu, __fmul_rn(p.std[t * p.A + a], eps)));
+  } else {
+    v = __fadd_rn(tanhf(mu), __fmul_rn(eps, 0.09f));
+    v = fminf(fmaxf(v, -0.99999f), 0.99999f);
+  }
+  p.cand[i] = v;
+}
+
+__global__ void critic_input_kernel(const __grid_constant__ CriticInParams p) {
+  const int w = p.obs + p.A;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.N * p.h * w) return;
+  const int row = i / w, c = i - row * w;
+  const int n = row / p.h, t = row - n * p.h;
+  float v;
+  if (c < p.obs) {
+    const float y = p.states_pred[(static_cast<size_t>(n) * p.T + (p.T - p.h + t)) * p.obs + c];
+    const float s = __fadd_rn(__fmul_rn(y, p.tok_std[c]), p.tok_mean[c]);  // tokenizer decode, continuous.py:90-92
+    v = (s - p.obs_mean[c]) / p.obs_std[c];                                 // TwinQ.both, model.py:166
+  } else {
+    v = p.cand[(static_cast<size_t>(n) * p.h + t) * p.A + (c - p.obs)];
+  }
+  p.sa[i] = v;
+}
+
+__global__ void critic_out_kernel(const float* __restrict__ h1, const float* __restrict__ h2, const float* __restrict__ w1,
+                                  const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                                  float* __restrict__ q, int rows, int H) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = lane; c < H; c += 32) {
+    s1 = fmaf(h1[static_cast<size_t>(row) * H + c], __ldg(w1 + c), s1);
+    s2 = fmaf(h2[static_cast<size_t>(row) * H + c], __ldg(w2 + c), s2);
+  }
+  s1 = warp_sum(s1) + __ldg(b1);
+  s2 = warp_sum(s2) + __ldg(b2);
+  if (lane == 0) q[row] = fminf(s1, s2);
+}
+
+__global__ void score_kernel(const __grid_constant__ ScoreParams p) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= p.N) return;
+  const int T = p.T, h = p.h;
+  float disc[M3PC_MAX_T], r[M3PC_MAX_T];
+  float d = 1.0f;
+  for (int i = 0; i < h; ++i) {  // torch.cumprod(discount * ones(t+1)) in fp32
+    d = __fmul_rn(d, p.discount);
+    disc[i] = d;
+    r[i] = __fadd_rn(__fmul_rn(p.rewards_pred[static_cast<size_t>(n) * T + (T - h + i)], p.rw_std), p.rw_mean);
+  }
+  const double lam = static_cast<double>(p.lmbda);
+  const float one_minus = static_cast<float>(1.0 - lam);
+  float J = 0.f;
+  double lam_t = 1.0;
+  for (int t = 0; t < h; ++t) {
+    float v;
+    if (p.qvals != nullptr) {
+      v = p.qvals[static_cast<size_t>(n) * h + t];
+    } else {
+      const float y = p.returns_pred[static_cast<size_t>(n) * T + (T - h + t)];
+      v = __fmul_rn(__fadd_rn(__fmul_rn(y, p.rt_std), p.rt_mean), 1000.0f);  // learner.py:305
+    }
+    float s = 0.f;
+    for (int j = 0; j < t; ++j) s = __fadd_rn(s, __fmul_rn(r[j], disc[j]));
+    s = __fadd_rn(s, __fmul_rn(v, disc[t]));
+    const float lt = static_cast<float>(lam_t);
+    if (t < h - 1)
+      J = __fadd_rn(J, __fmul_rn(__fmul_rn(s, one_minus), lt));
+    else
+      J = __fadd_rn(J, __fmul_rn(s, lt));
+    lam_t *= lam;
+  }
+  p.J[n] = J;
+}
+
+// ---- block reductions (1024 threads, deterministic order) ------------------------------------------------
+constexpr int SEL_THREADS = 1024;
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = (lane < SEL_THREADS / 32) ? red[lane] : 0.f;
+  t = warp_sum(t);
+  return t;  // every thread holds the total
+}
+// argmax with lowest-index tie break; returns value, index broadcast to all threads
+__device__ __forceinline__ void block_argmax(float& v, int& idx, float* redv, int* redi) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) { redv[warp] = v; redi[warp] = idx; }
+  __syncthreads();
+  v = (lane < SEL_THREADS / 32) ? redv[lane] : -INFINITY;
+  idx = (lane < SEL_THREADS / 32) ? redi[lane] : 0x7fffffff;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) select_kernel(const __grid_constant__ SelectParams p) {
+  __shared__ float redv[32];
+  __shared__ int redi[32];
+  const int tid = threadIdx.x;
+  const int stride_a0 = p.h * p.A;
+  // 1. max_n J_n (+ argmax)
+  float m = -INFINITY;
+  int mi = 0x7fffffff;
+  for (int n = tid; n < p.N; n += SEL_THREADS) {
+    const float j = p.J[n];
+    if (j > m) { m = j; mi = n; }
+  }
+  block_argmax(m, mi, redv, redi);
+  // 2. w_n = exp((J_n - m) * tau); Z = sum w_n; sample key = w_n / q_n  (== p_n / q_n up to the constant Z)
+  float z = 0.f, kbest = -INFINITY;
+  int ki = 0x7fffffff;
+  for (int n = tid; n < p.N; n += SEL_THREADS) {
+    const float w = expf(__fmul_rn(__fsub_rn(p.J[n], m), p.temperature));
+    z += w;
+    const float q = p.expq ? p.expq[n] : philox_exp(p.seed, static_cast<unsigned>(p.cand_offset + n), 1u);
+    const float key = w / q;
+    if (key > kbest) { kbest = key; ki = n; }
+  }
+  const float Z = block_sum(z, redv);
+  block_argmax(kbest, ki, redv, redi);
+  // 3. U[a] = sum w_n a0[n, a]
+  for (int a = 0; a < p.A; ++a) {
+    float u = 0.f;
+    for (int n = tid; n < p.N; n += SEL_THREADS) {
+      const float w = expf(__fmul_rn(__fsub_rn(p.J[n], m), p.temperature));
+      u = fmaf(w, p.cand[static_cast<size_t>(n) * stride_a0 + a], u);
+    }
+    const float U = block_sum(u, redv);
+    if (tid == 0) {
+      p.eval_action[a] = U / Z;
+      p.sample_action[a] = p.cand[static_cast<size_t>(ki) * stride_a0 + a];
+      if (p.partials) {
+        p.partials[8 + a] = U;
+        p.partials[8 + p.A + a] = p.cand[static_cast<size_t>(ki) * stride_a0 + a];
+      }
+    }
+  }
+  if (tid == 0) {
+    if (p.partials) {
+      p.partials[0] = m;
+      p.partials[1] = Z;
+      p.partials[2] = m;
+      p.partials[3] = __int_as_float(p.cand_offset + mi);
+      p.partials[4] = kbest;
+      p.partials[5] = __int_as_float(p.cand_offset + ki);
+      p.partials[6] = static_cast<float>(p.N);
+      p.partials[7] = 0.f;
+    }
+    if (p.indices) {
+      p.indices[0] = p.cand_offset + mi;
+      p.indices[1] = p.cand_offset + ki;
+    }
+  }
+}
+
+// log-sum-exp merge of per-shard records; one warp is plenty (n_shards <= 32... loop otherwise)
+__global__ void merge_kernel(const float* __restrict__ partials, int n_shards, int A, float temperature, float* eval_action,
+                             float* sample_action, int* indices) {
+  if (threadIdx.x != 0) return;
+  float m = -INFINITY;
+  for (int g = 0; g < n_shards; ++g) m = fmaxf(m, partials[g * M3PC_PARTIAL_FLOATS + 0]);
+  float Z = 0.f, kbest = -INFINITY, jbest = -INFINITY;
+  int kg = 0, ji = 0;
+  for (int g = 0; g < n_shards; ++g) {
+    const float* P = partials + g * M3PC_PARTIAL_FLOATS;
+    const float sc = expf((P[0] - m) * temperature);
+    Z += P[1] * sc;
+    const float key = P[4] * sc;
+    if (key > kbest) { kbest = key; kg = g; }
+    if (P[2] > jbest) { jbest = P[2]; ji = __float_as_int(P[3]); }
+  }
+  for (int a = 0; a < A; ++a) {
+    float U = 0.f;
+    for (int g = 0; g < n_shards; ++g) {
+      const float* P = partials + g * M3PC_PARTIAL_FLOATS;
+      U += P[8 + a] * expf((P[0] - m) * temperature);
+    }
+    eval_action[a] = U / Z;
+    sample_action[a] = partials[kg * M3PC_PARTIAL_FLOATS + 8 + A + a];
+  }
+  if (indices) {
+    indices[0] = ji;
+    indices[1] = __float_as_int(partials[kg * M3PC_PARTIAL_FLOATS + 5]);
+  }
+}
+
+__global__ void sampling_tail_kernel(const float* __restrict__ mu, const float* __restrict__ std, const float* __restrict__ eps, int T, int h,
+                                     int A, int E, float* eval_action, float* sample_action, unsigned long long seed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= E * A) return;
+  const int e = i / A, a = i - e * A;
+  const size_t src = (static_cast<size_t>(e) * T + (T - h)) * A + a;
+  const float m = mu[src];
+  const float z = eps ? eps[i] : philox_normal(seed, static_cast<unsigned>(e), static_cast<unsigned>(a), 2u);
+  eval_action[i] = tanhf(m);
+  sample_action[i] = tanhf(__fadd_rn(m, __fmul_rn(std[src], z)));
+}
+
+__global__ void piid_fill_kernel(const float* __restrict__ win_states, const float* __restrict__ states_pred, const float* __restrict__ tok_mean,
+                                 const float* __restrict__ tok_std, float* __restrict__ filled, int E, int T, int h, int obs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= E * T * obs) return;
+  const int c = i % obs, t = (i / obs) % T;
+  // zeroshot_omtm/learner.py:240-246: [T-h+2, T-1) and [0, T-h+1) come from the path-inference pass
+  const bool from_pred = (t < T - h + 1) || (t >= T - h + 2 && t < T - 1);
+  filled[i] = from_pred ? __fadd_rn(__fmul_rn(states_pred[i], tok_std[c]), tok_mean[c]) : win_states[i];
+}
+
+}  // namespace
+
+int launch_candidates(const CandParams& p, cudaStream_t st) {
+  const int n = p.N * p.h * p.A;
+  candidates_kernel<<<ceil_div(n, 256), 256, 0, st>>>(p);
+  M3PC_CHECK_LAUNCH();
+  return M3PC_OK;
+}
+int launch_critic_input(const CriticInParams& p, cudaStream_t st) {
+  const int n = p.N * p.h * (p.obs + p.A);
+  critic_input_kernel<<<ceil_div(n, 256), 256, 0, st>>>(p);
+  M3PC_CHECK_LAUNCH();
+  return M3PC_OK;
+}
+int launch_critic_out(const float* h1, const float* h2, const float* w1, const float* b1, const float* w2, const float* b2, float* q,
+                      int rows, int H, cudaStream_t st) {
+  critic_out_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(h1, h2, w1, b1, w2, b2, q, rows, H);
+  M3PC_CHECK_LAUNCH();
+  return M3PC_OK;
+}
+int launch_score(const ScoreParams& p, cudaStream_t st) {
+  M3PC_REQUIRE(p.h >= 1 && p.h <= M3PC_MAX_T, "score: bad horizon");
+  score_kernel<<<ceil_div(p.N, 128), 128, 0, st>>>(p);
+  M3PC_CHECK_LAUNCH();
+  return M3PC_OK;
+}
+int launch_select(const SelectParams& p, cudaStream_t st) {
+  M3PC_REQUIRE(p.A <= M3PC_MAX_ACT && p.N >= 1, "select: bad shape");
+  select_kernel<<<1, SEL_THREADS, 0, st>>>(p);
+  M3PC_CHECK_LAUNCH();
+  return M3PC_OK;
+}
+int launch_merge(const float* partials, int n_shards, int A, float temperature, float* eval_action, float* sample_action, int* indices,
+                 cudaStream_t st) {
+  merge_kernel<<<1, 32, 0, st>>>(partials, n_shards, A, temperature, eval_action, sample_action, indices);
+  M3PC_CHECK_LAUNCH();
+  return M3PC_OK;
+}
+int launch_sampling_tail(const float* mu, const float* std, const float* eps, int T, int h, int A, int E, float* eval_action,
+                         float* sample_action, unsigned long long seed, cudaStream_t st) {
+  sampling_tail_kernel<<<ceil_div(E * A, 128), 128, 0, st>>>(mu, std, eps, T, h, A, E, eval_action, sample_action, seed);
+  M3PC_CHECK_LAUNCH();
+  return M3PC_OK;
+}
+int launch_piid_fill(const float* win_states, const float* states_pred, const float* tok_mean, const float* tok_std, float* filled, int E,
+                     int T, int h, int obs, cudaStream_t st) {
+  piid_fill_kernel<<<ceil_div(E * T * obs, 256), 256, 0, st>>>(win_states, states_pred, tok_mean, tok_std, filled, E, T, h, obs);
+  M3PC_CHECK_LAUNCH();
+  return M3PC_OK;
+}
+
+}  // namespace m3pc

@@ -1,0 +1,236 @@
+"""Thin Python owner of one ``m3pc_handle_t`` (include/m3pc.h): parameter upload, forward, plan.
+
+PyTorch is used here only for device memory and streams; every FLOP of the path runs in ``libm3pc.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Mapping, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+MODALITIES = ("states", "actions", "rewards", "returns")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev_f32(t: torch.Tensor, what: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise NotImplementedError(f"{what} must be a CUDA tensor: m3pc_b200 has no CPU path by design")
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.to(torch.float32).contiguous()
+    return t
+
+
+class PlanEngine:
+    """One engine per (process, device).  Mirrors ``m3pc_create`` .. ``m3pc_destroy``."""
+
+    def __init__(self, *, n_embd: int, n_head: int, n_enc_layer: int, n_dec_layer: int, traj_length: int, obs_dim: int,
+                 act_dim: int, precision: str = "bf16", max_batch: int = 1024, chunk: int = 0, critic_hidden: int = 0,
+                 device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("m3pc_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = nat.lib()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.T, self.D, self.obs, self.act = traj_length, n_embd, obs_dim, act_dim
+        self.dims = {"states": obs_dim, "actions": act_dim, "rewards": 1, "returns": 1}
+        self.precision = precision
+        self.max_batch = int(max_batch)
+        self.critic_hidden = int(critic_hidden)
+        cfg = nat.Config(n_embd=n_embd, n_head=n_head, n_enc_layer=n_enc_layer, n_dec_layer=n_dec_layer,
+                         traj_length=traj_length, obs_dim=obs_dim, act_dim=act_dim,
+                         precision={"bf16": nat.PREC_BF16, "fp32": nat.PREC_FP32}[precision],
+                         max_batch=self.max_batch, chunk=int(chunk), critic_hidden=self.critic_hidden)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.m3pc_create(C.byref(self._h), C.byref(cfg)), "m3pc_create")
+        self.finalized = False
+        self.has_critic = False
+        # persistent small outputs
+        self._eval = torch.empty(act_dim, device=self.device)
+        self._sample = torch.empty(act_dim, device=self.device)
+        self._partials = torch.zeros(nat.PARTIAL_FLOATS, device=self.device)
+        self._indices = torch.zeros(2, dtype=torch.int32, device=self.device)
+
+    # ------------------------------------------------------------------ parameters
+    def set_param(self, name: str, value) -> None:
+        a = np.ascontiguousarray(value.detach().cpu().numpy() if isinstance(value, torch.Tensor) else np.asarray(value), dtype=np.float32)
+        nat.check(self.lib.m3pc_set_param(self._h, name.encode(), a.ctypes.data_as(C.c_void_p), a.size), f"m3pc_set_param({name})")
+        self.finalized = False
+
+    def load_state_dict(self, sd: Mapping[str, object]) -> None:
+        """Every key of the reference's ``omtm.state_dict()`` (learner.py:33-35)."""
+        for k, v in sd.items():
+            self.set_param(k, v)
+
+    def load_tokenizer_stats(self, stats: Mapping[str, Mapping[str, object]]) -> None:
+        """mean/std of states, rewards, returns (continuous.py:32-62); actions are not normalised."""
+        for k in ("states", "rewards", "returns"):
+            self.set_param(f"tokenizer.{k}.mean", stats[k]["mean"])
+            self.set_param(f"tokenizer.{k}.std", stats[k]["std"])
+
+    def load_critic(self, qsd: Mapping[str, object], obs_mean, obs_std) -> None:
+        """TwinQ parameters (finetune_omtm/model.py:146-160) + its observation normaliser."""
+        if self.critic_hidden <= 0:
+            raise ValueError("engine was created with critic_hidden=0")
+        for k, v in qsd.items():
+            self.set_param("critic." + k, v)
+        self.set_param("critic.obs_mean", obs_mean)
+        self.set_param("critic.obs_std", obs_std)
+        self.has_critic = True
+
+    def finalize(self) -> None:
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.m3pc_finalize_params(self._h), "m3pc_finalize_params")
+        self.finalized = True
+
+    # ------------------------------------------------------------------ omtm.forward
+    def forward(self, tokens: Mapping[str, torch.Tensor], masks: Mapping[str, object], want: Sequence[str] = MODALITIES
+                ) -> Dict[str, torch.Tensor]:
+        """tokens[k]: (B,T,d) fp32 CUDA; masks[k]: (T,) of {0,1}.  Returns raw head outputs (B,T,d), plus act_mu/act_std."""
+        if not self.finalized:
+            self.finalize()
+        T = self.T
+        ins = {}
+        B = None
+        for k in MODALITIES:
+            t = _dev_f32(tokens[k], f"tokens[{k}]")
+            if t.dim() != 3 or t.shape[1] != T or t.shape[2] != self.dims[k]:
+                raise ValueError(f"tokens[{k}] has shape {tuple(t.shape)}, expected (B,{T},{self.dims[k]})")
+            B = t.shape[0] if B is None else B
+            if t.shape[0] != B:
+                raise ValueError("all modalities must share the batch size")
+            ins[k] = t
+        m = np.zeros(4 * T, dtype=np.uint8)
+        for i, k in enumerate(MODALITIES):
+            mk = masks[k]
+            mk = mk.detach().cpu().numpy() if isinstance(mk, torch.Tensor) else np.asarray(mk)
+            if mk.shape != (T,):
+                raise ValueError(f"masks[{k}] must have shape ({T},)")
+            if not np.all((mk == 0) | (mk == 1)):
+                raise ValueError("mask entries must be 0 or 1")
+            m[i * T:(i + 1) * T] = (mk == 1)
+        out: Dict[str, torch.Tensor] = {}
+        for k in ("states", "rewards", "returns"):
+            if k in want:
+                out[k] = torch.empty(B, T, self.dims[k], device=self.device)
+        if "actions" in want:
+            out["act_mu"] = torch.empty(B, T, self.act, device=self.device)
+            out["act_std"] = torch.empty(B, T, self.act, device=self.device)
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.m3pc_forward(
+                self._h, B, _ptr(ins["states"]), _ptr(ins["actions"]), _ptr(ins["rewards"]), _ptr(ins["returns"]),
+                m.ctypes.data_as(C.c_void_p), _ptr(out.get("states")), _ptr(out.get("act_mu")), _ptr(out.get("act_std")),
+                _ptr(out.get("rewards")), _ptr(out.get("returns")), _stream()), "m3pc_forward")
+        return out
+
+    # ------------------------------------------------------------------ planners
+    def plan(self, *, guidance: str, horizon: int, n_cand: int, win_states: torch.Tensor, win_actions: torch.Tensor,
+             win_rewards: torch.Tensor, win_returns_tok: torch.Tensor, discount: float, temperature: float, lmbda: float,
+             eps: Optional[torch.Tensor] = None, expq: Optional[torch.Tensor] = None, seed: int = 0, cand_offset: int = 0,
+             debug: bool = False, want_partials: bool = False):
+        """One M^3PC plan on one window (learner.py:103-327).  All tensors are CUDA fp32, contiguous.
+        Returns (eval_action, sample_action, dbg) -- the action tensors are engine-owned and overwritten by the next call."""
+        if not self.finalized:
+            self.finalize()
+        a = nat.PlanArgs()
+        a.guidance = nat.GUIDANCE[guidance]
+        a.horizon, a.n_cand, a.cand_offset = int(horizon), int(n_cand), int(cand_offset)
+        a.discount, a.temperature, a.lmbda = float(discount), float(temperature), float(lmbda)
+        keep = [_dev_f32(win_states, "win_states"), _dev_f32(win_actions, "win_actions"), _dev_f32(win_rewards, "win_rewards"),
+                _dev_f32(win_returns_tok, "win_returns_tok")]
+        a.win_states, a.win_actions, a.win_rewards, a.win_returns_tok = (t.data_ptr() for t in keep)
+        if eps is not None:
+            eps = _dev_f32(eps, "eps")
+            a.eps = eps.data_ptr()
+        if expq is not None:
+            expq = _dev_f32(expq, "expq")
+            a.expq = expq.data_ptr()
+        a.seed = int(seed) & (2 ** 64 - 1)
+        a.out_eval_action, a.out_sample_action = self._eval.data_ptr(), self._sample.data_ptr()
+        dbg = {}
+        if want_partials or debug:
+            a.out_partials = self._partials.data_ptr()
+            dbg["partials"] = self._partials
+        if debug and guidance != "mtm_sampling":
+            dbg["expect_return"] = torch.empty(n_cand, device=self.device)
+            dbg["candidates"] = torch.empty(n_cand, horizon, self.act, device=self.device)
+            dbg["indices"] = self._indices
+            a.dbg_expect_return, a.dbg_candidates = dbg["expect_return"].data_ptr(), dbg["candidates"].data_ptr()
+            a.dbg_indices = self._indices.data_ptr()
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.m3pc_plan(self._h, C.byref(a), _stream()), "m3pc_plan")
+        return self._eval, self._sample, dbg
+
+    def merge_partials(self, gathered: torch.Tensor, temperature: float):
+        """Combine per-shard records (n_shards, PARTIAL_FLOATS) -> (eval_action, sample_action, indices)."""
+        g = _dev_f32(gathered, "partials")
+        n = g.numel() // nat.PARTIAL_FLOATS
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.m3pc_merge_partials(self._h, g.data_ptr(), n, float(temperature), self._eval.data_ptr(),
+                                                   self._sample.data_ptr(), self._indices.data_ptr(), _stream()), "m3pc_merge_partials")
+        return self._eval, self._sample, self._indices
+
+    def backward_plan(self, *, mode: str, horizon: int, win_states: torch.Tensor, win_actions: torch.Tensor, win_rewards: torch.Tensor,
+                      win_returns_tok: torch.Tensor, eps: Optional[torch.Tensor] = None, debug: bool = False):
+        """Zero-shot backward planners on E environments (zeroshot_omtm/learner.py:60-261). Windows have a leading E axis."""
+        if not self.finalized:
+            self.finalize()
+        ws = _dev_f32(win_states, "win_states")
+        E = ws.shape[0]
+        wa, wr, wt = _dev_f32(win_actions, "win_actions"), _dev_f32(win_rewards, "win_rewards"), _dev_f32(win_returns_tok, "win_returns_tok")
+        ev = torch.empty(E, self.act, device=self.device)
+        sm = torch.empty(E, self.act, device=self.device)
+        filled = torch.empty(E, self.T, self.obs, device=self.device) if debug else None
+        if eps is not None:
+            eps = _dev_f32(eps, "eps")
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.m3pc_backward_plan(self._h, {"id": 0, "piid": 1}[mode], E, int(horizon), ws.data_ptr(), wa.data_ptr(),
+                                                  wr.data_ptr(), wt.data_ptr(), _ptr(eps), ev.data_ptr(), sm.data_ptr(), _ptr(filled),
+                                                  _stream()), "m3pc_backward_plan")
+        return ev, sm, ({"states_filled": filled} if debug else {})
+
+    # ------------------------------------------------------------------ introspection
+    def last_device_ms(self) -> float:
+        ms = C.c_float()
+        nat.check(self.lib.m3pc_last_device_ms(self._h, C.byref(ms)), "m3pc_last_device_ms")
+        return float(ms.value)
+
+    def last_launch_count(self) -> int:
+        n = C.c_int32()
+        nat.check(self.lib.m3pc_last_launch_count(self._h, C.byref(n)), "m3pc_last_launch_count")
+        return int(n.value)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.m3pc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def engine_from_synthetic(shape, sd, stats, *, precision="bf16", max_batch=1024, chunk=0, critic_sd=None, obs_norm=None,
+                          device=None) -> PlanEngine:
+    """Build + load an engine from the numpy dicts of ``m3pc_b200.synthetic``."""
+    eng = PlanEngine(n_embd=shape.n_embd, n_head=shape.n_head, n_enc_layer=shape.n_enc_layer, n_dec_layer=shape.n_dec_layer,
+                     traj_length=shape.traj_length, obs_dim=shape.obs_dim, act_dim=shape.act_dim, precision=precision,
+                     max_batch=max_batch, chunk=chunk, critic_hidden=256 if critic_sd is not None else 0, device=device)
+    eng.load_state_dict(sd)
+    eng.load_tokenizer_stats(stats)
+    if critic_sd is not None:
+        eng.load_critic(critic_sd, obs_norm[0], obs_norm[1])
+    eng.finalize()
+    return eng
