@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py -- M^3PC plans/sec on B200 (BASELINE.json metric), one JSON line on rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--mode env|cand]
+
+A "step" is one plan: one pass of the hot path (pass 1 at B=1, candidate sampling, pass 2 at B=candidates, critic /
+return scoring, softmax selection) for one environment state.  Default workload = BASELINE.json configs[1]: walker2d
+shapes (obs 17 / act 6), critic_lambda_guiding, 1024 candidates, horizon 4, shipped MTM (D=512, 4 heads, 2+1 layers,
+T=8), random-init weights, synthetic history.
+
+  value     device-resident throughput: window already in HBM, K plans timed with CUDA events (one event pair per plan on
+            the launching stream; a 256 MiB L2 flush between plans sits outside the pairs), max over ranks.
+  e2e       the same K plans through the public API ``Learner.action_sample`` with HOST numpy histories: pinned H2D of
+            the window and a D2H read of the action inside the timed region (host wall clock, max over ranks).
+  roofline  tensor-core GEMMs (the dominant kernel): algorithmic FLOPs of the GEMM launches / their summed per-launch
+            CUDA-event time in a profiling pass of the same plan, against MEASURED_PEAKS.json (sustained bf16).
+  cpu_baseline  the oracle port of the reference planner (torch CPU fp32, all host threads), same workload, bounded sample.
+
+Multi-GPU (launched by torchrun, one rank per GPU): ``--mode env`` (default) gives every rank its own environment --
+independent plans, no data-path collective, weak scaling; ``--mode cand`` shards the candidates of ONE plan across
+ranks (BASELINE.json configs[2]) with one NCCL all-gather of a 72-float record per plan.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from types import SimpleNamespace
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: env, guidance, candidates, temperature, model
+    "walker2d_critic_1024": dict(env="walker2d", guidance="critic_lambda_guiding", n_cand=1024, temperature=1.0, model="shipped"),
+    "hopper_rtg_625": dict(env="hopper", guidance="rtg_guiding", n_cand=625, temperature=0.01, model="shipped"),
+    "hopper_rtg_1024": dict(env="hopper", guidance="rtg_guiding", n_cand=1024, temperature=0.01, model="shipped"),
+    "halfcheetah_rtg_16384": dict(env="halfcheetah", guidance="rtg_guiding", n_cand=16384, temperature=0.01, model="shipped"),
+    "scaled_rtg_4096": dict(env="hopper", guidance="rtg_guiding", n_cand=4096, temperature=0.01, model="scaled"),
+}
+METRIC = "plans_per_sec"
+UNIT = "plans/s"
+
+
+def model_shape(w):
+    from m3pc_b200 import synthetic as syn
+    return syn.scaled_shape(w["env"]) if w["model"] == "scaled" else syn.shipped_shape(w["env"])
+
+
+def flops_per_plan(shape, n_cand, guidance, h):
+    """Dense algorithmic FLOPs of one plan: pass-2 rows (fd mask) + one pass-1 row (rcbc mask) + critic."""
+    D, T, F = shape.n_embd, shape.traj_length, 4 * shape.n_embd
+    idx = T - h
+
+    def block(S):
+        return 2 * S * D * 3 * D + 4 * S * S * D + 2 * S * D * D + 4 * S * D * F
+
+    def fwd(S_enc):
+        emb = 2 * sum(shape.feature_dims.values()) * D * T
+        dec_embed = 2 * 4 * T * D * D
+        heads = 3 * T * (2 * D * D) + 2 * T * D * (shape.obs_dim + 2) + 2 * 2 * T * D * shape.act_dim
+        return emb + shape.n_enc_layer * block(S_enc) + dec_embed + shape.n_dec_layer * block(4 * T) + heads
+
+    s_fd, s_rcbc = (idx + 1) + T, (idx + 1) + idx + T
+    total = n_cand * fwd(s_fd) + fwd(s_rcbc)
+    if guidance != "rtg_guiding":
+        total += n_cand * h * 2 * 2 * ((shape.obs_dim + shape.act_dim) * 256 + 256 * 256 + 256)
+    return float(total), float(fwd(s_fd))
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip().split(", "))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        busy = [c for c in sm if c > 0.5 * mx] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
+def cpu_planner(w, shape):
+    import torch
+    from m3pc_b200 import synthetic as syn
+    from oracle import planner_oracle as po
+    crit = w["guidance"] != "rtg_guiding"
+    return po.from_synthetic(shape, syn.make_state_dict(shape, 0), syn.make_tokenizer_stats(shape, 1), dtype=torch.float32,
+                             critic_np=syn.make_critic_state_dict(shape) if crit else None, obs_norm=syn.make_obs_norm(shape) if crit else None,
+                             action_samples=w["n_cand"], temperature=w["temperature"], plan_guidance=w["guidance"])
+
+
+def time_cpu(w, shape, steps, warmup, budget_s=None):
+    """Oracle port of Learner.action_sample on the host cores; returns (plans/s, per-plan seconds list, threads)."""
+    import numpy as np
+    import torch
+    from m3pc_b200 import synthetic as syn
+    torch.set_num_threads(os.cpu_count() or 1)
+    P = cpu_planner(w, shape)
+    T, A, N = shape.traj_length, shape.act_dim, w["n_cand"]
+    rs = np.random.RandomState(7)
+    times = []
+    t_start = time.perf_counter()
+    for i in range(warmup + steps):
+        hist = syn.make_history(shape, seed=100 + i, path_length=50)
+        eps = torch.from_numpy(rs.randn(N, 1, T, 1, A).astype(np.float32))
+        q = torch.from_numpy(rs.exponential(1.0, N).astype(np.float32))
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            P.action_sample(hist, plan=True, eval=True, rtg=3.0, eps=eps, q=q)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        if budget_s is not None and i >= warmup and time.perf_counter() - t_start > budget_s:
+            break
+    return len(times) / sum(times), times, torch.get_num_threads()
+
+
+def run_reference(args, w, shape, rank):
+    if rank != 0:
+        return
+    steps, warmup = args.steps, args.warmup
+    val, times, threads = time_cpu(w, shape, steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times), "warmup": warmup,
+        "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "candidates": w["n_cand"], "horizon": 4, "guidance": w["guidance"], "env_shapes": w["env"],
+                   "model": f"D={shape.n_embd},heads={shape.n_head},enc={shape.n_enc_layer},dec={shape.n_dec_layer},T={shape.traj_length}"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{len(times)} full plans (oracle port of Learner.action_sample, torch CPU fp32, {threads} threads of {os.cpu_count()} host cpus)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "p50_ms": 1e3 * statistics.median(times),
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ ours
+def run_ours(args, w, shape, rank, local_rank, world):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from m3pc_b200 import synthetic as syn
+    from m3pc_b200 import dist as mdist
+    from m3pc_b200.learner import Learner
+    from m3pc_b200.mtm_model import omtmConfig
+    from m3pc_b200.tokenizers import manager_from_stats
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    h, T, A = 4, shape.traj_length, shape.act_dim
+    n_total = w["n_cand"]
+    cand_mode = args.mode == "cand" and world > 1
+    lo, hi = mdist.shard_range(n_total, rank, world) if cand_mode else (0, n_total)
+    n_local = hi - lo
+    crit = w["guidance"] != "rtg_guiding"
+    sd, stats = syn.make_state_dict(shape, 0), syn.make_tokenizer_stats(shape, 1)
+    cfg = SimpleNamespace(traj_length=T, device=str(dev), action_samples=n_local, discount=0.99, temperature=w["temperature"], horizon=h,
+                          plan_guidance=w["guidance"], lmbda=0.6)
+    mcfg = omtmConfig(n_embd=shape.n_embd, n_head=shape.n_head, n_enc_layer=shape.n_enc_layer, n_dec_layer=shape.n_dec_layer, dropout=0.1,
+                      norm="none", precision=args.precision, max_batch=n_local, chunk=args.chunk)
+    om, os_ = syn.make_obs_norm(shape)
+    L = Learner(cfg, None, shape.data_shapes, mcfg, None, om, os_, manager_from_stats(stats), {k: False for k in shape.data_shapes})
+    L.mtm.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    if crit:
+        L.iql.qf.load_state_dict({k: torch.from_numpy(v) for k, v in syn.make_critic_state_dict(shape).items()})
+    L.seed, L.cand_offset = 1234, lo
+    eng = L._engine()
+    K, W = args.steps, args.warmup
+    # env mode: every rank plans for its own environment(s); cand mode: all ranks share the environment
+    hists = [syn.make_history(shape, seed=1000 + (0 if cand_mode else rank) * 10007 + i, path_length=50 + i) for i in range(K + W)]
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
+
+    def plan_resident(i, want_partials=False):
+        ws, wa, wr, wt = windows[i]
+        ev, sm, dbg = eng.plan(guidance=w["guidance"], horizon=h, n_cand=n_local, win_states=ws, win_actions=wa, win_rewards=wr,
+                               win_returns_tok=wt, discount=0.99, temperature=w["temperature"], lmbda=0.6, seed=7 + i, cand_offset=lo,
+                               want_partials=want_partials)
+        if cand_mode and want_partials:
+            g = mdist.gather_partials(dbg["partials"])
+            ev, sm, _ = eng.merge_partials(g, w["temperature"])
+        return ev
+
+    # windows resident in HBM (built by the same host code the public API uses)
+    windows = []
+    for hist in hists:
+        ring, slot = L._window_buffers(shape.obs_dim, shape.act_dim)
+        L._fill_window(slot.h_states, slot.h_actions, slot.h_rewards, slot.h_returns, hist, h, 1.0, 3.0)
+        t = slot.host.to(dev)
+        o = [0, T * shape.obs_dim, T * (shape.obs_dim + A), T * (shape.obs_dim + A + 1), t.numel()]
+        windows.append((t[o[0]:o[1]].view(T, -1), t[o[1]:o[2]].view(T, -1), t[o[2]:o[3]], t[o[3]:o[4]]))
+
+    # ---- device-resident timing: K plans, one CUDA-event pair each, L2 flushed between plans ----
+    for i in range(W):
+        plan_resident(i, cand_mode)
+    torch.cuda.synchronize(); barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    pairs = []
+    torch.cuda.synchronize(); barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        flush.fill_(float(i))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        plan_resident(W + i, cand_mode)
+        e1.record()
+        pairs.append((e0, e1))
+    torch.cuda.synchronize(); barrier()
+    wall_resident = time.perf_counter() - t_wall0
+    per_plan_ms = [a.elapsed_time(b) for a, b in pairs]
+    launches = eng.last_launch_count() + (1 if cand_mode else 0)
+    dev_s = sum(per_plan_ms) / 1e3
+
+    # ---- e2e: public API with host histories (pinned H2D + D2H inside the timed region) ----
+    for i in range(W):
+        L.action_sample(hists[i], plan=True, eval=True, rtg=3.0).cpu()
+    torch.cuda.synchronize(); barrier()
+    t0 = time.perf_counter()
+    lat = []
+    for i in range(K):
+        t1 = time.perf_counter()
+        if cand_mode:
+            ring, slot = L._window_buffers(shape.obs_dim, shape.act_dim)
+            L._fill_window(slot.h_states, slot.h_actions, slot.h_rewards, slot.h_returns, hists[W + i], h, 1.0, 3.0)
+            L._upload_window(ring, slot)
+            ev, sm, dbg = eng.plan(guidance=w["guidance"], horizon=h, n_cand=n_local, win_states=ring.d_states, win_actions=ring.d_actions,
+                                   win_rewards=ring.d_rewards, win_returns_tok=ring.d_returns, discount=0.99, temperature=w["temperature"],
+                                   lmbda=0.6, seed=7 + i, cand_offset=lo, want_partials=True)
+            ev, sm, _ = eng.merge_partials(mdist.gather_partials(dbg["partials"]), w["temperature"])
+            a = ev.cpu()
+        else:
+            a = L.action_sample(hists[W + i], plan=True, eval=True, rtg=3.0).cpu()
+        lat.append(time.perf_counter() - t1)
+    torch.cuda.synchronize(); barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline pass: same plan with one event pair per GEMM launch ----
+    eng.set_profile(True)
+    g_ms, g_fl, g_n = 0.0, 0.0, 0
+    for i in range(3):
+        plan_resident(W + i)
+        torch.cuda.synchronize()
+        ms, fl, n = eng.get_profile()
+        g_ms, g_fl, g_n = g_ms + ms, g_fl + fl, g_n + n
+    eng.set_profile(False)
+
+    # ---- max over ranks ----
+    stats_t = torch.tensor([dev_s, e2e_s, wall_resident], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats_t, op=dist.ReduceOp.MAX)
+    dev_s, e2e_s, wall_resident = [float(x) for x in stats_t.tolist()]
+    plans_per_step = 1 if (cand_mode or world == 1) else world
+    value = plans_per_step * K / dev_s
+    e2e_value = plans_per_step * K / e2e_s
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md sustained)"
+    ach_tf = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    fl_plan, fl_row = flops_per_plan(shape, n_total, w["guidance"], h)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cval, ctimes, threads = time_cpu(w, shape, steps=8, warmup=1, budget_s=25.0)
+        cpu = {"value": cval, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{len(ctimes)} full plans of the same workload (oracle port of Learner.action_sample, torch CPU fp32, {threads} threads of {os.cpu_count()} host cpus)"}
+    win_bytes = 4 * T * (shape.obs_dim + A + 2)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * dev_s / K,
+        "higher_is_better": True, "scaling": "strong" if cand_mode else "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "candidates": n_total, "horizon": h, "guidance": w["guidance"], "env_shapes": w["env"],
+                   "model": f"D={shape.n_embd},heads={shape.n_head},enc={shape.n_enc_layer},dec={shape.n_dec_layer},T={shape.traj_length}",
+                   "parallelism": (f"cand-shard x{world} + allgather(72 floats)" if cand_mode else f"env-parallel x{world} (independent plans, no collective)"),
+                   "plans_per_step": plans_per_step, "l2": "256 MiB flush write between timed plans (outside the per-plan event pairs)",
+                   "weights": "random-init (numpy seed 0), reference state_dict layout", "chunk": args.chunk},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": win_bytes, "d2h_bytes_per_step": 4 * A,
+                "p50_latency_ms": 1e3 * statistics.median(lat), "api": "Learner.action_sample(host numpy history) -> .cpu()"},
+        "gpu_launches": launches * K,
+        "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None,
+                     "traffic": traffic, "kernel": "gemm_bf16_kernel (tcgen05)", "launches_per_plan": g_n // 3, "gemm_ms_per_plan": g_ms / 3,
+                     "gemm_flops_per_plan": g_fl / 3, "peak_source": peak_src,
+                     "whole_plan_dense_frac": fl_plan * value / (world * peak_tf * 1e12)},
+        "flops_per_plan_dense": fl_plan, "flops_per_candidate_row": fl_row,
+        "p50_ms": statistics.median(per_plan_ms), "wall_s_resident_loop": wall_resident,
+        "clocks": clocks,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="walker2d_critic_1024", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="env", choices=["env", "cand"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    w = WORKLOADS[args.workload]
+    shape = model_shape(w)
+    rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, w, shape, rank)
+        return
+    from m3pc_b200 import dist as mdist
+    mdist.init_from_env("nccl")
+    try:
+        run_ours(args, w, shape, rank, local_rank, world)
+    finally:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

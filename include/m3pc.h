@@ -174,6 +174,13 @@ int m3pc_last_device_ms(m3pc_handle_t h, float* ms);
 /* Number of kernels the most recent m3pc_plan / m3pc_forward call launched. */
 int m3pc_last_launch_count(m3pc_handle_t h, int32_t* n);
 
+/* Profiling mode (off by default): when on, every tensor-core / fp32 GEMM launch of m3pc_plan / m3pc_forward /
+ * m3pc_backward_plan is bracketed by its own CUDA event pair on the caller's stream.  m3pc_get_profile synchronises
+ * those events and reports, for the most recent call: summed GEMM device time (ms), the algorithmic FLOPs those
+ * launches executed (2*M*N*K each) and their count.  Used by bench.py for the live roofline numerator. */
+int m3pc_set_profile(m3pc_handle_t h, int32_t on);
+int m3pc_get_profile(m3pc_handle_t h, double* gemm_ms, double* gemm_flops, int32_t* gemm_launches);
+
 #ifdef __cplusplus
 }
 #endif

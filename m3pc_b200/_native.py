@@ -31,7 +31,7 @@ GUIDANCE = {
 SYMBOLS = (
     "m3pc_last_error", "m3pc_version", "m3pc_create", "m3pc_destroy", "m3pc_set_param", "m3pc_finalize_params",
     "m3pc_forward", "m3pc_plan", "m3pc_merge_partials", "m3pc_backward_plan", "m3pc_gemm_bf16", "m3pc_gemm_fp32",
-    "m3pc_layernorm", "m3pc_attention", "m3pc_last_device_ms", "m3pc_last_launch_count",
+    "m3pc_layernorm", "m3pc_attention", "m3pc_last_device_ms", "m3pc_last_launch_count", "m3pc_set_profile", "m3pc_get_profile",
 )
 
 
@@ -102,6 +102,8 @@ def lib() -> C.CDLL:
     L.m3pc_attention.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     L.m3pc_last_device_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.m3pc_last_launch_count.argtypes = [vp, C.POINTER(C.c_int32)]
+    L.m3pc_set_profile.argtypes = [vp, i32]
+    L.m3pc_get_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     for s in SYMBOLS:
         if s not in ("m3pc_last_error", "m3pc_version"):
             getattr(L, s).restype = C.c_int

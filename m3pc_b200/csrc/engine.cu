@@ -114,10 +114,19 @@ struct m3pc_engine {
 
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int last_launches = 0;
+  // profiling mode: one event pair per GEMM launch
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  std::vector<double> prof_flops;
+  size_t prof_used = 0;
 
   ~m3pc_engine() {
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    for (auto& pr : prof_events) {
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
   }
 };
 
@@ -366,8 +375,23 @@ int finalize(m3pc_engine* e) {
 // ------------------------------------------------------------------------------------------------ forward
 int gemm(m3pc_engine* e, const void* A, const float* w32, const __nv_bfloat16* w16, void* C, int M, int N, int K, const GemmEpilogue& epi,
          cudaStream_t st) {
-  if (e->bf16) return gemm_bf16_tcgen05(reinterpret_cast<const __nv_bfloat16*>(A), w16, C, M, N, K, epi, st);
-  return gemm_fp32(reinterpret_cast<const float*>(A), w32, reinterpret_cast<float*>(C), M, N, K, epi, st);
+  size_t slot = 0;
+  if (e->profile) {
+    slot = e->prof_used++;
+    if (slot >= e->prof_events.size()) {
+      cudaEvent_t a, b;
+      M3PC_CHECK_CUDA(cudaEventCreate(&a));
+      M3PC_CHECK_CUDA(cudaEventCreate(&b));
+      e->prof_events.push_back({a, b});
+      e->prof_flops.push_back(0.0);
+    }
+    e->prof_flops[slot] = 2.0 * M * static_cast<double>(N) * K;
+    M3PC_CHECK_CUDA(cudaEventRecord(e->prof_events[slot].first, st));
+  }
+  const int rc = e->bf16 ? gemm_bf16_tcgen05(reinterpret_cast<const __nv_bfloat16*>(A), w16, C, M, N, K, epi, st)
+                         : gemm_fp32(reinterpret_cast<const float*>(A), w32, reinterpret_cast<float*>(C), M, N, K, epi, st);
+  if (e->profile && rc == M3PC_OK) M3PC_CHECK_CUDA(cudaEventRecord(e->prof_events[slot].second, st));
+  return rc;
 }
 
 // one pre-LN transformer block on `rows` = S * Bc token-major rows; expects Y = LN1(X) on entry
@@ -772,6 +796,7 @@ int create(m3pc_handle_t* out, const m3pc_config_t* cfg) {
 template <typename Fn>
 int timed(m3pc_engine* e, cudaStream_t st, Fn&& fn) {
   g_launch_count = 0;
+  e->prof_used = 0;
   M3PC_CHECK_CUDA(cudaEventRecord(e->ev0, st));
   const int rc = fn();
   e->last_launches = g_launch_count;
@@ -891,6 +916,29 @@ int m3pc_last_device_ms(m3pc_handle_t h, float* ms) {
   M3PC_REQUIRE(h != nullptr && ms != nullptr, "null argument");
   M3PC_CHECK_CUDA(cudaEventSynchronize(h->ev1));
   M3PC_CHECK_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return M3PC_OK;
+}
+
+int m3pc_set_profile(m3pc_handle_t h, int32_t on) {
+  M3PC_REQUIRE(h != nullptr, "null handle");
+  h->profile = on != 0;
+  h->prof_used = 0;
+  return M3PC_OK;
+}
+
+int m3pc_get_profile(m3pc_handle_t h, double* gemm_ms, double* gemm_flops, int32_t* gemm_launches) {
+  M3PC_REQUIRE(h != nullptr && gemm_ms && gemm_flops && gemm_launches, "null argument");
+  double ms = 0.0, fl = 0.0;
+  for (size_t i = 0; i < h->prof_used; ++i) {
+    float t = 0.f;
+    M3PC_CHECK_CUDA(cudaEventSynchronize(h->prof_events[i].second));
+    M3PC_CHECK_CUDA(cudaEventElapsedTime(&t, h->prof_events[i].first, h->prof_events[i].second));
+    ms += t;
+    fl += h->prof_flops[i];
+  }
+  *gemm_ms = ms;
+  *gemm_flops = fl;
+  *gemm_launches = static_cast<int32_t>(h->prof_used);
   return M3PC_OK;
 }
 

@@ -210,6 +210,15 @@ class PlanEngine:
         nat.check(self.lib.m3pc_last_launch_count(self._h, C.byref(n)), "m3pc_last_launch_count")
         return int(n.value)
 
+    def set_profile(self, on: bool) -> None:
+        nat.check(self.lib.m3pc_set_profile(self._h, int(bool(on))), "m3pc_set_profile")
+
+    def get_profile(self):
+        """(summed GEMM device ms, algorithmic GEMM FLOPs, GEMM launches) of the most recent call in profiling mode."""
+        ms, fl, n = C.c_double(), C.c_double(), C.c_int32()
+        nat.check(self.lib.m3pc_get_profile(self._h, C.byref(ms), C.byref(fl), C.byref(n)), "m3pc_get_profile")
+        return float(ms.value), float(fl.value), int(n.value)
+
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
             self.lib.m3pc_destroy(self._h)

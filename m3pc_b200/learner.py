@@ -1,0 +1,225 @@
+"""Forward M^3PC planners -- drop-in for the planning half of research/finetune_omtm/learner.py.
+
+Same entry points, argument meaning and return shapes as the reference:
+
+  Learner.action_sample(sequence_history, percentage, horizon, plan, eval, rtg)   learner.py:329-417
+  Learner.rtg_guiding(trajectory, h, lmbda=0.6)                                   learner.py:271-327
+  Learner.critic_lambda_guiding(trajectory, h, lmbda)                             learner.py:211-268
+  Learner.noise_adding_lambda(trajectory, h, lmbda)                               learner.py:142-208
+  Learner.mtm_sampling(trajectory, h)                                             learner.py:103-115
+
+but one call is ONE ``m3pc_plan`` launch sequence on the device (pass 1 at B=1, candidate sampling, pass 2 at
+B=action_samples, critic / return scoring, softmax selection) with no host round trip in between; the host builds the
+(T, obs+act+2) window in pinned memory, copies it once, and reads back ``act_dim`` floats.
+
+``PlannerMixin`` carries the planners; a maintainer can mix it into the reference's own ``Learner``.
+The training / evaluation halves of the reference class (``mtm_update``, ``critic_update``, ``evaluate*``) are outside
+this path and are not provided.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .critic import TwinQ
+from .mtm_model import omtm
+from .tokenizers import TokenizerManager
+
+_PLAN_GUIDANCE = ("critic_lambda_guiding", "rtg_guiding", "noise_adding_lambda")
+
+
+class PlannerMixin:
+    """Needs: self.cfg (traj_length, device, action_samples, discount, temperature, horizon, plan_guidance, lmbda),
+    self.mtm (m3pc_b200.omtm), self.tokenizer_manager, and for the critic planners self.iql.qf (m3pc_b200.TwinQ)."""
+
+    # -- noise control ---------------------------------------------------------------------------------
+    #: (eps, q) to consume instead of the on-device Philox stream: eps (N,h,A) [or (A,) for mtm_sampling], q (N,).
+    injected_noise: Optional[Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]] = None
+    #: filled by every plan when ``debug_plans`` is True (expect_return, candidates, indices, partials)
+    debug_plans: bool = False
+    last_plan_debug: Optional[dict] = None
+    seed: int = 0
+    #: global candidate id of this process's first candidate / total (candidate sharding across ranks)
+    cand_offset: int = 0
+
+    def _engine(self):
+        if self.__dict__.get("_planner_bound") is not self.mtm:
+            critic = getattr(getattr(self, "iql", None), "qf", None)
+            max_batch = max(int(getattr(self.cfg, "action_samples", 1)), int(getattr(self, "max_envs", 1)))
+            self.mtm.bind_planner(self.tokenizer_manager, critic, max_batch=max_batch)
+            self.__dict__["_planner_bound"] = self.mtm
+            self.__dict__["_plan_counter"] = 0
+            rt = self.tokenizer_manager.tokenizers["returns"]
+            self.__dict__["_rt_norm"] = (rt._data_mean.detach().double().cpu().numpy(), rt._data_std.detach().double().cpu().numpy(), bool(rt.normalize))
+        return self.mtm.sync_engine()
+
+    def _returns_tok(self, returns: np.ndarray) -> np.ndarray:
+        """Tokenise the return-to-go exactly like the reference: float64 arithmetic, one rounding to fp32
+        (learner.py:368-385 builds a float64 tensor; continuous.py:74-79 normalises then casts)."""
+        mean, std, normalize = self.__dict__["_rt_norm"]
+        r = np.asarray(returns, dtype=np.float64)
+        if normalize:
+            r = (r - mean) / std
+        return r.astype(np.float32)
+
+    def _next_seed(self) -> int:
+        c = self.__dict__.get("_plan_counter", 0)
+        self.__dict__["_plan_counter"] = c + 1
+        return (int(self.seed) << 32) ^ c
+
+    def _plan_device(self, guidance: str, h: int, lmbda: float, ws, wa, wr, wt):
+        eng = self._engine()
+        eps, q = self.injected_noise if self.injected_noise is not None else (None, None)
+        ev, sm, dbg = eng.plan(guidance=guidance, horizon=h, n_cand=int(self.cfg.action_samples), win_states=ws, win_actions=wa,
+                               win_rewards=wr, win_returns_tok=wt, discount=float(self.cfg.discount), temperature=float(self.cfg.temperature),
+                               lmbda=float(lmbda), eps=eps, expq=q, seed=self._next_seed(), cand_offset=int(self.cand_offset),
+                               debug=self.debug_plans)
+        if self.debug_plans:
+            self.last_plan_debug = {k: v.clone() for k, v in dbg.items()}
+        return ev, sm
+
+    def _plan_from_trajectory(self, guidance: str, trajectory: Dict[str, torch.Tensor], h: int, lmbda: float):
+        self._engine()
+        T = self.cfg.traj_length
+        dev = self.mtm.pos_embed.device
+        ws = trajectory["states"].reshape(T, -1).to(dev, torch.float32)
+        wa = trajectory["actions"].reshape(T, -1).to(dev, torch.float32)
+        wr = trajectory["rewards"].reshape(T).to(dev, torch.float32)
+        wt = torch.from_numpy(self._returns_tok(trajectory["returns"].detach().reshape(T).cpu().numpy())).to(dev)
+        return self._plan_device(guidance, h, lmbda, ws, wa, wr, wt)
+
+    # -- the reference's planner entry points -------------------------------------------------------------
+    @torch.no_grad()
+    def mtm_sampling(self, trajectory: Dict[str, torch.Tensor], h):
+        ev, sm = self._plan_from_trajectory("mtm_sampling", trajectory, h, 0.0)
+        return sm.clone()[None, :], ev.clone()[None, :]
+
+    @torch.no_grad()
+    def noise_adding_lambda(self, trajectory: Dict[str, torch.Tensor], h: int, lmbda: float):
+        ev, sm = self._plan_from_trajectory("noise_adding_lambda", trajectory, h, lmbda)
+        return sm.clone()[None, :], ev.clone()
+
+    @torch.no_grad()
+    def critic_lambda_guiding(self, trajectory: Dict[str, torch.Tensor], h: int, lmbda: float):
+        ev, sm = self._plan_from_trajectory("critic_lambda_guiding", trajectory, h, lmbda)
+        return sm.clone()[None, :], ev.clone()
+
+    @torch.no_grad()
+    def rtg_guiding(self, trajectory: Dict[str, torch.Tensor], h: int, lmbda: float = 0.6):
+        ev, sm = self._plan_from_trajectory("rtg_guiding", trajectory, h, lmbda)
+        return sm.clone()[None, :], ev.clone()
+
+    # -- window builder (host) ------------------------------------------------------------------------------
+    def _window_buffers(self, obs_dim: int, act_dim: int, n_env: int = 1):
+        """Two pinned host staging buffers (alternating, each guarded by a CUDA event so a buffer is never rewritten while
+        its H2D copy is still queued) and one device buffer, laid out [states | actions | rewards | returns_tok]."""
+        T = self.cfg.traj_length
+        key = (obs_dim, act_dim, T, n_env)
+        ring = self.__dict__.get("_win")
+        if ring is None or ring.key != key:
+            n = n_env * T * (obs_dim + act_dim + 2)
+            dev = torch.zeros(n, dtype=torch.float32, device=self.mtm.pos_embed.device)
+            o = [0, n_env * T * obs_dim, n_env * T * (obs_dim + act_dim), n_env * T * (obs_dim + act_dim + 1), n]
+            shp = [(n_env, T, obs_dim), (n_env, T, act_dim), (n_env, T), (n_env, T)]
+            if n_env == 1:
+                shp = [s_[1:] for s_ in shp]
+            slots = []
+            for _ in range(2):
+                host = torch.zeros(n, dtype=torch.float32).pin_memory()
+                hn = host.numpy()
+                slots.append(SimpleNamespace(host=host, event=torch.cuda.Event(), used=False,
+                                             h_states=hn[o[0]:o[1]].reshape(shp[0]), h_actions=hn[o[1]:o[2]].reshape(shp[1]),
+                                             h_rewards=hn[o[2]:o[3]].reshape(shp[2]), h_returns=hn[o[3]:o[4]].reshape(shp[3])))
+            ring = SimpleNamespace(key=key, slots=slots, turn=0, dev=dev,
+                                   d_states=dev[o[0]:o[1]].view(shp[0]), d_actions=dev[o[1]:o[2]].view(shp[1]),
+                                   d_rewards=dev[o[2]:o[3]].view(shp[2]), d_returns=dev[o[3]:o[4]].view(shp[3]))
+            self.__dict__["_win"] = ring
+        slot = ring.slots[ring.turn]
+        ring.turn ^= 1
+        if slot.used:
+            slot.event.synchronize()
+        return ring, slot
+
+    def _upload_window(self, ring, slot) -> None:
+        ring.dev.copy_(slot.host, non_blocking=True)
+        slot.event.record()
+        slot.used = True
+
+    def _fill_window(self, states, actions, rewards, returns, sequence_history, horizon: int, percentage: float, rtg,
+                     future_obs: bool = False) -> None:
+        """learner.py:346-385 (and zeroshot_omtm/learner.py:75-132 when ``future_obs``), written into pinned memory.
+        ``states`` (T,obs), ``actions`` (T,act), ``rewards`` (T,), ``returns`` (T,) are numpy views of the staging buffer."""
+        T = self.cfg.traj_length
+        end_idx = sequence_history["path_length"]
+        hl = T - horizon + 1
+        lo, hi = end_idx - hl + 1, end_idx + 1
+        states[:] = 0
+        actions[:] = 0
+        rewards[:] = 0
+        states[:hl] = sequence_history["observations"][lo:hi]
+        actions[:hl] = sequence_history["actions"][lo:hi]
+        rewards[:hl] = np.asarray(sequence_history["rewards"][lo:hi]).reshape(-1)
+        if future_obs:
+            smart_T = T
+            if end_idx + horizon > 1000:
+                smart_T = smart_T - (end_idx + horizon - 1000)
+            states[:smart_T] = sequence_history["observations"][lo:lo + T]
+        if rtg is not None:
+            return_to_go = float(rtg)
+        else:
+            stats = self.tokenizer_manager.tokenizers["returns"].stats
+            return_to_go = float(np.asarray(stats.min + (stats.max - stats.min) * percentage).reshape(-1)[0])
+        returns[:] = self._returns_tok(return_to_go * np.ones(T))
+
+    def _clamped_horizon(self, sequence_history) -> int:
+        """learner.py:342-345: early in an episode the planning horizon grows so the window stays full."""
+        horizon = self.cfg.horizon
+        if sequence_history["path_length"] + horizon < self.cfg.traj_length:
+            horizon = self.cfg.traj_length - sequence_history["path_length"]
+        return horizon
+
+    @torch.no_grad()
+    def action_sample(self, sequence_history, percentage=1.0, horizon=4, plan=True, eval=False, rtg=None):
+        if eval == True:  # noqa: E712  (mirrors learner.py:339-340)
+            assert rtg is not None
+        self._engine()
+        horizon = self._clamped_horizon(sequence_history)
+        wb, slot = self._window_buffers(sequence_history["observations"].shape[-1], sequence_history["actions"].shape[-1])
+        self._fill_window(slot.h_states, slot.h_actions, slot.h_rewards, slot.h_returns, sequence_history, horizon, percentage, rtg)
+        self._upload_window(wb, slot)
+        if plan:
+            assert self.cfg.plan_guidance in _PLAN_GUIDANCE
+            lmbda = 0.6 if self.cfg.plan_guidance == "rtg_guiding" else self.cfg.lmbda  # learner.py:405-407 drops cfg.lmbda
+            ev, sm = self._plan_device(self.cfg.plan_guidance, horizon, lmbda, wb.d_states, wb.d_actions, wb.d_rewards, wb.d_returns)
+            return ev.clone() if eval else sm.clone()[None, :]
+        ev, sm = self._plan_device("mtm_sampling", horizon, 0.0, wb.d_states, wb.d_actions, wb.d_rewards, wb.d_returns)
+        return ev.clone()[None, :] if eval else sm.clone()[None, :]
+
+
+class Learner(PlannerMixin):
+    """Constructor-compatible with finetune_omtm/learner.py:17-101 (the optimiser / IQL-trainer halves are not built)."""
+
+    def __init__(self, cfg, env, data_shapes, model_config, pretrain_model_path, obs_mean, obs_std,
+                 tokenizer_manager: TokenizerManager, discrete_map: Dict[str, bool]):
+        self.cfg = cfg
+        self.env = env
+        self.mtm: omtm = model_config.create(data_shapes, cfg.traj_length, discrete_map)
+        if pretrain_model_path is not None:
+            self.mtm.load_state_dict(torch.load(pretrain_model_path, map_location="cpu")["model"])
+        self.mtm.to(cfg.device)
+        self.tokenizer_manager = tokenizer_manager
+        self.obs_mean = obs_mean
+        self.obs_std = obs_std
+        self.discrete_map = discrete_map
+        if env is not None:
+            state_dim, action_dim = env.observation_space.shape[0], env.action_space.shape[0]
+        else:
+            state_dim, action_dim = data_shapes["states"][1], data_shapes["actions"][1]
+        om = torch.as_tensor(obs_mean, dtype=torch.float32) if obs_mean is not None else torch.zeros(state_dim)
+        os_ = torch.as_tensor(obs_std, dtype=torch.float32) if obs_std is not None else torch.ones(state_dim)
+        q_network = TwinQ(state_dim, action_dim, om.to(cfg.device), os_.to(cfg.device)).to(cfg.device)
+        # the planners reach the critic as self.iql.qf (learner.py:250-252)
+        self.iql = SimpleNamespace(qf=q_network)

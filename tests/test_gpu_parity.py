@@ -1,0 +1,403 @@
+"""Parity tests proper (need a B200): every call goes through the C-ABI (include/m3pc.h) via ctypes.
+
+Tolerances
+  fp32 mode  -- "1e-5 with an fp32 accumulate mode" (BASELINE.json north_star): max |x - ref| <= 2e-5 * max(1, max|ref|).
+                Measured ~1e-6 against the float64 oracle.
+  bf16 mode  -- "within 1e-2 relative error at bf16": max |x - ref| <= 1e-2 * max(1, max|ref|) for states / rewards / returns /
+                action mu / action mean; the action std = exp(-5 + 3.5 (tanh(.) + 1)) amplifies its pre-activation error by up
+                to 3.5x, so it gets 3.5e-2.  Measured 3e-3 .. 7e-3 (std up to 1.2e-2).
+  indices    -- bit-exact wherever the score gap exceeds twice the measured score error.
+"""
+import json
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from m3pc_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 2e-5, "bf16": 1e-2}
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / max(1.0, float(b.abs().max())))
+
+
+@pytest.fixture(scope="module")
+def nat():
+    from m3pc_b200 import _native
+    _native.lib()
+    return _native
+
+
+# ------------------------------------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("M,N,K,flags", [(17, 1536, 512, 0), (200, 512, 2048, 1), (333, 256, 23, 4), (64, 1, 256, 0), (1000, 512, 512, 2)])
+def test_gemm_fp32(nat, M, N, K, flags):
+    torch.manual_seed(0)
+    A, W, b = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda") / K ** 0.5, torch.randn(N, device="cuda")
+    Cm = torch.randn(M, N, device="cuda")
+    C0 = Cm.clone()
+    nat.check(nat.lib().m3pc_gemm_fp32(A.data_ptr(), W.data_ptr(), b.data_ptr(), Cm.data_ptr(), M, N, K, flags, None))
+    ref = A.double() @ W.double().T + b.double()
+    if flags & 1: ref = torch.nn.functional.gelu(ref)
+    if flags & 4: ref = torch.relu(ref)
+    if flags & 2: ref = ref + C0.double()
+    assert rel(Cm, ref) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K,flags", [(128, 128, 64, 0), (17, 1536, 512, 0), (8125, 512, 512, 2), (1000, 2048, 512, 1), (333, 512, 2048, 2),
+                                         (4096, 1536, 512, 0), (130, 128, 128, 4), (1, 128, 64, 0), (20000, 2048, 512, 1), (32768, 512, 2048, 2)])
+def test_gemm_bf16_tcgen05(nat, M, N, K, flags):
+    """The tensor-core GEMM against an fp64 product of the same bf16 operands (operand rounding excluded):
+    fp32-output epilogues must be fp32-accurate, bf16 outputs within half a bf16 ulp of the largest value."""
+    torch.manual_seed(1)
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    W = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+    b = torch.randn(N, device="cuda")
+    ref = A.double() @ W.double().T + b.double()
+    if flags & 1: ref = torch.nn.functional.gelu(ref)
+    if flags & 4: ref = torch.relu(ref)
+    if flags & 2:
+        Cm = torch.randn(M, N, device="cuda")
+        ref = ref + Cm.double()
+    else:
+        Cm = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    nat.check(nat.lib().m3pc_gemm_bf16(A.data_ptr(), W.data_ptr(), b.data_ptr(), Cm.data_ptr(), M, N, K, flags, None))
+    torch.cuda.synchronize()
+    assert torch.isfinite(Cm.float()).all()
+    assert rel(Cm, ref) < (2e-5 if flags & 2 else 4e-3)
+
+
+def test_gemm_rejects_bad_shapes(nat):
+    A = torch.zeros(128, 100, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        nat.check(nat.lib().m3pc_gemm_bf16(A.data_ptr(), A.data_ptr(), None, A.data_ptr(), 128, 128, 100, 0, None))
+    with pytest.raises(ValueError):
+        nat.check(nat.lib().m3pc_gemm_bf16(A.data_ptr(), A.data_ptr(), None, A.data_ptr(), 128, 100, 64, 0, None))
+
+
+@pytest.mark.parametrize("D", [512, 1024])
+def test_layernorm(nat, D):
+    torch.manual_seed(0)
+    x, g, b = torch.randn(1000, D, device="cuda") * 3 + 1, torch.rand(D, device="cuda") + 0.5, torch.randn(D, device="cuda")
+    ref = torch.nn.functional.layer_norm(x.double(), (D,), g.double(), b.double(), 1e-5)
+    y = torch.empty(1000, D, device="cuda")
+    nat.check(nat.lib().m3pc_layernorm(x.data_ptr(), g.data_ptr(), b.data_ptr(), y.data_ptr(), 1000, D, 0, None))
+    y16 = torch.empty(1000, D, device="cuda", dtype=torch.bfloat16)
+    nat.check(nat.lib().m3pc_layernorm(x.data_ptr(), g.data_ptr(), b.data_ptr(), y16.data_ptr(), 1000, D, 1, None))
+    assert rel(y, ref) < 1e-5 and rel(y16, ref) < 4e-3
+
+
+@pytest.mark.parametrize("B,S,H", [(5, 13, 4), (3, 32, 4), (2, 64, 8), (70, 17, 4), (1, 9, 4), (33, 10, 4)])
+def test_attention(nat, B, S, H):
+    torch.manual_seed(0)
+    D = H * 128
+    qkv = torch.randn(S * B, 3 * D, device="cuda")
+
+    def ref_of(t):
+        q, k, v = [u.reshape(S, B, H, 128).permute(1, 2, 0, 3).double() for u in t.split(D, dim=1)]
+        return (torch.softmax(q @ k.transpose(-1, -2) / 128 ** 0.5, -1) @ v).permute(2, 0, 1, 3).reshape(S * B, D)
+
+    out = torch.empty(S * B, D, device="cuda")
+    nat.check(nat.lib().m3pc_attention(qkv.data_ptr(), out.data_ptr(), B, S, H, 0, None))
+    assert rel(out, ref_of(qkv)) < 1e-5
+    qkv16 = qkv.bfloat16()
+    out16 = torch.empty(S * B, D, device="cuda", dtype=torch.bfloat16)
+    nat.check(nat.lib().m3pc_attention(qkv16.data_ptr(), out16.data_ptr(), B, S, H, 1, None))
+    assert rel(out16, ref_of(qkv16)) < 8e-3
+
+
+# ------------------------------------------------------------------------------------------------ omtm.forward
+def _module(shape, precision, max_batch=64, chunk=0):
+    from m3pc_b200.mtm_model import omtmConfig
+    cfg = omtmConfig(n_embd=shape.n_embd, n_head=shape.n_head, n_enc_layer=shape.n_enc_layer, n_dec_layer=shape.n_dec_layer, dropout=0.1,
+                     norm="none", precision=precision, max_batch=max_batch, chunk=chunk)
+    m = cfg.create(shape.data_shapes, shape.traj_length, {k: False for k in shape.data_shapes})
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in syn.make_state_dict(shape, 0).items()})
+    return m.to("cuda")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_forward_matches_reference_golden(golden_dir, precision):
+    """omtm.forward through the module API against outputs of the REFERENCE itself (tests/golden/forward_hopper.npz)."""
+    from m3pc_b200 import masks as M
+    from m3pc_b200.tokenizers import manager_from_stats
+    z = np.load(os.path.join(golden_dir, "forward_hopper.npz"))
+    meta = json.loads(str(z["meta"]))
+    shape = syn.shipped_shape("hopper")
+    m = _module(shape, precision)
+    tm = manager_from_stats(syn.make_tokenizer_stats(shape, meta["stat_seed"]))
+    traj = {k: torch.from_numpy(v).cuda() for k, v in syn.make_trajectories(shape, meta["batch"], meta["traj_seed"]).items()}
+    enc = tm.encode(traj)
+    fns = {"rcbc": M.create_rcbc_mask, "fd": M.create_fd_mask, "pi": M.create_pi_mask, "fid": M.create_fid_mask, "gid": M.create_gid_mask}
+    tol = TOL[precision]
+    for case in meta["cases"]:
+        tag = case["tag"]
+        out = m(enc, fns[case["mask"]](shape.traj_length, "cuda", case["idx"]))
+        assert list(out.keys()) == ["states", "actions", "rewards", "returns"]
+        for k in ("states", "rewards", "returns"):
+            assert out[k].shape == z[f"{tag}/{k}"].shape
+            assert rel(out[k], torch.from_numpy(z[f"{tag}/{k}"])) < tol, (tag, k)
+        assert rel(out["actions"].loc, torch.from_numpy(z[f"{tag}/act_mu"])) < tol, tag
+        assert rel(out["actions"].mean, torch.from_numpy(z[f"{tag}/act_mean"])) < tol, tag
+        assert rel(out["actions"].std, torch.from_numpy(z[f"{tag}/act_std"])) < 3.5 * tol, tag
+
+
+@pytest.mark.parametrize("env,batch", [("walker2d", 1), ("halfcheetah", 131), ("hopper", 300)])
+def test_forward_fp32_vs_fp64_oracle_ragged_batches(env, batch):
+    from oracle import mtm_oracle as mo, planner_oracle as po
+    shape = syn.shipped_shape(env)
+    m = _module(shape, "fp32", max_batch=512, chunk=128)  # 131 and 300 rows span several ragged chunks
+    sd64 = mo.to_torch(syn.make_state_dict(shape, 0), torch.float64)
+    traj = {k: torch.from_numpy(v) for k, v in syn.make_trajectories(shape, batch, 11).items()}
+    toks = {k: v.unsqueeze(2) for k, v in traj.items()}  # forward takes tokens: feed the raw values as if tokenised
+    mask = po.create_fd_mask(shape.traj_length, 3)
+    ref = mo.mtm_forward(sd64, {k: v.double() for k, v in toks.items()}, {k: torch.from_numpy(v) for k, v in mask.items()},
+                         shape.n_head, shape.n_enc_layer, shape.n_dec_layer)
+    out = m({k: v.cuda() for k, v in toks.items()}, {k: torch.from_numpy(v).cuda() for k, v in mask.items()})
+    for k in ("states", "rewards", "returns"):
+        assert rel(out[k], ref[k]) < TOL["fp32"], k
+    assert rel(out["actions"].loc, ref["actions"]["mu"]) < TOL["fp32"]
+    assert rel(out["actions"].std, ref["actions"]["std"]) < 3.5 * TOL["fp32"]
+
+
+def test_forward_scaled_model_bf16():
+    """BASELINE.json config 5 shapes: D=1024, 8 heads, 4+2 layers, T=16 (64 decoder tokens)."""
+    from oracle import mtm_oracle as mo, planner_oracle as po
+    shape = syn.scaled_shape("hopper")
+    m = _module(shape, "bf16", max_batch=16)
+    traj = {k: torch.from_numpy(v) for k, v in syn.make_trajectories(shape, 9, 11).items()}
+    toks = {k: v.unsqueeze(2) for k, v in traj.items()}
+    mask = po.create_fd_mask(shape.traj_length, 8)
+    ref = mo.mtm_forward(mo.to_torch(syn.make_state_dict(shape, 0), torch.float64), {k: v.double() for k, v in toks.items()},
+                         {k: torch.from_numpy(v) for k, v in mask.items()}, shape.n_head, shape.n_enc_layer, shape.n_dec_layer)
+    out = m({k: v.cuda() for k, v in toks.items()}, {k: torch.from_numpy(v).cuda() for k, v in mask.items()})
+    for k in ("states", "rewards", "returns"):
+        assert rel(out[k], ref[k]) < 2e-2, k  # twice the layers of the shipped model
+
+
+# ------------------------------------------------------------------------------------------------ planners
+def _learner(env, guidance, n_cand, temperature, precision, chunk=0, cls=None, **kw):
+    from m3pc_b200.learner import Learner
+    from m3pc_b200.mtm_model import omtmConfig
+    from m3pc_b200.tokenizers import manager_from_stats
+    shape = syn.shipped_shape(env)
+    cfg = SimpleNamespace(traj_length=shape.traj_length, device="cuda", action_samples=n_cand, discount=0.99, temperature=temperature,
+                          horizon=4, plan_guidance=guidance, lmbda=0.6)
+    mcfg = omtmConfig(n_embd=shape.n_embd, n_head=shape.n_head, n_enc_layer=shape.n_enc_layer, n_dec_layer=shape.n_dec_layer, dropout=0.1,
+                      norm="none", precision=precision, max_batch=n_cand, chunk=chunk)
+    om, os_ = syn.make_obs_norm(shape)
+    L = (cls or Learner)(cfg, None, shape.data_shapes, mcfg, None, om, os_, manager_from_stats(syn.make_tokenizer_stats(shape, 1)),
+                         {k: False for k in shape.data_shapes}, **kw)
+    L.mtm.load_state_dict({k: torch.from_numpy(v) for k, v in syn.make_state_dict(shape, 0).items()})
+    if hasattr(L, "iql"):
+        L.iql.qf.load_state_dict({k: torch.from_numpy(v) for k, v in syn.make_critic_state_dict(shape).items()})
+    return shape, L
+
+
+def _inject(L, case, z, shape):
+    tag, T, h = case["tag"], shape.traj_length, case["horizon"]
+    eps = torch.from_numpy(z[f"{tag}/eps"])
+    if not case["plan"]:
+        L.injected_noise = (eps[0, T - h, 0, :].contiguous().cuda(), None)
+    elif case["guidance"] == "noise_adding_lambda":
+        L.injected_noise = (eps.contiguous().cuda(), torch.from_numpy(z[f"{tag}/q"]).cuda())
+    else:
+        L.injected_noise = (eps[:, 0, T - h:, 0, :].contiguous().cuda(), torch.from_numpy(z[f"{tag}/q"]).cuda())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_planners_match_reference_golden(golden_dir, precision):
+    """Learner.action_sample against actions the REFERENCE produced on the same inputs and the same injected noise."""
+    z = np.load(os.path.join(golden_dir, "planner.npz"))
+    meta = json.loads(str(z["meta"]))
+    atol = 1e-4 if precision == "fp32" else 2e-2
+    for case in meta["cases"]:
+        shape, L = _learner(case["env"], case["guidance"], case["n_cand"], case["temperature"], precision)
+        _inject(L, case, z, shape)
+        hist = syn.make_history(shape, seed=case["hist_seed"], path_length=case["path_length"])
+        kw = dict(percentage=case["percentage"], plan=case["plan"], rtg=case["rtg"])
+        act = L.action_sample(hist, eval=case["eval"], **kw)
+        ref = z[f"{case['tag']}/action"]
+        assert tuple(act.shape) == ref.shape, (case["tag"], act.shape, ref.shape)
+        if case["eval"] or not case["plan"] or precision == "fp32":
+            np.testing.assert_allclose(act.cpu().numpy(), ref, rtol=0, atol=atol, err_msg=case["tag"])
+        if f"{case['tag']}/action_other" in z.files and (precision == "fp32" or not case["eval"]):
+            other = L.action_sample(hist, eval=not case["eval"], **{**kw, "rtg": 3.0 if case["rtg"] is None else case["rtg"]})
+            np.testing.assert_allclose(other.cpu().numpy(), z[f"{case['tag']}/action_other"], rtol=0, atol=atol, err_msg=case["tag"] + " other")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("env,guidance,temp,N,pl", [("hopper", "rtg_guiding", 0.01, 200, 50), ("hopper", "rtg_guiding", 0.01, 77, 1),
+                                                    ("walker2d", "critic_lambda_guiding", 1.0, 130, 50),
+                                                    ("halfcheetah", "noise_adding_lambda", 1.0, 96, 3)])
+def test_plan_internals_vs_fp64_oracle(precision, env, guidance, temp, N, pl):
+    """Candidates, per-candidate scores, selected indices and actions against the float64 oracle."""
+    from oracle import planner_oracle as po
+    shape, L = _learner(env, guidance, N, temp, precision)
+    need_c = guidance != "rtg_guiding"
+    P = po.from_synthetic(shape, syn.make_state_dict(shape, 0), syn.make_tokenizer_stats(shape, 1), dtype=torch.float64,
+                          critic_np=syn.make_critic_state_dict(shape) if need_c else None, obs_norm=syn.make_obs_norm(shape) if need_c else None,
+                          action_samples=N, temperature=temp, plan_guidance=guidance)
+    hist = syn.make_history(shape, seed=9, path_length=pl)
+    T, A = shape.traj_length, shape.act_dim
+    h = 4 if pl + 4 >= T else T - pl
+    rs = np.random.RandomState(3)
+    q = torch.from_numpy(rs.exponential(1.0, N))
+    if guidance == "noise_adding_lambda":
+        eps = torch.from_numpy(rs.randn(N, h, A))
+        L.injected_noise = (eps.float().cuda(), q.float().cuda())
+    else:
+        eps = torch.from_numpy(rs.randn(N, 1, T, 1, A))
+        L.injected_noise = (eps[:, 0, T - h:, 0, :].float().contiguous().cuda(), q.float().cuda())
+    L.debug_plans = True
+    ev = L.action_sample(hist, plan=True, eval=True, rtg=3.0)
+    dbg = L.last_plan_debug
+    _, ref = P.action_sample(hist, plan=True, eval=True, rtg=3.0, eps=eps, q=q)
+    tol = TOL[precision]
+    assert rel(dbg["candidates"], ref["candidates"]) < tol
+    J, Jr = dbg["expect_return"].double().cpu(), ref["expect_return"]
+    errJ = float((J - Jr).abs().max())
+    assert errJ <= tol * max(1.0, float(Jr.abs().max()))
+    assert rel(ev, ref["eval_action"]) < (1e-4 if precision == "fp32" else 2e-2)
+    # the device argmax / exponential-race sample are consistent with the device scores ...
+    amax, sidx = [int(v) for v in dbg["indices"].tolist()]
+    assert amax == int(torch.argmax(J))
+    w = torch.exp((J - J.max()) * temp)
+    assert sidx == int(torch.argmax(w / q))
+    # ... and bit-exact with the oracle wherever the score gap exceeds twice the score error
+    top2 = torch.topk(Jr, 2).values
+    if float(top2[0] - top2[1]) > 2 * errJ:
+        assert amax == int(ref["argmax"])
+    key = torch.exp((Jr - Jr.max()) * temp) / q
+    k2 = torch.topk(key, 2).values
+    if float(torch.log(k2[0]) - torch.log(k2[1])) > 2 * temp * 2 * errJ:
+        assert sidx == int(ref["sample_idx"])
+        assert rel(L.action_sample(hist, plan=True, eval=False, rtg=3.0)[0], ref["sample_action"][0]) < max(tol, 1e-4)
+
+
+def test_planner_method_signatures_and_shapes():
+    """rtg_guiding / critic_lambda_guiding / noise_adding_lambda / mtm_sampling called directly, as the reference allows."""
+    shape, L = _learner("walker2d", "critic_lambda_guiding", 64, 1.0, "bf16")
+    T, A = shape.traj_length, shape.act_dim
+    traj = {"states": torch.randn(1, T, shape.obs_dim, device="cuda"), "actions": torch.rand(1, T, A, device="cuda") * 2 - 1,
+            "rewards": torch.randn(1, T, 1, device="cuda"), "returns": torch.full((1, T, 1), 3.0, dtype=torch.float64, device="cuda")}
+    for fn, args in ((L.rtg_guiding, (traj, 4)), (L.critic_lambda_guiding, (traj, 4, 0.6)), (L.noise_adding_lambda, (traj, 4, 0.6))):
+        s, e = fn(*args)
+        assert s.shape == (1, A) and e.shape == (A,) and s.is_cuda and float(e.abs().max()) <= 1.0
+    s, e = L.mtm_sampling(traj, 4)
+    assert s.shape == (1, A) and e.shape == (1, A)
+    L.cfg.plan_guidance = "bogus"
+    with pytest.raises(AssertionError):
+        L.action_sample(syn.make_history(shape), plan=True, eval=True, rtg=1.0)
+
+
+# ------------------------------------------------------------------------------------------------ size-independent properties at BASELINE sizes
+@pytest.mark.parametrize("env,guidance,temp,N", [("walker2d", "critic_lambda_guiding", 1.0, 1024), ("halfcheetah", "rtg_guiding", 0.01, 16384)])
+def test_full_size_properties(env, guidance, temp, N):
+    """At BASELINE.json's sizes (configs[1], configs[2]): chunk invariance, candidate-permutation equivariance, shard-count
+    invariance of the merged result, and softmax sanity -- properties that do not need the (slow) oracle."""
+    from m3pc_b200 import dist as mdist
+    shape, L = _learner(env, guidance, N, temp, "bf16", chunk=1024)
+    eng = L._engine()
+    T, A, h = shape.traj_length, shape.act_dim, 4
+    g = torch.Generator(device="cuda").manual_seed(0)
+    ws, wa = torch.randn(T, shape.obs_dim, device="cuda", generator=g), torch.rand(T, A, device="cuda", generator=g) * 2 - 1
+    wr, wt = torch.randn(T, device="cuda", generator=g), torch.full((T,), 0.7, device="cuda")
+    eps, q = torch.randn(N, h, A, device="cuda", generator=g), torch.empty(N, device="cuda").exponential_(1.0, generator=g)
+    common = dict(guidance=guidance, horizon=h, win_states=ws, win_actions=wa, win_rewards=wr, win_returns_tok=wt, discount=0.99,
+                  temperature=temp, lmbda=0.6)
+
+    def run(engine, eps_, q_, n, off=0, **kw):
+        ev, sm, d = engine.plan(n_cand=n, eps=eps_, expq=q_, cand_offset=off, debug=True, **common, **kw)
+        return ev.clone(), sm.clone(), {k: v.clone() for k, v in d.items()}
+
+    ev, sm, d = run(eng, eps, q, N)
+    J = d["expect_return"]
+    assert torch.isfinite(J).all() and float(d["candidates"].abs().max()) < 1.0
+    assert int(d["indices"][0]) == int(torch.argmax(J))
+    w = torch.exp((J.double() - J.double().max()) * temp)
+    np.testing.assert_allclose(ev.cpu().numpy(), ((w[:, None] * d["candidates"][:, 0].double()).sum(0) / w.sum()).cpu().numpy(), atol=2e-5)
+    assert torch.equal(sm, d["candidates"][int(d["indices"][1]), 0])
+    # permutation equivariance: permuting the noise permutes the scores
+    perm = torch.randperm(N, device="cuda", generator=g)
+    ev_p, _, d_p = run(eng, eps[perm].contiguous(), q[perm].contiguous(), N)
+    assert torch.equal(d_p["expect_return"], J[perm])
+    np.testing.assert_allclose(ev_p.cpu().numpy(), ev.cpu().numpy(), atol=2e-5)
+    assert int(perm[int(d_p["indices"][0])]) == int(d["indices"][0])
+    # shard-count invariance: 4 shards + merge == one call
+    recs = []
+    for r in range(4):
+        lo, hi = mdist.shard_range(N, r, 4)
+        _, _, ds = run(eng, eps[lo:hi].contiguous(), q[lo:hi].contiguous(), hi - lo, off=lo)
+        assert torch.equal(ds["expect_return"], J[lo:hi])
+        recs.append(ds["partials"])
+    ev_m, sm_m, idx_m = eng.merge_partials(torch.stack(recs), temp)
+    np.testing.assert_allclose(ev_m.cpu().numpy(), ev.cpu().numpy(), atol=2e-5)
+    assert torch.equal(sm_m, sm) and idx_m.tolist() == d["indices"].tolist()
+    hev, hsm, hamax, hsidx = mdist.merge_partials_host(torch.stack(recs).cpu().numpy(), A, temp)
+    np.testing.assert_allclose(hev, ev.cpu().numpy(), atol=2e-5)
+    assert [hamax, hsidx] == d["indices"].tolist()
+    # chunk invariance: a different L2 blocking gives bit-identical scores
+    _, L2 = _learner(env, guidance, N, temp, "bf16", chunk=256)
+    _, _, d2 = run(L2._engine(), eps, q, N)
+    assert torch.equal(d2["expect_return"], J)
+
+
+def test_philox_noise_is_shard_invariant_and_seeded():
+    shape, L = _learner("hopper", "rtg_guiding", 512, 0.01, "bf16")
+    eng = L._engine()
+    T, A, h = shape.traj_length, shape.act_dim, 4
+    ws, wa, wr, wt = torch.randn(T, shape.obs_dim, device="cuda"), torch.rand(T, A, device="cuda"), torch.randn(T, device="cuda"), torch.ones(T, device="cuda")
+    common = dict(guidance="rtg_guiding", horizon=h, win_states=ws, win_actions=wa, win_rewards=wr, win_returns_tok=wt, discount=0.99,
+                  temperature=0.01, lmbda=0.6, debug=True)
+    _, _, d = eng.plan(n_cand=512, seed=5, **common)
+    c = d["candidates"].clone()
+    assert float(c.abs().max()) < 1.0 and float(c.std()) > 0.01
+    _, _, d1 = eng.plan(n_cand=256, seed=5, cand_offset=256, **common)
+    assert torch.equal(d1["candidates"], c[256:])          # noise is a function of the GLOBAL candidate id
+    _, _, d2 = eng.plan(n_cand=512, seed=6, **common)
+    assert not torch.equal(d2["candidates"], c)
+    z = torch.atanh(c.double().clamp(-0.999999, 0.999999))   # tanh^-1 recovers mu + std * eps: check eps ~ N(0,1) per (t, a)
+    zs = (z - z.mean(0)) / z.std(0)
+    assert abs(float(zs.mean())) < 0.05 and abs(float((zs ** 2).mean()) - 1.0) < 0.05 and abs(float((zs ** 3).mean())) < 0.3
+
+
+# ------------------------------------------------------------------------------------------------ zero-shot backward planners
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_zeroshot_matches_reference_golden(golden_dir, precision):
+    from m3pc_b200.zeroshot_learner import Learner as ZLearner
+    z = np.load(os.path.join(golden_dir, "zeroshot_hopper.npz"))
+    meta = json.loads(str(z["meta"]))
+    shape, L = _learner("hopper", "rtg_guiding", 1, 0.01, precision, cls=ZLearner, max_envs=8)
+    atol = 1e-4 if precision == "fp32" else 2e-2
+    T = shape.traj_length
+    for case in meta["cases"]:
+        tag = case["tag"]
+        hist = syn.make_history(shape, seed=case["hist_seed"], path_length=case["path_length"])
+        h = L._clamped_horizon(hist)
+        L.injected_eps = torch.from_numpy(z[f"{tag}/eps"])[0, T - h, 0, :].reshape(1, -1).contiguous().cuda()
+        fn = getattr(L, case["fn"])
+        np.testing.assert_allclose(fn(hist, eval=True, rtg=case["rtg"]).cpu().numpy(), z[f"{tag}/eval_action"], atol=atol, err_msg=tag)
+        np.testing.assert_allclose(fn(hist, eval=False, rtg=case["rtg"]).cpu().numpy(), z[f"{tag}/sample_action"], atol=atol, err_msg=tag)
+    L.action_piid_list_sample(syn.make_history(shape, seed=4, path_length=50), eval=True, rtg=2.5)
+    np.testing.assert_allclose(L.action_list[0].cpu().numpy(), z["piid_pl50/eval_action"], atol=atol)
+
+
+def test_zeroshot_batch_rows_equal_single_env_calls():
+    """Config-4 extension: E lock-step environments in one call; row e == the B=1 call on history e (bit-exact)."""
+    from m3pc_b200.zeroshot_learner import Learner as ZLearner
+    shape, L = _learner("hopper", "rtg_guiding", 1, 0.01, "bf16", cls=ZLearner, max_envs=37)
+    hists = [syn.make_history(shape, seed=20 + e, path_length=40 + e) for e in range(37)]
+    batch = L.action_piid_sample_batch(hists, eval=True, rtg=2.0).clone()
+    assert batch.shape == (37, shape.act_dim)
+    for e in (0, 5, 36):
+        single = L.action_piid_sample(hists[e], eval=True, rtg=2.0)
+        assert torch.equal(single[0], batch[e])
+    ids = L.action_id_sample_batch(hists, eval=True, rtg=2.0)
+    assert ids.shape == (37, shape.act_dim) and torch.isfinite(ids).all()

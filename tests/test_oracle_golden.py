@@ -116,3 +116,14 @@ def test_fp64_oracle_close_to_fp32(hopper):
         outs.append(mo.mtm_forward(sd, enc, masks, shape.n_head, shape.n_enc_layer, shape.n_dec_layer))
     for k in ("states", "rewards", "returns"):
         np.testing.assert_allclose(outs[0][k].numpy(), outs[1][k].numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_library_ops_equal_their_published_formulas():
+    torch.manual_seed(0)
+    x = torch.randn(7, 13, 512, dtype=torch.float64) * 2 + 0.3
+    w, b = torch.rand(512, dtype=torch.float64) + 0.5, torch.randn(512, dtype=torch.float64)
+    np.testing.assert_allclose(mo.layer_norm(x, w, b).numpy(), mo.layer_norm_plain(x, w, b).numpy(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(mo.gelu_erf(x).numpy(), mo.gelu_erf_plain(x).numpy(), rtol=1e-12, atol=1e-12)
+    q, k, v = (torch.randn(3, 4, 13, 128, dtype=torch.float64) for _ in range(3))
+    ref = torch.softmax(q @ k.transpose(-1, -2) / 128 ** 0.5, dim=-1) @ v
+    np.testing.assert_allclose(torch.nn.functional.scaled_dot_product_attention(q, k, v).numpy(), ref.numpy(), rtol=1e-10, atol=1e-12)
