@@ -341,8 +341,8 @@ def run_ours(args, w, shape, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="walker2d_critic_1024", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="env", choices=["env", "cand"])

@@ -1,9 +1,14 @@
-// K3: bidirectional multi-head attention for very short sequences (S = kept tokens <= 64, head_dim 128).
+// K3: bidirectional multi-head attention for very short sequences (S = tokens <= 64, head_dim 128).
 //
 // Reference call site: nn.MultiheadAttention inside nn.TransformerEncoderLayer (mtm_model.py:379-409):
-// softmax(q k^T / sqrt(128)) v, no mask, eval mode.  One CTA per (batch row, head): Q, K, V of that head
-// (S x 128 each) live in shared memory as fp32, the S x S score matrix never leaves the SM.
-// Activations are token-major: row = token * B + b, so a (b, head) slice is S rows of 128 contiguous values.
+// softmax(q k^T / sqrt(128)) v, no mask, eval mode.  Activations are token-major (row = token * B + b), so the
+// (b, head) slice of Q / K / V is S rows of 128 contiguous values.  The S x S score matrix never leaves the SM.
+//
+//   attention_mma_kernel  (bf16 mode)  one WARP per (batch row, head): Q, K, V staged in swizzled shared memory with
+//       cp.async, Q K^T and P V on mma.sync.m16n8k16 (bf16 in, fp32 accumulate) -- these contractions are a few
+//       hundred kFLOP per (b, head), far below what a tcgen05 tile (M = 128) could be filled with --, softmax in the
+//       accumulator registers with quad shuffles.
+//   attention_kernel      (fp32 mode)  one CTA per (b, head), fp32 everywhere (reference-grade path).
 #include "kernels.cuh"
 
 namespace m3pc {
@@ -13,6 +18,7 @@ constexpr int HD = 128;       // head dim
 constexpr int QS = HD + 1;    // padded row stride (floats) for conflict-free row-parallel reads
 constexpr int ATT_THREADS = 128;
 
+// ------------------------------------------------------------------------------------------------ fp32 path
 template <typename AT>
 __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AT* __restrict__ q_base, int q_ld, const AT* __restrict__ k_base,
                                                                 const AT* __restrict__ v_base, int kv_ld, AT* __restrict__ out, int out_ld,
@@ -25,7 +31,6 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AT* __rest
   const int b = blockIdx.x / n_head, h = blockIdx.x % n_head;
   const int tid = threadIdx.x;
 
-  // stage Q, K, V (4 elements per access)
   for (int idx = tid; idx < n_q * (HD / 4); idx += ATT_THREADS) {
     const int i = idx / (HD / 4), c = (idx % (HD / 4)) * 4;
     const float4 v = ld4(q_base + (static_cast<size_t>(i) * B + b) * q_ld + h * HD + c);
@@ -42,7 +47,6 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AT* __rest
   }
   __syncthreads();
 
-  // scores: consecutive threads take consecutive keys j of the same query i (Ks rows conflict-free, Qs broadcast)
   const float scale = 0.08838834764831845f;  // 1/sqrt(128)
   for (int pidx = tid; pidx < n_q * S; pidx += ATT_THREADS) {
     const int i = pidx / S, j = pidx - i * S;
@@ -60,7 +64,6 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AT* __rest
   }
   __syncthreads();
 
-  // softmax per query row: one warp per row
   const int lane = tid & 31, warp = tid >> 5;
   for (int i = warp; i < n_q; i += ATT_THREADS / 32) {
     float* pr = Ps + i * (S + 1);
@@ -79,7 +82,6 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AT* __rest
   }
   __syncthreads();
 
-  // out[i, d] = sum_j P[i, j] V[j, d]; thread = d
   for (int i = 0; i < n_q; ++i) {
     const float* pr = Ps + i * (S + 1);
     float acc = 0.f;
@@ -89,8 +91,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AT* __rest
 }
 
 template <typename AT>
-int launch_t(const AT* q, int q_ld, const AT* k, const AT* v, int kv_ld, AT* out, int out_ld, int B, int n_q, int S, int n_head,
-             cudaStream_t st) {
+int launch_simple(const AT* q, int q_ld, const AT* k, const AT* v, int kv_ld, AT* out, int out_ld, int B, int n_q, int S, int n_head,
+                  cudaStream_t st) {
   const size_t smem = (static_cast<size_t>(n_q) * QS + static_cast<size_t>(S) * QS + static_cast<size_t>(S) * HD +
                        static_cast<size_t>(n_q) * (S + 1)) * sizeof(float);
   M3PC_REQUIRE(smem <= 200 * 1024, "attention: sequence too long for the shared-memory resident kernel");
@@ -104,17 +106,185 @@ int launch_t(const AT* q, int q_ld, const AT* k, const AT* v, int kv_ld, AT* out
   return M3PC_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ bf16 tensor-core path
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+// byte offset of 16-byte chunk `c` (0..15) of row `r` in a [rows][256 B] tile, XOR-swizzled so that the 8 rows an
+// ldmatrix phase touches fall in 8 different 16-byte bank groups
+__device__ __forceinline__ uint32_t swz(int r, int c) { return static_cast<uint32_t>(r * 256 + ((c ^ (r & 7)) << 4)); }
+
+constexpr int MMA_WARPS = 4;  // (b, head) pairs per CTA
+
+// NT = S_pad / 16
+template <int NT>
+__global__ void __launch_bounds__(MMA_WARPS * 32) attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                                                                       int B, int S, int n_head) {
+  constexpr int SP = NT * 16;
+  extern __shared__ __align__(128) uint8_t smem_att[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.x * MMA_WARPS + warp;
+  if (pair >= B * n_head) return;
+  const int b = pair / n_head, h = pair - b * n_head;
+  const int D = n_head * HD, ld = 3 * D;
+  uint8_t* sQ = smem_att + static_cast<size_t>(warp) * 3 * SP * 256;
+  uint8_t* sK = sQ + SP * 256;
+  uint8_t* sV = sK + SP * 256;
+  const uint32_t uQ = smem_u32(sQ), uK = smem_u32(sK), uV = smem_u32(sV);
+
+  // ---- stage Q, K, V: 16 chunks of 16 bytes per row; pad rows are zeroed ----
+  for (int idx = lane; idx < SP * 16; idx += 32) {
+    const int r = idx >> 4, c = idx & 15;
+    const uint32_t off = swz(r, c);
+    if (r < S) {
+      const __nv_bfloat16* src = qkv + (static_cast<size_t>(r) * B + b) * ld + h * HD + c * 8;
+      cp_async16(uQ + off, src);
+      cp_async16(uK + off, src + D);
+      cp_async16(uV + off, src + 2 * D);
+    } else {
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(sQ + off) = z;
+      *reinterpret_cast<uint4*>(sK + off) = z;
+      *reinterpret_cast<uint4*>(sV + off) = z;
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+
+  const int g = lane >> 2, t = lane & 3;
+  const float sl2 = 0.08838834764831845f * 1.4426950408889634f;  // 1/sqrt(128) * log2(e)
+
+#pragma unroll 1
+  for (int mt = 0; mt < NT; ++mt) {
+    // ---- scores = Q[mt] K^T : 16 x SP, fp32 accumulators ----
+    float sc[2 * NT][4];
+#pragma unroll
+    for (int j = 0; j < 2 * NT; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; ++kk) {
+      uint32_t a[4];
+      {
+        const int r = mt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1), c = 2 * kk + (lane >> 4);
+        ldsm_x4(uQ + swz(r, c), a[0], a[1], a[2], a[3]);
+      }
+#pragma unroll
+      for (int jp = 0; jp < NT; ++jp) {  // two key tiles (16 keys) per ldmatrix.x4
+        uint32_t b0, b1, b2, b3;
+        const int r = jp * 16 + (lane & 7) + 8 * (lane >> 4), c = 2 * kk + ((lane >> 3) & 1);
+        ldsm_x4(uK + swz(r, c), b0, b1, b2, b3);
+        mma_bf16_16816(sc[2 * jp], a, b0, b1);
+        mma_bf16_16816(sc[2 * jp + 1], a, b2, b3);
+      }
+    }
+    // ---- softmax over keys (rows g and g+8 of this m-tile); pad keys masked ----
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 2 * NT; ++j) {
+      const int key = 8 * j + 2 * t;
+      if (key >= S) sc[j][0] = sc[j][2] = -INFINITY;
+      if (key + 1 >= S) sc[j][1] = sc[j][3] = -INFINITY;
+      m0 = fmaxf(m0, fmaxf(sc[j][0], sc[j][1]));
+      m1 = fmaxf(m1, fmaxf(sc[j][2], sc[j][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2 * NT; ++j) {
+      sc[j][0] = exp2f((sc[j][0] - m0) * sl2); sc[j][1] = exp2f((sc[j][1] - m0) * sl2);
+      sc[j][2] = exp2f((sc[j][2] - m1) * sl2); sc[j][3] = exp2f((sc[j][3] - m1) * sl2);
+      l0 += sc[j][0] + sc[j][1];
+      l1 += sc[j][2] + sc[j][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+
+    // ---- O = P V : 16 x 128 ----
+    float o[HD / 8][4];
+#pragma unroll
+    for (int n = 0; n < HD / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < NT; ++kk) {  // 16 keys per step; the score tiles (2kk, 2kk+1) are exactly the A fragment
+      uint32_t a[4];
+      a[0] = pack_bf16(sc[2 * kk][0] * inv0, sc[2 * kk][1] * inv0);
+      a[1] = pack_bf16(sc[2 * kk][2] * inv1, sc[2 * kk][3] * inv1);
+      a[2] = pack_bf16(sc[2 * kk + 1][0] * inv0, sc[2 * kk + 1][1] * inv0);
+      a[3] = pack_bf16(sc[2 * kk + 1][2] * inv1, sc[2 * kk + 1][3] * inv1);
+#pragma unroll
+      for (int np = 0; np < HD / 16; ++np) {  // two 8-wide dim tiles per ldmatrix.x4.trans
+        uint32_t b0, b1, b2, b3;
+        const int r = kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1), c = 2 * np + (lane >> 4);
+        ldsm_x4_t(uV + swz(r, c), b0, b1, b2, b3);
+        mma_bf16_16816(o[2 * np], a, b0, b1);
+        mma_bf16_16816(o[2 * np + 1], a, b2, b3);
+      }
+    }
+    // ---- stage O into this m-tile's (now dead) Q rows, same swizzle ----
+    __syncwarp();
+#pragma unroll
+    for (int n = 0; n < HD / 8; ++n) {
+      const int r0 = mt * 16 + g, r1 = r0 + 8;
+      *reinterpret_cast<uint32_t*>(sQ + swz(r0, n) + 4 * t) = pack_bf16(o[n][0], o[n][1]);
+      *reinterpret_cast<uint32_t*>(sQ + swz(r1, n) + 4 * t) = pack_bf16(o[n][2], o[n][3]);
+    }
+  }
+  __syncwarp();
+  // ---- coalesced copy-out: 16 lanes x 16 bytes per row ----
+  for (int idx = lane; idx < S * 16; idx += 32) {
+    const int r = idx >> 4, c = idx & 15;
+    const uint4 v = *reinterpret_cast<const uint4*>(sQ + swz(r, c));
+    *reinterpret_cast<uint4*>(out + (static_cast<size_t>(r) * B + b) * D + h * HD + c * 8) = v;
+  }
+}
+
+template <int NT>
+int launch_mma(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int n_head, cudaStream_t st) {
+  constexpr int smem = MMA_WARPS * 3 * NT * 16 * 256;
+  static bool configured = false;
+  if (!configured) {
+    M3PC_CHECK_CUDA(cudaFuncSetAttribute(attention_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  attention_mma_kernel<NT><<<ceil_div(B * n_head, MMA_WARPS), MMA_WARPS * 32, smem, st>>>(qkv, out, B, S, n_head);
+  M3PC_CHECK_LAUNCH();
+  return M3PC_OK;
+}
+
 }  // namespace
 
 int launch_attention(const void* qkv, void* out, int B, int S, int n_head, bool bf16, cudaStream_t st) {
-  M3PC_REQUIRE(B > 0 && S > 0 && S <= 128 && n_head > 0, "attention: bad shape");
+  M3PC_REQUIRE(B > 0 && S > 0 && S <= 64 && n_head > 0, "attention: bad shape (S must be <= 64)");
   const int D = n_head * HD;
   if (bf16) {
     const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(qkv);
-    return launch_t<__nv_bfloat16>(p, 3 * D, p + D, p + 2 * D, 3 * D, reinterpret_cast<__nv_bfloat16*>(out), D, B, S, S, n_head, st);
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+    switch ((S + 15) / 16) {
+      case 1: return launch_mma<1>(p, o, B, S, n_head, st);
+      case 2: return launch_mma<2>(p, o, B, S, n_head, st);
+      case 3: return launch_mma<3>(p, o, B, S, n_head, st);
+      default: return launch_mma<4>(p, o, B, S, n_head, st);
+    }
   }
   const float* p = reinterpret_cast<const float*>(qkv);
-  return launch_t<float>(p, 3 * D, p + D, p + 2 * D, 3 * D, reinterpret_cast<float*>(out), D, B, S, S, n_head, st);
+  return launch_simple<float>(p, 3 * D, p + D, p + 2 * D, 3 * D, reinterpret_cast<float*>(out), D, B, S, S, n_head, st);
 }
 
 }  // namespace m3pc

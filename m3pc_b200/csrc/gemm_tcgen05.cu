@@ -4,17 +4,20 @@
 // nn.TransformerEncoderLayer QKV / out-proj / linear1 / linear2 at omtm/models/mtm_model.py:379-409,
 // decoder_embed_dict at :646-661, output_head_dict[*].1 at :428-433).
 //
-// Structure (one 128 x BN output tile per CTA, warp-specialised):
-//   warp 0      TMA producer: cp.async.bulk.tensor 2-D loads of the A (128 x 64) and W (BN x 64) k-blocks
-//               into a STAGES-deep shared-memory ring (SWIZZLE_128B), completion on `full` mbarriers.
-//   warp 1      allocates TMEM, then one elected lane issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32,
-//               M=128, N=BN, K=16 per instruction) with smem descriptors; tcgen05.commit releases ring
-//               slots (`empty` mbarriers) and finally signals the accumulator (`acc_full`).
-//   warps 2..5  epilogue: tcgen05.ld the accumulator (each warp its own 32-lane TMEM quarter, one output
-//               row per thread), fused bias / per-token table / GELU(erf) / ReLU / residual add, stores.
-// Two CTAs fit per SM (<=100 KB smem, 128 TMEM columns each), so one CTA's epilogue overlaps the other's
-// main loop.  Both operands are K-major, which is the layout the activations (row-major (rows, K)) and
-// nn.Linear weights ((out, in) row-major) already have -- no transposes anywhere.
+// Persistent, warp-specialised, one CTA per SM (grid = min(tiles, #SM)); each CTA walks output tiles
+// (128 x BN, n fastest so concurrently running CTAs share A panels and the whole weight in L2):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D loads of the A (128 x 64) and W (BN x 64) k-blocks into a
+//               STAGES-deep shared-memory ring (SWIZZLE_128B), completion on `full` mbarriers.
+//   warp 1      allocates TMEM (2 accumulators of BN fp32 columns), then one lane issues tcgen05.mma
+//               (kind::f16, bf16 x bf16 -> fp32, M=128, N=BN, K=16 per instruction) from smem descriptors;
+//               tcgen05.commit releases ring slots (`empty`) and publishes the accumulator (`acc_full`).
+//   warps 2..9  epilogue, overlapped with the next tile's main loop through the second accumulator: tcgen05.ld
+//               (each warp its own 32-lane TMEM quarter and half of the columns), transpose through a padded
+//               smem tile so that global accesses are full 128-byte lines, fused bias / per-token table /
+//               GELU(erf) / ReLU / residual add, 16-byte stores; `acc_empty` hands the accumulator back.
+// Both operands are K-major, which is the layout the activations (row-major (rows, K)) and nn.Linear weights
+// ((out, in) row-major) already have -- no transposes anywhere.  Rows beyond M are zero-filled by TMA and masked
+// in the epilogue, so M is arbitrary (ragged candidate counts, B = 1).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -26,12 +29,15 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one SWIZZLE_128B atom row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 32 * (2 + NUM_EPI_WARPS);
+constexpr int XPOSE_LD = 36;  // floats per staged row: 128-bit accesses are bank-conflict free both row- and column-wise
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode_tiled = nullptr;
+int g_num_sms = 0;
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -41,6 +47,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t addr = smem_u32(bar);
@@ -129,28 +138,37 @@ struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kXposeOffset = STAGES * kStageBytes;
+  static constexpr int kXposeBytesPerWarp = 32 * XPOSE_LD * 4;
+  static constexpr int kBarOffset = kXposeOffset + NUM_EPI_WARPS * kXposeBytesPerWarp;
   static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
 };
 
+__device__ __forceinline__ float apply_act(float v, bool do_gelu, bool do_relu) {
+  if (do_gelu) v = gelu_erf(v);
+  if (do_relu) v = fmaxf(v, 0.0f);
+  return v;
+}
+
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                                                                 const __grid_constant__ CUtensorMap tmap_w,
-                                                                 void* __restrict__ C, int M, int N, int K, EpiParams ep) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                                    const __grid_constant__ CUtensorMap tmap_w,
+                                                                    void* __restrict__ C, int M, int N, int K, EpiParams ep) {
   using L = SmemLayout<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* acc_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  uint64_t* acc_full = empty_bar + STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * BM;
   const int num_kb = K / BK;
+  const int n_tiles = N / BN;
+  const int total_tiles = n_tiles * ((M + BM - 1) / BM);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -160,12 +178,15 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_kernel(const __grid_co
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(acc_bar, 1);
+    mbar_init(&acc_full[0], 1);
+    mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_empty[0], NUM_EPI_WARPS);
+    mbar_init(&acc_empty[1], NUM_EPI_WARPS);
     fence_barrier_init();
     fence_proxy_async();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -175,106 +196,146 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_kernel(const __grid_co
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], L::kStageBytes);
-        uint8_t* sa = smem + s * L::kStageBytes;
-        tma_load_2d(sa, &tmap_a, &full_bar[s], kb * BK, m0);
-        tma_load_2d(sa + L::kABytes, &tmap_w, &full_bar[s], kb * BK, n0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], L::kStageBytes);
+          uint8_t* sa = smem + s * L::kStageBytes;
+          tma_load_2d(sa, &tmap_a, &full_bar[s], kb * BK, m0);
+          tma_load_2d(sa + L::kABytes, &tmap_w, &full_bar[s], kb * BK, n0);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int a = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&acc_empty[a], aph ^ 1);  // epilogue has drained this accumulator (first use passes immediately)
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
-        const uint32_t b_addr = a_addr + L::kABytes;
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(a * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+          const uint32_t b_addr = a_addr + L::kABytes;
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advance inside the 128-byte swizzle atom: +32 bytes per K=16 step
-          umma_bf16(tmem_base, make_smem_desc(a_addr + k * UMMA_K * 2), make_smem_desc(b_addr + k * UMMA_K * 2), idesc,
-                    (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance inside the 128-byte swizzle atom: +32 bytes per K=16 step
+            umma_bf16(tmem_d, make_smem_desc(a_addr + k * UMMA_K * 2), make_smem_desc(b_addr + k * UMMA_K * 2), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // slot reusable once these MMAs have read it
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&empty_bar[s]);  // slot reusable once these MMAs have read it
+        umma_commit(&acc_full[a]);  // accumulator complete
       }
-      umma_commit(acc_bar);  // accumulator complete
     }
   } else {
-    // ---- epilogue: TMEM -> registers -> global ----
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
-    const int row = m0 + quarter * 32 + lane;
-    mbar_wait(acc_bar, 0);
-    tc_fence_after();
-    const bool row_ok = row < M;
+    // ---- epilogue warps: TMEM -> registers -> smem transpose -> coalesced global ----
+    const int ew = warp - 2;
+    const int quarter = warp & 3;       // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
+    const int half = ew >> 2;           // which half of the BN columns
+    float* xp = reinterpret_cast<float*>(smem + L::kXposeOffset + ew * L::kXposeBytesPerWarp);
     const bool do_gelu = ep.flags & EPI_GELU, do_relu = ep.flags & EPI_RELU, do_res = ep.flags & EPI_RESIDUAL;
     const bool out_f32 = do_res || (ep.flags & EPI_OUT_F32);
-    const float* trow = (ep.table != nullptr && row_ok) ? ep.table + static_cast<size_t>(row / ep.rows_per_group) * N : nullptr;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      const int a = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&acc_full[a], aph);
+      tc_fence_after();
+      const int row_base = m0 + quarter * 32;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0), r);
-      tmem_ld_wait();
-      if (row_ok) {
-        const int col0 = n0 + c0;
-        float v[32];
+      for (int c = 0; c < BN / 2; c += 32) {
+        const int col_in_tile = half * (BN / 2) + c;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(a * BN + col_in_tile), r);
+        tmem_ld_wait();
+        // row-per-lane -> staging tile (lane = row)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (ep.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
-            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-          }
-        }
-        if (trow != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 t4 = __ldg(reinterpret_cast<const float4*>(trow + col0 + j));
-            v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
-          }
-        }
-        if (do_gelu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        }
-        if (do_relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-        }
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(xp + lane * XPOSE_LD + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        __syncwarp();
+        const int col0 = n0 + col_in_tile;
         if (out_f32) {
-          float* crow = reinterpret_cast<float*>(C) + static_cast<size_t>(row) * N + col0;
+          // lane -> 4 consecutive columns, 8 lanes per row, 4 rows per pass
+          const int cc = 4 * (lane & 7);
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ep.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + cc));
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (do_res) {
-              float4 x = *reinterpret_cast<const float4*>(crow + j);
-              o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + (lane >> 3);
+            const int row = row_base + rr;
+            float4 v = *reinterpret_cast<const float4*>(xp + rr * XPOSE_LD + cc);
+            if (row < M) {
+              v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+              if (ep.table != nullptr) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(ep.table + static_cast<size_t>(row / ep.rows_per_group) * N + col0 + cc));
+                v.x += t4.x; v.y += t4.y; v.z += t4.z; v.w += t4.w;
+              }
+              v.x = apply_act(v.x, do_gelu, do_relu); v.y = apply_act(v.y, do_gelu, do_relu);
+              v.z = apply_act(v.z, do_gelu, do_relu); v.w = apply_act(v.w, do_gelu, do_relu);
+              float* cp = reinterpret_cast<float*>(C) + static_cast<size_t>(row) * N + col0 + cc;
+              if (do_res) {
+                const float4 x = *reinterpret_cast<const float4*>(cp);
+                v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+              }
+              *reinterpret_cast<float4*>(cp) = v;
             }
-            *reinterpret_cast<float4*>(crow + j) = o;
           }
         } else {
-          __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(C) + static_cast<size_t>(row) * N + col0;
+          // lane -> 8 consecutive columns, 4 lanes per row, 8 rows per pass
+          const int cc = 8 * (lane & 3);
+          float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (ep.bias != nullptr) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + cc));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + cc + 4));
+            bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+          }
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 o;
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-            __nv_bfloat162 p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-            __nv_bfloat162 p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-            o.x = *reinterpret_cast<uint32_t*>(&p0);
-            o.y = *reinterpret_cast<uint32_t*>(&p1);
-            o.z = *reinterpret_cast<uint32_t*>(&p2);
-            o.w = *reinterpret_cast<uint32_t*>(&p3);
-            *reinterpret_cast<uint4*>(crow + j) = o;
+          for (int i = 0; i < 4; ++i) {
+            const int rr = 8 * i + (lane >> 2);
+            const int row = row_base + rr;
+            const float4 v0 = *reinterpret_cast<const float4*>(xp + rr * XPOSE_LD + cc);
+            const float4 v1 = *reinterpret_cast<const float4*>(xp + rr * XPOSE_LD + cc + 4);
+            if (row < M) {
+              float v[8] = {v0.x + bb[0], v0.y + bb[1], v0.z + bb[2], v0.w + bb[3], v1.x + bb[4], v1.y + bb[5], v1.z + bb[6], v1.w + bb[7]};
+              if (ep.table != nullptr) {
+                const float* tr = ep.table + static_cast<size_t>(row / ep.rows_per_group) * N + col0 + cc;
+                const float4 t0 = __ldg(reinterpret_cast<const float4*>(tr));
+                const float4 t1 = __ldg(reinterpret_cast<const float4*>(tr + 4));
+                v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w; v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], do_gelu, do_relu);
+              uint4 o;
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]);
+              __nv_bfloat162 p1 = __floats2bfloat162_rn(v[2], v[3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]);
+              __nv_bfloat162 p3 = __floats2bfloat162_rn(v[6], v[7]);
+              o.x = *reinterpret_cast<uint32_t*>(&p0);
+              o.y = *reinterpret_cast<uint32_t*>(&p1);
+              o.z = *reinterpret_cast<uint32_t*>(&p2);
+              o.w = *reinterpret_cast<uint32_t*>(&p3);
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(C) + static_cast<size_t>(row) * N + col0 + cc) = o;
+            }
           }
         }
+        __syncwarp();  // staging tile is reused by the next chunk
       }
+      // all of this warp's TMEM reads are complete (tcgen05.wait::ld above): hand the accumulator back
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(&acc_empty[a]);
     }
   }
 
@@ -282,7 +343,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_kernel(const __grid_co
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
   }
 }
 
@@ -305,6 +366,7 @@ int make_tmap(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, u
 template <int BN, int STAGES>
 int launch(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, int M, int N, int K, const GemmEpilogue& epi, cudaStream_t st) {
   using L = SmemLayout<BN, STAGES>;
+  static_assert(L::kTotal <= 227 * 1024, "shared memory budget exceeded");
   static bool configured = false;
   if (!configured) {
     M3PC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -314,8 +376,8 @@ int launch(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, int M, int N
   M3PC_TRY(make_tmap(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), BM));
   M3PC_TRY(make_tmap(&tw, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), BN));
   EpiParams ep{epi.bias, epi.table, epi.rows_per_group > 0 ? epi.rows_per_group : 1, epi.flags};
-  dim3 grid(N / BN, ceil_div(M, BM));
-  gemm_bf16_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::kTotal, st>>>(ta, tw, C, M, N, K, ep);
+  const int tiles = (N / BN) * ceil_div(M, BM);
+  gemm_bf16_kernel<BN, STAGES><<<std::min(tiles, g_num_sms), GEMM_THREADS, L::kTotal, st>>>(ta, tw, C, M, N, K, ep);
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
 }
@@ -331,6 +393,9 @@ int gemm_init_driver_api() {
     set_error("cuTensorMapEncodeTiled not available from the CUDA driver");
     return M3PC_ERR_CUDA;
   }
+  int dev = 0;
+  M3PC_CHECK_CUDA(cudaGetDevice(&dev));
+  M3PC_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
   return M3PC_OK;
 }
@@ -344,7 +409,14 @@ int gemm_bf16_tcgen05(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, i
                    (reinterpret_cast<uintptr_t>(C) & 15) == 0,
                "gemm_bf16: operands must be 16-byte aligned");
   M3PC_TRY(gemm_init_driver_api());
-  return launch<128, 3>(A, W, C, M, N, K, epi, st);
+  // tile width: minimise (rounds of the persistent grid) x (cost of one tile ~ BN); ties go to the wide tile (less L2 traffic)
+  const int m_tiles = ceil_div(M, BM);
+  if (N % 256 == 0) {
+    const long cost256 = static_cast<long>(ceil_div((N / 256) * m_tiles, g_num_sms)) * 256;
+    const long cost128 = static_cast<long>(ceil_div((N / 128) * m_tiles, g_num_sms)) * 128;
+    if (cost256 <= cost128) return launch<256, 3>(A, W, C, M, N, K, epi, st);
+  }
+  return launch<128, 4>(A, W, C, M, N, K, epi, st);
 }
 
 }  // namespace m3pc
