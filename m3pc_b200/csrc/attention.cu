@@ -1,8 +1,13 @@
-// K3: bidirectional multi-head attention for very short sequences (S = tokens <= 64, head_dim 128).
+// K3: bidirectional multi-head attention for very short sequences (<= 64 tokens, head_dim 128).
 //
 // Reference call site: nn.MultiheadAttention inside nn.TransformerEncoderLayer (mtm_model.py:379-409):
 // softmax(q k^T / sqrt(128)) v, no mask, eval mode.  Activations are token-major (row = token * B + b), so the
-// (b, head) slice of Q / K / V is S rows of 128 contiguous values.  The S x S score matrix never leaves the SM.
+// (b, head) slice of a token is 128 contiguous values.  The score matrix never leaves the SM.
+//
+// Both kernels take the token-gather form (AttnParams): every query / key / value token carries its own source
+// pointer and batch stride.  Plain self-attention is the special case where all tokens point into one qkv matrix;
+// the planner's decoder uses the general case: queries only for the rows the planner consumes, keys / values split
+// between per-candidate rows and batch-constant mask-token rows (bstride 0).
 //
 //   attention_mma_kernel  (bf16 mode)  one WARP per (batch row, head): Q, K, V staged in swizzled shared memory with
 //       cp.async, Q K^T and P V on mma.sync.m16n8k16 (bf16 in, fp32 accumulate) -- these contractions are a few
@@ -19,31 +24,28 @@ constexpr int QS = HD + 1;    // padded row stride (floats) for conflict-free ro
 constexpr int ATT_THREADS = 128;
 
 // ------------------------------------------------------------------------------------------------ fp32 path
-template <typename AT>
-__global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AT* __restrict__ q_base, int q_ld, const AT* __restrict__ k_base,
-                                                                const AT* __restrict__ v_base, int kv_ld, AT* __restrict__ out, int out_ld,
-                                                                int B, int n_q, int S, int n_head) {
+__global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ float sm[];
+  const int n_q = p.n_q, S = p.n_kv, B = p.B;
   float* Vs = sm;                 // S x HD (first: keeps its float4 stores 16-byte aligned)
   float* Qs = Vs + S * HD;        // n_q x QS
   float* Ks = Qs + n_q * QS;      // S x QS
   float* Ps = Ks + S * QS;        // n_q x (S + 1)
-  const int b = blockIdx.x / n_head, h = blockIdx.x % n_head;
+  const int b = blockIdx.x / p.n_head, h = blockIdx.x % p.n_head;
   const int tid = threadIdx.x;
 
   for (int idx = tid; idx < n_q * (HD / 4); idx += ATT_THREADS) {
     const int i = idx / (HD / 4), c = (idx % (HD / 4)) * 4;
-    const float4 v = ld4(q_base + (static_cast<size_t>(i) * B + b) * q_ld + h * HD + c);
+    const float4 v = ld4(reinterpret_cast<const float*>(p.q[i].ptr) + static_cast<size_t>(b) * p.q[i].bstride + h * HD + c);
     float* d = Qs + i * QS + c;
     d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
   }
   for (int idx = tid; idx < S * (HD / 4); idx += ATT_THREADS) {
     const int j = idx / (HD / 4), c = (idx % (HD / 4)) * 4;
-    const size_t row = (static_cast<size_t>(j) * B + b) * kv_ld + h * HD + c;
-    const float4 kv = ld4(k_base + row);
+    const float4 kv = ld4(reinterpret_cast<const float*>(p.k[j].ptr) + static_cast<size_t>(b) * p.k[j].bstride + h * HD + c);
     float* d = Ks + j * QS + c;
     d[0] = kv.x; d[1] = kv.y; d[2] = kv.z; d[3] = kv.w;
-    *reinterpret_cast<float4*>(Vs + j * HD + c) = ld4(v_base + row);
+    *reinterpret_cast<float4*>(Vs + j * HD + c) = ld4(reinterpret_cast<const float*>(p.v[j].ptr) + static_cast<size_t>(b) * p.v[j].bstride + h * HD + c);
   }
   __syncthreads();
 
@@ -82,26 +84,26 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AT* __rest
   }
   __syncthreads();
 
+  float* out = reinterpret_cast<float*>(p.out);
+  const int D = p.n_head * HD;
   for (int i = 0; i < n_q; ++i) {
     const float* pr = Ps + i * (S + 1);
     float acc = 0.f;
     for (int j = 0; j < S; ++j) acc = fmaf(pr[j], Vs[j * HD + tid], acc);
-    Act<AT>::st(out + (static_cast<size_t>(i) * B + b) * out_ld + h * HD + tid, acc);
+    out[(static_cast<size_t>(i) * B + b) * D + h * HD + tid] = acc;
   }
 }
 
-template <typename AT>
-int launch_simple(const AT* q, int q_ld, const AT* k, const AT* v, int kv_ld, AT* out, int out_ld, int B, int n_q, int S, int n_head,
-                  cudaStream_t st) {
-  const size_t smem = (static_cast<size_t>(n_q) * QS + static_cast<size_t>(S) * QS + static_cast<size_t>(S) * HD +
-                       static_cast<size_t>(n_q) * (S + 1)) * sizeof(float);
+int launch_simple(const AttnParams& p, cudaStream_t st) {
+  const size_t smem = (static_cast<size_t>(p.n_q) * QS + static_cast<size_t>(p.n_kv) * QS + static_cast<size_t>(p.n_kv) * HD +
+                       static_cast<size_t>(p.n_q) * (p.n_kv + 1)) * sizeof(float);
   M3PC_REQUIRE(smem <= 200 * 1024, "attention: sequence too long for the shared-memory resident kernel");
   static size_t configured = 0;
   if (smem > configured) {
-    M3PC_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    M3PC_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
   }
-  attention_kernel<AT><<<B * n_head, ATT_THREADS, smem, st>>>(q, q_ld, k, v, kv_ld, out, out_ld, B, n_q, S, n_head);
+  attention_kernel<<<p.B * p.n_head, ATT_THREADS, smem, st>>>(p);
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
 }
@@ -132,36 +134,38 @@ __device__ __forceinline__ uint32_t swz(int r, int c) { return static_cast<uint3
 
 constexpr int MMA_WARPS = 4;  // (b, head) pairs per CTA
 
-// NT = S_pad / 16
-template <int NT>
-__global__ void __launch_bounds__(MMA_WARPS * 32) attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                                                                       int B, int S, int n_head) {
-  constexpr int SP = NT * 16;
+// NTQ = ceil(n_q / 16) query tiles, NTK = ceil(n_kv / 16) key tiles
+template <int NTQ, int NTK>
+__global__ void __launch_bounds__(MMA_WARPS * 32) attention_mma_kernel(const __grid_constant__ AttnParams p) {
+  constexpr int QP = NTQ * 16, KP = NTK * 16;
   extern __shared__ __align__(128) uint8_t smem_att[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = blockIdx.x * MMA_WARPS + warp;
-  if (pair >= B * n_head) return;
-  const int b = pair / n_head, h = pair - b * n_head;
-  const int D = n_head * HD, ld = 3 * D;
-  uint8_t* sQ = smem_att + static_cast<size_t>(warp) * 3 * SP * 256;
-  uint8_t* sK = sQ + SP * 256;
-  uint8_t* sV = sK + SP * 256;
+  if (pair >= p.B * p.n_head) return;
+  const int b = pair / p.n_head, h = pair - b * p.n_head;
+  const int n_q = p.n_q, S = p.n_kv;
+  uint8_t* sQ = smem_att + static_cast<size_t>(warp) * (QP + 2 * KP) * 256;
+  uint8_t* sK = sQ + QP * 256;
+  uint8_t* sV = sK + KP * 256;
   const uint32_t uQ = smem_u32(sQ), uK = smem_u32(sK), uV = smem_u32(sV);
 
   // ---- stage Q, K, V: 16 chunks of 16 bytes per row; pad rows are zeroed ----
-  for (int idx = lane; idx < SP * 16; idx += 32) {
+  for (int idx = lane; idx < QP * 16; idx += 32) {
+    const int r = idx >> 4, c = idx & 15;
+    if (r < n_q)
+      cp_async16(uQ + swz(r, c), reinterpret_cast<const __nv_bfloat16*>(p.q[r].ptr) + static_cast<size_t>(b) * p.q[r].bstride + h * HD + c * 8);
+    else
+      *reinterpret_cast<uint4*>(sQ + swz(r, c)) = make_uint4(0, 0, 0, 0);
+  }
+  for (int idx = lane; idx < KP * 16; idx += 32) {
     const int r = idx >> 4, c = idx & 15;
     const uint32_t off = swz(r, c);
     if (r < S) {
-      const __nv_bfloat16* src = qkv + (static_cast<size_t>(r) * B + b) * ld + h * HD + c * 8;
-      cp_async16(uQ + off, src);
-      cp_async16(uK + off, src + D);
-      cp_async16(uV + off, src + 2 * D);
+      cp_async16(uK + off, reinterpret_cast<const __nv_bfloat16*>(p.k[r].ptr) + static_cast<size_t>(b) * p.k[r].bstride + h * HD + c * 8);
+      cp_async16(uV + off, reinterpret_cast<const __nv_bfloat16*>(p.v[r].ptr) + static_cast<size_t>(b) * p.v[r].bstride + h * HD + c * 8);
     } else {
-      const uint4 z = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(sQ + off) = z;
-      *reinterpret_cast<uint4*>(sK + off) = z;
-      *reinterpret_cast<uint4*>(sV + off) = z;
+      *reinterpret_cast<uint4*>(sK + off) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(sV + off) = make_uint4(0, 0, 0, 0);
     }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
@@ -172,11 +176,11 @@ __global__ void __launch_bounds__(MMA_WARPS * 32) attention_mma_kernel(const __n
   const float sl2 = 0.08838834764831845f * 1.4426950408889634f;  // 1/sqrt(128) * log2(e)
 
 #pragma unroll 1
-  for (int mt = 0; mt < NT; ++mt) {
-    // ---- scores = Q[mt] K^T : 16 x SP, fp32 accumulators ----
-    float sc[2 * NT][4];
+  for (int mt = 0; mt < NTQ; ++mt) {
+    // ---- scores = Q[mt] K^T : 16 x KP, fp32 accumulators ----
+    float sc[2 * NTK][4];
 #pragma unroll
-    for (int j = 0; j < 2 * NT; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+    for (int j = 0; j < 2 * NTK; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < HD / 16; ++kk) {
       uint32_t a[4];
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(MMA_WARPS * 32) attention_mma_kernel(const __n
         ldsm_x4(uQ + swz(r, c), a[0], a[1], a[2], a[3]);
       }
 #pragma unroll
-      for (int jp = 0; jp < NT; ++jp) {  // two key tiles (16 keys) per ldmatrix.x4
+      for (int jp = 0; jp < NTK; ++jp) {  // two key tiles (16 keys) per ldmatrix.x4
         uint32_t b0, b1, b2, b3;
         const int r = jp * 16 + (lane & 7) + 8 * (lane >> 4), c = 2 * kk + ((lane >> 3) & 1);
         ldsm_x4(uK + swz(r, c), b0, b1, b2, b3);
@@ -196,7 +200,7 @@ __global__ void __launch_bounds__(MMA_WARPS * 32) attention_mma_kernel(const __n
     // ---- softmax over keys (rows g and g+8 of this m-tile); pad keys masked ----
     float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < 2 * NT; ++j) {
+    for (int j = 0; j < 2 * NTK; ++j) {
       const int key = 8 * j + 2 * t;
       if (key >= S) sc[j][0] = sc[j][2] = -INFINITY;
       if (key + 1 >= S) sc[j][1] = sc[j][3] = -INFINITY;
@@ -207,7 +211,7 @@ __global__ void __launch_bounds__(MMA_WARPS * 32) attention_mma_kernel(const __n
     m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
     float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 2 * NT; ++j) {
+    for (int j = 0; j < 2 * NTK; ++j) {
       sc[j][0] = exp2f((sc[j][0] - m0) * sl2); sc[j][1] = exp2f((sc[j][1] - m0) * sl2);
       sc[j][2] = exp2f((sc[j][2] - m1) * sl2); sc[j][3] = exp2f((sc[j][3] - m1) * sl2);
       l0 += sc[j][0] + sc[j][1];
@@ -222,7 +226,7 @@ __global__ void __launch_bounds__(MMA_WARPS * 32) attention_mma_kernel(const __n
 #pragma unroll
     for (int n = 0; n < HD / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
 #pragma unroll
-    for (int kk = 0; kk < NT; ++kk) {  // 16 keys per step; the score tiles (2kk, 2kk+1) are exactly the A fragment
+    for (int kk = 0; kk < NTK; ++kk) {  // 16 keys per step; the score tiles (2kk, 2kk+1) are exactly the A fragment
       uint32_t a[4];
       a[0] = pack_bf16(sc[2 * kk][0] * inv0, sc[2 * kk][1] * inv0);
       a[1] = pack_bf16(sc[2 * kk][2] * inv1, sc[2 * kk][3] * inv1);
@@ -248,43 +252,67 @@ __global__ void __launch_bounds__(MMA_WARPS * 32) attention_mma_kernel(const __n
   }
   __syncwarp();
   // ---- coalesced copy-out: 16 lanes x 16 bytes per row ----
-  for (int idx = lane; idx < S * 16; idx += 32) {
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+  const int D = p.n_head * HD;
+  for (int idx = lane; idx < n_q * 16; idx += 32) {
     const int r = idx >> 4, c = idx & 15;
     const uint4 v = *reinterpret_cast<const uint4*>(sQ + swz(r, c));
-    *reinterpret_cast<uint4*>(out + (static_cast<size_t>(r) * B + b) * D + h * HD + c * 8) = v;
+    *reinterpret_cast<uint4*>(out + (static_cast<size_t>(r) * p.B + b) * D + h * HD + c * 8) = v;
   }
 }
 
-template <int NT>
-int launch_mma(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int n_head, cudaStream_t st) {
-  constexpr int smem = MMA_WARPS * 3 * NT * 16 * 256;
+template <int NTQ, int NTK>
+int launch_mma(const AttnParams& p, cudaStream_t st) {
+  constexpr int smem = MMA_WARPS * (NTQ + 2 * NTK) * 16 * 256;
   static bool configured = false;
   if (!configured) {
-    M3PC_CHECK_CUDA(cudaFuncSetAttribute(attention_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    M3PC_CHECK_CUDA(cudaFuncSetAttribute(attention_mma_kernel<NTQ, NTK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  attention_mma_kernel<NT><<<ceil_div(B * n_head, MMA_WARPS), MMA_WARPS * 32, smem, st>>>(qkv, out, B, S, n_head);
+  attention_mma_kernel<NTQ, NTK><<<ceil_div(p.B * p.n_head, MMA_WARPS), MMA_WARPS * 32, smem, st>>>(p);
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
 }
 
+template <int NTK>
+int dispatch_q(const AttnParams& p, cudaStream_t st) {
+  switch ((p.n_q + 15) / 16) {
+    case 1: return launch_mma<1, NTK>(p, st);
+    case 2: return launch_mma<2, NTK>(p, st);
+    case 3: return launch_mma<3, NTK>(p, st);
+    default: return launch_mma<4, NTK>(p, st);
+  }
+}
+
 }  // namespace
 
-int launch_attention(const void* qkv, void* out, int B, int S, int n_head, bool bf16, cudaStream_t st) {
-  M3PC_REQUIRE(B > 0 && S > 0 && S <= 64 && n_head > 0, "attention: bad shape (S must be <= 64)");
-  const int D = n_head * HD;
-  if (bf16) {
-    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(qkv);
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-    switch ((S + 15) / 16) {
-      case 1: return launch_mma<1>(p, o, B, S, n_head, st);
-      case 2: return launch_mma<2>(p, o, B, S, n_head, st);
-      case 3: return launch_mma<3>(p, o, B, S, n_head, st);
-      default: return launch_mma<4>(p, o, B, S, n_head, st);
-    }
+int launch_attention_gather(const AttnParams& p, bool bf16, cudaStream_t st) {
+  M3PC_REQUIRE(p.B > 0 && p.n_q > 0 && p.n_kv > 0 && p.n_q <= MAX_TOK && p.n_kv <= MAX_TOK && p.n_head > 0, "attention: bad shape (<= 64 tokens)");
+  if (!bf16) return launch_simple(p, st);
+  switch ((p.n_kv + 15) / 16) {
+    case 1: return dispatch_q<1>(p, st);
+    case 2: return dispatch_q<2>(p, st);
+    case 3: return dispatch_q<3>(p, st);
+    default: return dispatch_q<4>(p, st);
   }
-  const float* p = reinterpret_cast<const float*>(qkv);
-  return launch_simple<float>(p, 3 * D, p + D, p + 2 * D, 3 * D, reinterpret_cast<float*>(out), D, B, S, S, n_head, st);
+}
+
+int launch_attention(const void* qkv, void* out, int B, int S, int n_head, bool bf16, cudaStream_t st) {
+  M3PC_REQUIRE(B > 0 && S > 0 && S <= MAX_TOK && n_head > 0, "attention: bad shape (S must be <= 64)");
+  const int D = n_head * HD;
+  const size_t es = bf16 ? 2 : 4;
+  AttnParams p{};
+  p.n_q = p.n_kv = S;
+  p.B = B;
+  p.n_head = n_head;
+  p.out = out;
+  for (int s = 0; s < S; ++s) {
+    const char* row = reinterpret_cast<const char*>(qkv) + static_cast<size_t>(s) * B * 3 * D * es;
+    p.q[s] = AttnTok{row, 3 * D};
+    p.k[s] = AttnTok{row + D * es, 3 * D};
+    p.v[s] = AttnTok{row + 2 * D * es, 3 * D};
+  }
+  return launch_attention_gather(p, bf16, st);
 }
 
 }  // namespace m3pc

@@ -107,6 +107,25 @@ __device__ __forceinline__ float warp_max(float v) {
 // nn.GELU() (erf form), evaluated in fp32.
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// Branch-free GELU(erf) for the bf16 tensor-core epilogues: erf(a) = 1 - (1 + a1 a + ... + a6 a^6)^-16 for a >= 0
+// (Abramowitz & Stegun 7.1.28, |error| <= 3e-7, far below the bf16 rounding of the result).  ~17 instructions, one MUFU,
+// no divergence -- erff() costs 25-40 with a data-dependent branch, which made the FFN1 epilogue the bottleneck.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float a = fminf(fabsf(x) * 0.70710678118654752440f, 6.0f);
+  float t = fmaf(a, 0.0000430638f, 0.0002765672f);
+  t = fmaf(a, t, 0.0001520143f);
+  t = fmaf(a, t, 0.0092705272f);
+  t = fmaf(a, t, 0.0422820123f);
+  t = fmaf(a, t, 0.0705230784f);
+  t = fmaf(a, t, 1.0f);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));  // 1 ulp; the ^16 below keeps the result within 2e-6
+  r *= r; r *= r; r *= r; r *= r;
+  const float erf_abs = 1.0f - r;
+  const float hx = 0.5f * x;
+  return fmaf(fabsf(hx), erf_abs, hx);  // 0.5 x (1 + sign(x) erf|x|)
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // ---- kernel launchers implemented across the .cu files -----------------------------------------------
@@ -114,6 +133,8 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 int gemm_bf16_tcgen05(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, int M, int N, int K,
                       const GemmEpilogue& epi, cudaStream_t st);
 int gemm_init_driver_api();
+// gemm_skinny.cu: M <= 32 rows (B = 1 passes): a latency-optimised CUDA-core kernel, same epilogues
+int gemm_bf16_skinny(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, int M, int N, int K, const GemmEpilogue& epi, cudaStream_t st);
 // sgemm.cu
 int gemm_fp32(const float* A, const float* W, float* C, int M, int N, int K, const GemmEpilogue& epi, cudaStream_t st);
 

@@ -52,26 +52,28 @@ __global__ void __launch_bounds__(256) embed_kernel(const __grid_constant__ Embe
   const int s = blockIdx.y;
   const EmbedTok& tk = p.tok[s];
   const int b_end = min(p.B, (static_cast<int>(blockIdx.x) + 1) * 64);
+  const bool shared_tok = tk.bstride == 0;  // history token: identical for every batch row -> embed + normalise once
+  float4 acc[NJ], o[NJ];
   for (int b = blockIdx.x * 64 + warp; b < b_end; b += 8) {
-    const float* src = tk.src + static_cast<size_t>(b) * tk.bstride;
-    float4 acc[NJ];
+    if (!shared_tok || b == blockIdx.x * 64 + warp) {
+      const float* src = tk.src + static_cast<size_t>(b) * tk.bstride;
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) acc[j] = __ldg(reinterpret_cast<const float4*>(tk.cvec + j * 128 + lane * 4));
-    for (int i = 0; i < tk.d; ++i) {
-      float xi = __ldg(src + i);
-      if (tk.nmean != nullptr) xi = (xi - __ldg(tk.nmean + i)) / __ldg(tk.nstd + i);
+      for (int j = 0; j < NJ; ++j) acc[j] = __ldg(reinterpret_cast<const float4*>(tk.cvec + j * 128 + lane * 4));
+      for (int i = 0; i < tk.d; ++i) {
+        float xi = __ldg(src + i);
+        if (tk.nmean != nullptr) xi = (xi - __ldg(tk.nmean + i)) / __ldg(tk.nstd + i);
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(tk.wt + static_cast<size_t>(i) * D + j * 128 + lane * 4));
-        acc[j].x = fmaf(xi, w.x, acc[j].x);
-        acc[j].y = fmaf(xi, w.y, acc[j].y);
-        acc[j].z = fmaf(xi, w.z, acc[j].z);
-        acc[j].w = fmaf(xi, w.w, acc[j].w);
+        for (int j = 0; j < NJ; ++j) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(tk.wt + static_cast<size_t>(i) * D + j * 128 + lane * 4));
+          acc[j].x = fmaf(xi, w.x, acc[j].x);
+          acc[j].y = fmaf(xi, w.y, acc[j].y);
+          acc[j].z = fmaf(xi, w.z, acc[j].z);
+          acc[j].w = fmaf(xi, w.w, acc[j].w);
+        }
       }
+      warp_layernorm<NJ>(acc, gamma, beta, lane, o);
     }
     const size_t row = static_cast<size_t>(s) * p.B + b;
-    float4 o[NJ];
-    warp_layernorm<NJ>(acc, gamma, beta, lane, o);
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       st4(x + row * D + j * 128 + lane * 4, acc[j]);
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __grid_constant__ 
     for (int j = 0; j < NJ; ++j) o[j] = v[j];
   }
   if (p.y2 != nullptr) {
-    const int grp = row / p.rows_per_group;
+    const int grp = p.tok_group[row / p.rows_per_group];
     const float* g2 = p.g2[grp];
     if (g2 != nullptr) {
       float4 o2[NJ];
@@ -118,12 +120,19 @@ __global__ void __launch_bounds__(256) fill_rows_kernel(const __grid_constant__ 
   constexpr int D = NJ * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.y;
+  const int bs = p.bstride[i];
   float4 v[NJ];
+  if (bs == 0) {
 #pragma unroll
-  for (int j = 0; j < NJ; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(p.row[i] + j * 128 + lane * 4));
+    for (int j = 0; j < NJ; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(p.row[i] + j * 128 + lane * 4));
+  }
   const int b_end = min(p.B, (static_cast<int>(blockIdx.x) + 1) * 64);
   for (int b = blockIdx.x * 64 + warp; b < b_end; b += 8) {
     const size_t row = static_cast<size_t>(p.tok[i]) * p.B + b;
+    if (bs != 0) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) v[j] = *reinterpret_cast<const float4*>(p.row[i] + static_cast<size_t>(b) * bs + j * 128 + lane * 4);
+    }
 #pragma unroll
     for (int j = 0; j < NJ; ++j) st4(x + row * D + j * 128 + lane * 4, v[j]);
   }

@@ -71,6 +71,10 @@ struct FwdIO {
   float* out_std = nullptr;
   float* out_rewards = nullptr;
   float* out_returns = nullptr;
+  // time steps whose head outputs the caller consumes, per modality: [need_t0, need_t0 + need_nt); need_nt < 0 = all T.
+  // Rows outside these ranges are never written (dead-row elimination in the last decoder layer).
+  int need_t0[4] = {0, 0, 0, 0};
+  int need_nt[4] = {-1, -1, -1, -1};
 };
 
 }  // namespace
@@ -106,9 +110,16 @@ struct m3pc_engine {
   float h_tok_mean[4] = {0, 0, 0, 0}, h_tok_std[4] = {1, 1, 1, 1};  // scalar modalities (rewards, returns) on host
   bool has_critic = false;
   const float *q_w[2][3] = {}, *q_b[2][3] = {}, *obs_mean = nullptr, *obs_std = nullptr;
+  const __nv_bfloat16* q_w16[2][2] = {};  // bf16 copies of the two hidden layers (layer 0 zero-padded to q_kp inputs)
+  int q_kp = 0;                            // critic input width padded to a multiple of 64 (tensor-core critic)
+  bool critic_tc = false;
+
+  // batch-constant decoder rows (single-layer decoder only): [Q | K | V] of LN1(decoder_embed(mask token) + per-dim + pos[t])
+  // for every decoder token, (4T, 3D) in the activation type; independent of inputs and of the mask layout
+  DevBuf const_qkv;
 
   // workspaces (per chunk)
-  DevBuf X, Y, Y2, QKV, ATT, HID, ENC;
+  DevBuf X, XS, Y, Y2, QKV, QSEL, ATT, HID, ENC;
   // planner buffers
   DevBuf p1_mu, p1_std, cand, pred_states, pred_rewards, pred_returns, sa, qa, qb1, qb2, qvals, J, filled, e_mu, e_std;
 
@@ -218,6 +229,8 @@ void bind_stack(m3pc_engine* e, StackW& s, const std::string& prefix, int n_laye
   s.norm_b = f(prefix + ".norm.bias");
 }
 
+int build_const_rows(m3pc_engine* e);
+
 int finalize(m3pc_engine* e) {
   const size_t D = e->D, T = e->T;
   Packer pk;
@@ -299,12 +312,20 @@ int finalize(m3pc_engine* e) {
   e->has_critic = false;
   if (e->QH > 0 && e->staged.count("critic.q1.net.0.weight")) {
     const size_t in = e->obs + e->act, Hq = e->QH;
+    e->q_kp = static_cast<int>((in + 63) / 64 * 64);
+    e->critic_tc = e->bf16 && Hq % 128 == 0;
     const size_t wn[3] = {Hq * in, Hq * Hq, Hq}, bn[3] = {Hq, Hq, 1};
     for (int q = 0; q < 2; ++q)
       for (int l = 0; l < 3; ++l) {
         const std::string p = "critic.q" + std::to_string(q + 1) + ".net." + std::to_string(2 * l);
         M3PC_TRY(need(e, p + ".weight", wn[l], &v));
-        pk.add(p + ".weight", v->data(), wn[l]);
+        pk.add(p + ".weight", v->data(), wn[l], l == 1 && e->critic_tc);
+        if (l == 0 && e->critic_tc) {  // zero-pad the input dimension to a TMA/UMMA friendly multiple of 64
+          std::vector<float> wp(Hq * e->q_kp, 0.f);
+          for (size_t r = 0; r < Hq; ++r)
+            for (size_t c = 0; c < in; ++c) wp[r * e->q_kp + c] = (*v)[r * in + c];
+          pk.add(p + ".weight.padded", wp.data(), wp.size(), true);
+        }
         M3PC_TRY(need(e, p + ".bias", bn[l], &v));
         pk.add(p + ".bias", v->data(), bn[l]);
       }
@@ -363,16 +384,43 @@ int finalize(m3pc_engine* e) {
         const std::string p = "critic.q" + std::to_string(q + 1) + ".net." + std::to_string(2 * l);
         e->q_w[q][l] = f(p + ".weight");
         e->q_b[q][l] = f(p + ".bias");
+        if (e->critic_tc && l == 0) e->q_w16[q][0] = h16(p + ".weight.padded");
+        if (e->critic_tc && l == 1) e->q_w16[q][1] = h16(p + ".weight");
       }
     e->obs_mean = f("critic.obs_mean");
     e->obs_std = f("critic.obs_std");
   }
   e->staged.clear();
   e->finalized = true;
+  if (e->Ld == 1) M3PC_TRY(build_const_rows(e));
   return M3PC_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ forward
+int gemm(m3pc_engine* e, const void* A, const float* w32, const __nv_bfloat16* w16, void* C, int M, int N, int K, const GemmEpilogue& epi,
+         cudaStream_t st);
+
+// Batch-constant decoder rows.  With a single decoder layer, a masked token's decoder input is the same vector for every
+// batch row: decoder_embed(mask_token) + per-dim + pos[t] (dec_maskrow, mtm_model.py:646-696).  Its LayerNorm and its Q / K / V
+// projections are therefore constants of the weights: computed once here, with the same kernels the per-batch rows use.
+int build_const_rows(m3pc_engine* e) {
+  const int D = e->D, rows = 4 * e->T;
+  const LayerW& w = e->dec.layers[0];
+  LnParams ln{};
+  ln.x = e->dec_maskrow;
+  ln.rows = rows;
+  ln.rows_per_group = 1;
+  ln.g1 = w.n1_w;
+  ln.b1 = w.n1_b;
+  ln.y1 = e->Y.p;
+  M3PC_TRY(launch_layernorm(ln, D, e->bf16, 0));
+  GemmEpilogue ge;
+  ge.bias = w.in_b;
+  M3PC_TRY(gemm(e, e->Y.p, w.in_w, w.in_w16, e->const_qkv.p, rows, 3 * D, D, ge, 0));
+  M3PC_CHECK_CUDA(cudaDeviceSynchronize());
+  return M3PC_OK;
+}
+
 int gemm(m3pc_engine* e, const void* A, const float* w32, const __nv_bfloat16* w16, void* C, int M, int N, int K, const GemmEpilogue& epi,
          cudaStream_t st) {
   size_t slot = 0;
@@ -422,6 +470,228 @@ int block(m3pc_engine* e, const LayerW& w, int Bc, int S, cudaStream_t st) {
   ep.flags = EPI_RESIDUAL;
   M3PC_TRY(gemm(e, e->HID.p, w.l2_w, w.l2_w16, e->X.p, rows, D, F, ep, st));
   return M3PC_OK;
+}
+
+struct NeedSet {
+  int n = 0;
+  int tok[MAX_TOK];  // needed decoder tokens (k*T + t), modality-major
+  int q0[4] = {0, 0, 0, 0};  // first index in tok[] of each modality
+  int t0[4] = {0, 0, 0, 0}, nt[4] = {0, 0, 0, 0};
+};
+
+// decoder_embed of the encoder outputs: one grouped GEMM per run of kept tokens of one modality (mtm_model.py:646-661).
+// `compact`: write rows in encoder-token order (row block = dec_src[j]); otherwise in decoder order (row block = j).
+int decoder_embed(m3pc_engine* e, const void* enc_out, const int* dec_src, int Bc, bool compact, cudaStream_t st) {
+  const int D = e->D, T = e->T;
+  const size_t ab = act_bytes(e);
+  for (int j = 0; j < 4 * T;) {
+    if (dec_src[j] < 0) { ++j; continue; }
+    const int k = j / T;
+    int len = 1;
+    while (j + len < (k + 1) * T && dec_src[j + len] == dec_src[j] + len) ++len;
+    GemmEpilogue ge;
+    ge.table = e->dec_cvec + static_cast<size_t>(j) * D;
+    ge.rows_per_group = Bc;
+    ge.flags = EPI_OUT_F32 | EPI_ROWTABLE;
+    const char* a = reinterpret_cast<const char*>(enc_out) + static_cast<size_t>(dec_src[j]) * Bc * D * ab;
+    float* c = e->X.as<float>() + static_cast<size_t>(compact ? dec_src[j] : j) * Bc * D;
+    M3PC_TRY(gemm(e, a, e->dec_w[k], e->dec_w16[k], c, len * Bc, D, D, ge, st));
+    j += len;
+  }
+  return M3PC_OK;
+}
+
+// K5: per-modality output heads on `y2` (head-LayerNorm'ed) / `y1` (final-norm only, for the actor), whose row blocks are
+// the needed tokens in NeedSet order.
+int heads(m3pc_engine* e, const FwdIO& io, const NeedSet& need, const void* y1, const void* y2, int b0, int Bc, cudaStream_t st) {
+  const int D = e->D, T = e->T;
+  const size_t ab = act_bytes(e);
+  float* outs[4] = {io.out_states, nullptr, io.out_rewards, io.out_returns};
+  for (int k = 0; k < 4; ++k) {
+    if (k == M3PC_ACTIONS || outs[k] == nullptr || need.nt[k] == 0) continue;
+    const int d = e->dims[k];
+    GemmEpilogue ge;
+    ge.bias = e->head_b1[k];
+    ge.flags = EPI_GELU;
+    const char* a = reinterpret_cast<const char*>(y2) + static_cast<size_t>(need.q0[k]) * Bc * D * ab;
+    M3PC_TRY(gemm(e, a, e->head_w1[k], e->head_w1_16[k], e->HID.p, need.nt[k] * Bc, D, D, ge, st));
+    RowDotParams rp{};
+    rp.y = e->HID.p;
+    rp.B = Bc; rp.tok0 = 0; rp.n_t = need.nt[k]; rp.t_out0 = need.t0[k]; rp.T_out = T; rp.d_out = d;
+    rp.w = e->head_w3[k];
+    rp.b = e->head_b3[k];
+    rp.out = outs[k] + static_cast<size_t>(b0) * T * d;
+    M3PC_TRY(launch_rowdot(rp, D, e->bf16, st));
+  }
+  if (io.out_mu != nullptr && need.nt[M3PC_ACTIONS] > 0) {
+    RowDotParams rp{};
+    rp.y = y1;
+    rp.B = Bc; rp.tok0 = need.q0[M3PC_ACTIONS]; rp.n_t = need.nt[M3PC_ACTIONS]; rp.t_out0 = need.t0[M3PC_ACTIONS]; rp.T_out = T;
+    rp.d_out = e->act;
+    rp.w = e->mu_w; rp.b = e->mu_b;
+    rp.out = io.out_mu + static_cast<size_t>(b0) * T * e->act;
+    rp.w2 = e->ls_w; rp.b2 = e->ls_b;
+    rp.out2 = io.out_std + static_cast<size_t>(b0) * T * e->act;
+    M3PC_TRY(launch_rowdot(rp, D, e->bf16, st));
+  }
+  return M3PC_OK;
+}
+
+// final decoder norm (-> Y) chained with each head's own LayerNorm (-> Y2), mtm_model.py:428-433
+int final_norms(m3pc_engine* e, const float* x, int n_tok, const int* tok, int Bc, cudaStream_t st) {
+  LnParams ln{};
+  ln.x = x;
+  ln.rows = n_tok * Bc;
+  ln.g1 = e->dec.norm_w;
+  ln.b1 = e->dec.norm_b;
+  ln.y1 = e->Y.p;
+  ln.y2 = e->Y2.p;
+  ln.rows_per_group = Bc;
+  for (int i = 0; i < n_tok; ++i) ln.tok_group[i] = static_cast<unsigned char>(tok[i] / e->T);
+  for (int k = 0; k < 4; ++k) {
+    ln.g2[k] = e->head_ln_w[k];  // null for actions: the actor reads the final norm directly
+    ln.b2[k] = e->head_ln_b[k];
+  }
+  return launch_layernorm(ln, e->D, e->bf16, st);
+}
+
+// Full decoder: every one of the 4T rows goes through every layer (mtm_model.py:663-716).
+int decode_full(m3pc_engine* e, const FwdIO& io, const void* enc_out, const int* dec_src, const NeedSet& need_in, int b0, int Bc,
+                cudaStream_t st) {
+  const int D = e->D, T = e->T;
+  FillParams fp{};
+  fp.B = Bc;
+  for (int j = 0; j < 4 * T; ++j)
+    if (dec_src[j] < 0) {
+      fp.row[fp.n] = e->dec_maskrow + static_cast<size_t>(j) * D;
+      fp.bstride[fp.n] = 0;
+      fp.tok[fp.n] = j;
+      ++fp.n;
+    }
+  M3PC_TRY(launch_fill_rows(fp, D, e->X.as<float>(), st));
+  M3PC_TRY(decoder_embed(e, enc_out, dec_src, Bc, false, st));
+  const int Sd = 4 * T;
+  LnParams ln{};
+  ln.x = e->X.as<float>();
+  ln.rows = Sd * Bc;
+  ln.rows_per_group = Bc;
+  for (int l = 0; l < e->Ld; ++l) {
+    ln.g1 = e->dec.layers[l].n1_w;
+    ln.b1 = e->dec.layers[l].n1_b;
+    ln.y1 = e->Y.p;
+    M3PC_TRY(launch_layernorm(ln, D, e->bf16, st));
+    M3PC_TRY(block(e, e->dec.layers[l], Bc, Sd, st));
+  }
+  // heads over all rows: token blocks in decoder order
+  int all_tok[MAX_TOK];
+  for (int j = 0; j < Sd; ++j) all_tok[j] = j;
+  M3PC_TRY(final_norms(e, e->X.as<float>(), Sd, all_tok, Bc, st));
+  NeedSet need = need_in;
+  for (int k = 0; k < 4; ++k) need.q0[k] = k * T + need.t0[k];  // row block of (k, t0) in decoder order
+  return heads(e, io, need, e->Y.p, e->Y2.p, b0, Bc, st);
+}
+
+// Single-layer decoder restricted to the rows the caller consumes.  Identical results to decode_full for those rows:
+//   * keys / values still cover all 4T tokens, but the mask-token rows are batch-constant, so their K/V (and Q) come from the
+//     table built once at finalize (const_qkv) and only the kept tokens' K/V are projected per batch row;
+//   * queries, out-projection, MLP, norms and heads run on the needed tokens only.
+int decode_restricted(m3pc_engine* e, const FwdIO& io, const void* enc_out, const int* dec_src, int S, const NeedSet& need, int b0, int Bc,
+                      cudaStream_t st) {
+  const int D = e->D, T = e->T, F = e->F;
+  const size_t ab = act_bytes(e);
+  const LayerW& w = e->dec.layers[0];
+  // (a) decoder embedding of the kept tokens, compact (encoder order) -> X[0 : S*Bc)
+  M3PC_TRY(decoder_embed(e, enc_out, dec_src, Bc, true, st));
+  // (b) LN1 -> Y
+  LnParams ln{};
+  ln.x = e->X.as<float>();
+  ln.rows = S * Bc;
+  ln.rows_per_group = Bc;
+  ln.g1 = w.n1_w;
+  ln.b1 = w.n1_b;
+  ln.y1 = e->Y.p;
+  M3PC_TRY(launch_layernorm(ln, D, e->bf16, st));
+  // (c) K, V of the kept tokens: rows D..3D of in_proj -> QKV as (S*Bc, 2D)
+  GemmEpilogue ge;
+  ge.bias = w.in_b + D;
+  M3PC_TRY(gemm(e, e->Y.p, w.in_w + static_cast<size_t>(D) * D, e->bf16 ? w.in_w16 + static_cast<size_t>(D) * D : nullptr, e->QKV.p, S * Bc, 2 * D, D,
+                ge, st));
+  // (d) Q of needed tokens that are kept (per-batch) tokens -> QSEL row block qi
+  for (int qi = 0; qi < need.n; ++qi) {
+    const int src = dec_src[need.tok[qi]];
+    if (src < 0) continue;
+    GemmEpilogue gq;
+    gq.bias = w.in_b;
+    const char* a = reinterpret_cast<const char*>(e->Y.p) + static_cast<size_t>(src) * Bc * D * ab;
+    char* c = reinterpret_cast<char*>(e->QSEL.p) + static_cast<size_t>(qi) * Bc * D * ab;
+    M3PC_TRY(gemm(e, a, w.in_w, w.in_w16, c, Bc, D, D, gq, st));
+  }
+  // (e) attention: needed queries x all 4T keys
+  AttnParams ap{};
+  ap.n_q = need.n;
+  ap.n_kv = 4 * T;
+  ap.B = Bc;
+  ap.n_head = e->H;
+  ap.out = e->ATT.p;
+  const char* cq = reinterpret_cast<const char*>(e->const_qkv.p);
+  for (int qi = 0; qi < need.n; ++qi) {
+    const int j = need.tok[qi];
+    if (dec_src[j] < 0)
+      ap.q[qi] = AttnTok{cq + static_cast<size_t>(j) * 3 * D * ab, 0};
+    else
+      ap.q[qi] = AttnTok{reinterpret_cast<const char*>(e->QSEL.p) + static_cast<size_t>(qi) * Bc * D * ab, D};
+  }
+  for (int j = 0; j < 4 * T; ++j) {
+    if (dec_src[j] < 0) {
+      ap.k[j] = AttnTok{cq + (static_cast<size_t>(j) * 3 * D + D) * ab, 0};
+      ap.v[j] = AttnTok{cq + (static_cast<size_t>(j) * 3 * D + 2 * D) * ab, 0};
+    } else {
+      const char* row = reinterpret_cast<const char*>(e->QKV.p) + static_cast<size_t>(dec_src[j]) * Bc * 2 * D * ab;
+      ap.k[j] = AttnTok{row, 2 * D};
+      ap.v[j] = AttnTok{row + D * ab, 2 * D};
+    }
+  }
+  M3PC_TRY(launch_attention_gather(ap, e->bf16, st));
+  // (f) residual rows of the needed tokens -> XS, then out-projection accumulates into them
+  FillParams fp{};
+  fp.B = Bc;
+  for (int qi = 0; qi < need.n; ++qi) {
+    const int j = need.tok[qi];
+    if (dec_src[j] < 0) {
+      fp.row[fp.n] = e->dec_maskrow + static_cast<size_t>(j) * D;
+      fp.bstride[fp.n] = 0;
+    } else {
+      fp.row[fp.n] = e->X.as<float>() + static_cast<size_t>(dec_src[j]) * Bc * D;
+      fp.bstride[fp.n] = D;
+    }
+    fp.tok[fp.n++] = qi;
+  }
+  M3PC_TRY(launch_fill_rows(fp, D, e->XS.as<float>(), st));
+  const int rows = need.n * Bc;
+  ge = GemmEpilogue{};
+  ge.bias = w.out_b;
+  ge.flags = EPI_RESIDUAL;
+  M3PC_TRY(gemm(e, e->ATT.p, w.out_w, w.out_w16, e->XS.p, rows, D, D, ge, st));
+  // (g) MLP
+  ln = LnParams{};
+  ln.x = e->XS.as<float>();
+  ln.rows = rows;
+  ln.rows_per_group = Bc;
+  ln.g1 = w.n2_w;
+  ln.b1 = w.n2_b;
+  ln.y1 = e->Y.p;
+  M3PC_TRY(launch_layernorm(ln, D, e->bf16, st));
+  ge = GemmEpilogue{};
+  ge.bias = w.l1_b;
+  ge.flags = EPI_GELU;
+  M3PC_TRY(gemm(e, e->Y.p, w.l1_w, w.l1_w16, e->HID.p, rows, F, D, ge, st));
+  ge = GemmEpilogue{};
+  ge.bias = w.l2_b;
+  ge.flags = EPI_RESIDUAL;
+  M3PC_TRY(gemm(e, e->HID.p, w.l2_w, w.l2_w16, e->XS.p, rows, D, F, ge, st));
+  // (h) norms + heads
+  M3PC_TRY(final_norms(e, e->XS.as<float>(), need.n, need.tok, Bc, st));
+  return heads(e, io, need, e->Y.p, e->Y2.p, b0, Bc, st);
 }
 
 int forward_chunk(m3pc_engine* e, const FwdIO& io, int b0, int Bc, cudaStream_t st) {
@@ -487,92 +757,22 @@ int forward_chunk(m3pc_engine* e, const FwdIO& io, int b0, int Bc, cudaStream_t 
     M3PC_TRY(launch_layernorm(ln, D, e->bf16, st));
   }
 
-  // ---- K4: decoder input = decoder_embed(encoder output | mask token) + per-dim + pos (mtm_model.py:646-696) ----
-  FillParams fp{};
-  fp.B = Bc;
-  for (int j = 0; j < 4 * T; ++j)
-    if (dec_src[j] < 0) {
-      fp.row[fp.n] = e->dec_maskrow + static_cast<size_t>(j) * D;
-      fp.tok[fp.n] = j;
-      ++fp.n;
-    }
-  M3PC_TRY(launch_fill_rows(fp, D, e->X.as<float>(), st));
-  for (int j = 0; j < 4 * T;) {  // runs of kept tokens with one modality: one grouped GEMM each
-    if (dec_src[j] < 0) { ++j; continue; }
-    const int k = j / T;
-    int len = 1;
-    while (j + len < (k + 1) * T && dec_src[j + len] == dec_src[j] + len) ++len;
-    GemmEpilogue ge;
-    ge.table = e->dec_cvec + static_cast<size_t>(j) * D;
-    ge.rows_per_group = Bc;
-    ge.flags = EPI_OUT_F32 | EPI_ROWTABLE;
-    const char* a = reinterpret_cast<const char*>(enc_out) + static_cast<size_t>(dec_src[j]) * Bc * D * ab;
-    M3PC_TRY(gemm(e, a, e->dec_w[k], e->dec_w16[k], e->X.as<float>() + static_cast<size_t>(j) * Bc * D, len * Bc, D, D, ge, st));
-    j += len;
-  }
-  const int Sd = 4 * T, rows_d = Sd * Bc;
-  LnParams ln{};
-  ln.x = e->X.as<float>();
-  ln.rows = rows_d;
-  ln.rows_per_group = 1;
-  if (e->Ld > 0) {
-    ln.g1 = e->dec.layers[0].n1_w;
-    ln.b1 = e->dec.layers[0].n1_b;
-    ln.y1 = e->Y.p;
-    M3PC_TRY(launch_layernorm(ln, D, e->bf16, st));
-  }
-  // ---- decoder stack (mtm_model.py:397-409, 701-705) ----
-  for (int l = 0; l < e->Ld; ++l) {
-    M3PC_TRY(block(e, e->dec.layers[l], Bc, Sd, st));
-    if (l + 1 < e->Ld) {
-      ln.g1 = e->dec.layers[l + 1].n1_w;
-      ln.b1 = e->dec.layers[l + 1].n1_b;
-      ln.y1 = e->Y.p;
-      ln.y2 = nullptr;
-      M3PC_TRY(launch_layernorm(ln, D, e->bf16, st));
-    }
-  }
-  // final decoder norm (-> Y) chained with each head's own LayerNorm (-> Y2), mtm_model.py:428-433
-  ln.g1 = e->dec.norm_w;
-  ln.b1 = e->dec.norm_b;
-  ln.y1 = e->Y.p;
-  ln.y2 = e->Y2.p;
-  ln.rows_per_group = T * Bc;
+  // ---- which head rows does the caller consume? ----
+  NeedSet need;
+  const float* outp[4] = {io.out_states, io.out_mu, io.out_rewards, io.out_returns};
   for (int k = 0; k < 4; ++k) {
-    ln.g2[k] = e->head_ln_w[k];  // null for actions
-    ln.b2[k] = e->head_ln_b[k];
+    need.q0[k] = need.n;
+    if (outp[k] == nullptr) continue;
+    const int t0 = io.need_nt[k] < 0 ? 0 : io.need_t0[k];
+    const int nt = io.need_nt[k] < 0 ? T : io.need_nt[k];
+    M3PC_REQUIRE(t0 >= 0 && nt >= 0 && t0 + nt <= T, "need range out of bounds");
+    need.t0[k] = t0;
+    need.nt[k] = nt;
+    for (int t = t0; t < t0 + nt; ++t) need.tok[need.n++] = k * T + t;
   }
-  M3PC_TRY(launch_layernorm(ln, D, e->bf16, st));
-
-  // ---- K5: heads ----
-  float* outs[4] = {io.out_states, nullptr, io.out_rewards, io.out_returns};
-  for (int k = 0; k < 4; ++k) {
-    if (k == M3PC_ACTIONS || outs[k] == nullptr) continue;
-    const int d = e->dims[k];
-    GemmEpilogue ge;
-    ge.bias = e->head_b1[k];
-    ge.flags = EPI_GELU;
-    const char* a = reinterpret_cast<const char*>(e->Y2.p) + static_cast<size_t>(k) * T * Bc * D * ab;
-    M3PC_TRY(gemm(e, a, e->head_w1[k], e->head_w1_16[k], e->HID.p, T * Bc, D, D, ge, st));
-    RowDotParams rp{};
-    rp.y = e->HID.p;
-    rp.B = Bc; rp.tok0 = 0; rp.n_t = T; rp.t_out0 = 0; rp.T_out = T; rp.d_out = d;
-    rp.w = e->head_w3[k];
-    rp.b = e->head_b3[k];
-    rp.out = outs[k] + static_cast<size_t>(b0) * T * d;
-    M3PC_TRY(launch_rowdot(rp, D, e->bf16, st));
-  }
-  if (io.out_mu != nullptr) {
-    RowDotParams rp{};
-    rp.y = e->Y.p;
-    rp.B = Bc; rp.tok0 = M3PC_ACTIONS * T; rp.n_t = T; rp.t_out0 = 0; rp.T_out = T; rp.d_out = e->act;
-    rp.w = e->mu_w; rp.b = e->mu_b;
-    rp.out = io.out_mu + static_cast<size_t>(b0) * T * e->act;
-    rp.w2 = e->ls_w; rp.b2 = e->ls_b;
-    rp.out2 = io.out_std + static_cast<size_t>(b0) * T * e->act;
-    M3PC_TRY(launch_rowdot(rp, D, e->bf16, st));
-  }
-  return M3PC_OK;
+  if (need.n == 0) return M3PC_OK;
+  if (e->Ld == 1 && need.n < 4 * T) return decode_restricted(e, io, enc_out, dec_src, S, need, b0, Bc, st);
+  return decode_full(e, io, enc_out, dec_src, need, b0, Bc, st);
 }
 
 int forward(m3pc_engine* e, const FwdIO& io, int B, cudaStream_t st) {
@@ -583,6 +783,9 @@ int forward(m3pc_engine* e, const FwdIO& io, int B, cudaStream_t st) {
   return M3PC_OK;
 }
 
+// K7: TwinQ on all (candidate, step) rows at once (the reference calls it h times on N rows, learner.py:250-252).
+// bf16 mode: the two hidden layers run on the tcgen05 GEMM (bf16 operands, fp32 accumulate, second layer written in fp32);
+// fp32 mode: CUDA-core fp32 GEMMs.  The final 256 -> 1 layer and min(q1, q2) are fp32 in both.
 int critic(m3pc_engine* e, int N, int h, cudaStream_t st) {
   const int rows = N * h, in = e->obs + e->act, Hq = e->QH;
   CriticInParams ci{};
@@ -592,17 +795,26 @@ int critic(m3pc_engine* e, int N, int h, cudaStream_t st) {
   ci.tok_std = e->tok_std[M3PC_STATES];
   ci.obs_mean = e->obs_mean;
   ci.obs_std = e->obs_std;
-  ci.sa = e->sa.as<float>();
+  ci.sa = e->sa.p;
   ci.N = N; ci.h = h; ci.T = e->T; ci.obs = e->obs; ci.A = e->act;
+  ci.ld = e->critic_tc ? e->q_kp : in;
+  ci.out_bf16 = e->critic_tc;
   M3PC_TRY(launch_critic_input(ci, st));
   float* outs[2] = {e->qb1.as<float>(), e->qb2.as<float>()};
   for (int q = 0; q < 2; ++q) {
     GemmEpilogue ge;
     ge.bias = e->q_b[q][0];
     ge.flags = EPI_RELU;
-    M3PC_TRY(gemm_fp32(e->sa.as<float>(), e->q_w[q][0], e->qa.as<float>(), rows, Hq, in, ge, st));
-    ge.bias = e->q_b[q][1];
-    M3PC_TRY(gemm_fp32(e->qa.as<float>(), e->q_w[q][1], outs[q], rows, Hq, Hq, ge, st));
+    if (e->critic_tc) {
+      M3PC_TRY(gemm(e, e->sa.p, nullptr, e->q_w16[q][0], e->qa.p, rows, Hq, e->q_kp, ge, st));
+      ge.bias = e->q_b[q][1];
+      ge.flags = EPI_RELU | EPI_OUT_F32;
+      M3PC_TRY(gemm(e, e->qa.p, nullptr, e->q_w16[q][1], outs[q], rows, Hq, Hq, ge, st));
+    } else {
+      M3PC_TRY(gemm_fp32(e->sa.as<float>(), e->q_w[q][0], e->qa.as<float>(), rows, Hq, in, ge, st));
+      ge.bias = e->q_b[q][1];
+      M3PC_TRY(gemm_fp32(e->qa.as<float>(), e->q_w[q][1], outs[q], rows, Hq, Hq, ge, st));
+    }
   }
   return launch_critic_out(outs[0], outs[1], e->q_w[0][2], e->q_b[0][2], e->q_w[1][2], e->q_b[1][2], e->qvals.as<float>(), rows, Hq, st);
 }
@@ -637,6 +849,8 @@ int plan(m3pc_engine* e, const m3pc_plan_args_t* a, cudaStream_t st) {
   }
   io.out_mu = e->p1_mu.as<float>();
   io.out_std = e->p1_std.as<float>();
+  io.need_t0[M3PC_ACTIONS] = idx;  // only the planned steps of the action head are consumed
+  io.need_nt[M3PC_ACTIONS] = h;
   M3PC_TRY(forward(e, io, 1, st));
   if (a->guidance == M3PC_GUIDE_SAMPLING)
     return launch_sampling_tail(io.out_mu, io.out_std, a->eps, T, h, A, 1, a->out_eval_action, a->out_sample_action, a->seed, st);
@@ -663,11 +877,19 @@ int plan(m3pc_engine* e, const m3pc_plan_args_t* a, cudaStream_t st) {
     io2.mask[M3PC_REWARDS * T + t] = 0;
     io2.mask[M3PC_RETURNS * T + t] = 0;
   }
+  // consumed by the scorer (learner.py:301-316): rewards[idx .. T-2], and returns[idx ..] (rtg) or states[idx ..] (critic)
   io2.out_rewards = e->pred_rewards.as<float>();
-  if (needs_critic)
+  io2.need_t0[M3PC_REWARDS] = idx;
+  io2.need_nt[M3PC_REWARDS] = h - 1;
+  if (needs_critic) {
     io2.out_states = e->pred_states.as<float>();
-  else
+    io2.need_t0[M3PC_STATES] = idx;
+    io2.need_nt[M3PC_STATES] = h;
+  } else {
     io2.out_returns = e->pred_returns.as<float>();
+    io2.need_t0[M3PC_RETURNS] = idx;
+    io2.need_nt[M3PC_RETURNS] = h;
+  }
   M3PC_TRY(forward(e, io2, N, st));
 
   // ---- K7 + K8 ----
@@ -710,6 +932,8 @@ int backward_plan(m3pc_engine* e, int mode, int E, int h, const float* ws, const
   if (mode == 0) {
     io.out_mu = e->e_mu.as<float>();
     io.out_std = e->e_std.as<float>();
+    io.need_t0[M3PC_ACTIONS] = idx;
+    io.need_nt[M3PC_ACTIONS] = 1;
     M3PC_TRY(forward(e, io, E, st));
   } else {
     io.out_states = e->pred_states.as<float>();
@@ -726,6 +950,8 @@ int backward_plan(m3pc_engine* e, int mode, int E, int h, const float* ws, const
     }
     io2.out_mu = e->e_mu.as<float>();
     io2.out_std = e->e_std.as<float>();
+    io2.need_t0[M3PC_ACTIONS] = idx;
+    io2.need_nt[M3PC_ACTIONS] = 1;
     M3PC_TRY(forward(e, io2, E, st));
   }
   return launch_sampling_tail(e->e_mu.as<float>(), e->e_std.as<float>(), eps, T, h, A, E, out_eval, out_sample, 0ull, st);
@@ -761,13 +987,17 @@ int create(m3pc_handle_t* out, const m3pc_config_t* cfg) {
   const size_t rows = static_cast<size_t>(4) * e->T * e->chunk + 128;  // +128: slack rows for tile tails
   const size_t ab = act_bytes(e.get()), D = e->D;
   M3PC_TRY(e->X.alloc(rows * D * 4));
+  M3PC_TRY(e->XS.alloc(rows * D * 4));
+  M3PC_TRY(e->QSEL.alloc(rows * D * ab));
+  M3PC_TRY(e->const_qkv.alloc(static_cast<size_t>(4) * e->T * 3 * D * ab));
   M3PC_TRY(e->Y.alloc(rows * D * ab));
   M3PC_TRY(e->Y2.alloc(rows * D * ab));
   M3PC_TRY(e->QKV.alloc(rows * 3 * D * ab));
   M3PC_TRY(e->ATT.alloc(rows * D * ab));
   M3PC_TRY(e->HID.alloc(rows * 4 * D * ab));
   M3PC_TRY(e->ENC.alloc(rows * D * ab));
-  for (DevBuf* b : {&e->X, &e->Y, &e->Y2, &e->QKV, &e->ATT, &e->HID, &e->ENC}) M3PC_CHECK_CUDA(cudaMemset(b->p, 0, b->bytes));
+  for (DevBuf* b : {&e->X, &e->XS, &e->Y, &e->Y2, &e->QKV, &e->QSEL, &e->ATT, &e->HID, &e->ENC})
+    M3PC_CHECK_CUDA(cudaMemset(b->p, 0, b->bytes));
   const size_t N = cfg->max_batch, T = e->T;
   M3PC_TRY(e->p1_mu.alloc(T * e->act * 4));
   M3PC_TRY(e->p1_std.alloc(T * e->act * 4));
@@ -780,8 +1010,8 @@ int create(m3pc_handle_t* out, const m3pc_config_t* cfg) {
   M3PC_TRY(e->e_mu.alloc(N * T * e->act * 4));
   M3PC_TRY(e->e_std.alloc(N * T * e->act * 4));
   if (e->QH > 0) {
-    M3PC_TRY(e->sa.alloc(N * T * (e->obs + e->act) * 4));
-    M3PC_TRY(e->qa.alloc(N * T * e->QH * 4));
+    M3PC_TRY(e->sa.alloc((N * T + 128) * static_cast<size_t>((e->obs + e->act + 63) / 64 * 64) * 4));
+    M3PC_TRY(e->qa.alloc((N * T + 128) * e->QH * 4));
     M3PC_TRY(e->qb1.alloc(N * T * e->QH * 4));
     M3PC_TRY(e->qb2.alloc(N * T * e->QH * 4));
     M3PC_TRY(e->qvals.alloc(N * T * 4));

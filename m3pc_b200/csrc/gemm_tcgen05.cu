@@ -145,7 +145,7 @@ struct SmemLayout {
 };
 
 __device__ __forceinline__ float apply_act(float v, bool do_gelu, bool do_relu) {
-  if (do_gelu) v = gelu_erf(v);
+  if (do_gelu) v = gelu_erf_fast(v);
   if (do_relu) v = fmaxf(v, 0.0f);
   return v;
 }
@@ -258,6 +258,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const __grid
 #pragma unroll 1
       for (int c = 0; c < BN / 2; c += 32) {
         const int col_in_tile = half * (BN / 2) + c;
+        const int col0 = n0 + col_in_tile;
+        // residual rows are independent of the accumulator: issue all 8 coalesced loads first so their DRAM/L2 latency
+        // overlaps the TMEM load and the transpose (lane -> 4 consecutive columns, 8 lanes per row, 4 rows per pass)
+        float4 res[8];
+        if (do_res) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = row_base + 4 * i + (lane >> 3);
+            res[i] = (row < M) ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(C) + static_cast<size_t>(row) * N + col0 + 4 * (lane & 7))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         uint32_t r[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(a * BN + col_in_tile), r);
         tmem_ld_wait();
@@ -266,7 +278,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const __grid
         for (int j = 0; j < 8; ++j)
           *reinterpret_cast<uint4*>(xp + lane * XPOSE_LD + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         __syncwarp();
-        const int col0 = n0 + col_in_tile;
         if (out_f32) {
           // lane -> 4 consecutive columns, 8 lanes per row, 4 rows per pass
           const int cc = 4 * (lane & 7);
@@ -286,10 +297,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const __grid
               v.x = apply_act(v.x, do_gelu, do_relu); v.y = apply_act(v.y, do_gelu, do_relu);
               v.z = apply_act(v.z, do_gelu, do_relu); v.w = apply_act(v.w, do_gelu, do_relu);
               float* cp = reinterpret_cast<float*>(C) + static_cast<size_t>(row) * N + col0 + cc;
-              if (do_res) {
-                const float4 x = *reinterpret_cast<const float4*>(cp);
-                v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
-              }
+              if (do_res) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
               *reinterpret_cast<float4*>(cp) = v;
             }
           }
@@ -409,6 +417,7 @@ int gemm_bf16_tcgen05(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, i
                    (reinterpret_cast<uintptr_t>(C) & 15) == 0,
                "gemm_bf16: operands must be 16-byte aligned");
   M3PC_TRY(gemm_init_driver_api());
+  if (M <= 32 && static_cast<size_t>(M) * K * 2 <= 160 * 1024) return gemm_bf16_skinny(A, W, C, M, N, K, epi, st);
   // tile width: minimise (rounds of the persistent grid) x (cost of one tile ~ BN); ties go to the wide tile (less L2 traffic)
   const int m_tiles = ceil_div(M, BM);
   if (N % 256 == 0) {

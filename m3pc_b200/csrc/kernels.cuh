@@ -35,15 +35,17 @@ struct LnParams {
   void* y1;  // may be null
   const float* g2[4];
   const float* b2[4];
-  int rows_per_group;
+  int rows_per_group;            // rows per token block (B); the second LN's parameter set is tok_group[row / rows_per_group]
+  unsigned char tok_group[MAX_TOK];
   void* y2;  // may be null
 };
 int launch_layernorm(const LnParams& p, int D, bool out_bf16, cudaStream_t st);
 
 // ---- K4 helper: broadcast batch-constant decoder rows (mask tokens after decoder embedding) ------------
 struct FillParams {
-  const float* row[MAX_TOK];  // (D) constant row for each listed decoder token
-  int tok[MAX_TOK];           // decoder token index j (row block j*B .. j*B+B)
+  const float* row[MAX_TOK];  // source row of batch row 0 for each listed token
+  int bstride[MAX_TOK];       // floats between batch rows of the source (0 = one constant row broadcast to all)
+  int tok[MAX_TOK];           // destination token index j (row block j*B .. j*B+B)
   int n;
   int B;
 };
@@ -65,6 +67,19 @@ struct RowDotParams {
 int launch_rowdot(const RowDotParams& p, int D, bool y_bf16, cudaStream_t st);
 
 // ---- K3: small-sequence bidirectional attention ----------------------------------------------------------
+// Token-gather form: every query / key / value token names its own source row block (row for batch b = ptr + b*bstride
+// elements, bstride = 0 for rows shared by the whole batch: history tokens, batch-constant mask-token rows).
+struct AttnTok {
+  const void* ptr;
+  int bstride;
+};
+struct AttnParams {
+  AttnTok q[MAX_TOK], k[MAX_TOK], v[MAX_TOK];
+  int n_q, n_kv, B, n_head;
+  void* out;  // (n_q * B, n_head * 128), row = query token * B + b
+};
+int launch_attention_gather(const AttnParams& p, bool bf16, cudaStream_t st);
+// self-attention over token-major qkv (S*B rows, [Q | K | V] columns)
 int launch_attention(const void* qkv, void* out, int B, int S, int n_head, bool bf16, cudaStream_t st);
 
 // ---- K6..K8: the candidate loop ---------------------------------------------------------------------------
@@ -87,8 +102,10 @@ struct CriticInParams {
   const float* tok_std;
   const float* obs_mean;     // (obs) critic normaliser
   const float* obs_std;
-  float* sa;                 // (N*h, obs+A), row = n*h + t
+  void* sa;                  // (N*h, ld), row = n*h + t: fp32 (ld = obs+A) or bf16 zero-padded to ld (tensor-core critic)
   int N, h, T, obs, A;
+  int ld;
+  int out_bf16;
 };
 int launch_critic_input(const CriticInParams& p, cudaStream_t st);
 // q = min(h1 . w1 + b1, h2 . w2 + b2) per row; h1, h2 (rows, H) fp32

@@ -56,20 +56,23 @@ __global__ void candidates_kernel(const __grid_constant__ CandParams p) {
 }
 
 __global__ void critic_input_kernel(const __grid_constant__ CriticInParams p) {
-  const int w = p.obs + p.A;
+  const int w = p.ld;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.N * p.h * w) return;
   const int row = i / w, c = i - row * w;
   const int n = row / p.h, t = row - n * p.h;
-  float v;
+  float v = 0.f;  // zero padding beyond obs + A
   if (c < p.obs) {
     const float y = p.states_pred[(static_cast<size_t>(n) * p.T + (p.T - p.h + t)) * p.obs + c];
     const float s = __fadd_rn(__fmul_rn(y, p.tok_std[c]), p.tok_mean[c]);  // tokenizer decode, continuous.py:90-92
     v = (s - p.obs_mean[c]) / p.obs_std[c];                                 // TwinQ.both, model.py:166
-  } else {
+  } else if (c < p.obs + p.A) {
     v = p.cand[(static_cast<size_t>(n) * p.h + t) * p.A + (c - p.obs)];
   }
-  p.sa[i] = v;
+  if (p.out_bf16)
+    reinterpret_cast<__nv_bfloat16*>(p.sa)[i] = __float2bfloat16_rn(v);
+  else
+    reinterpret_cast<float*>(p.sa)[i] = v;
 }
 
 __global__ void critic_out_kernel(const float* __restrict__ h1, const float* __restrict__ h2, const float* __restrict__ w1,
@@ -97,7 +100,8 @@ __global__ void score_kernel(const __grid_constant__ ScoreParams p) {
   for (int i = 0; i < h; ++i) {  // torch.cumprod(discount * ones(t+1)) in fp32
     d = __fmul_rn(d, p.discount);
     disc[i] = d;
-    r[i] = __fadd_rn(__fmul_rn(p.rewards_pred[static_cast<size_t>(n) * T + (T - h + i)], p.rw_std), p.rw_mean);
+    // rewards are consumed for steps < h-1 only (the last step contributes its value term); later rows are never written
+    r[i] = (i < h - 1) ? __fadd_rn(__fmul_rn(p.rewards_pred[static_cast<size_t>(n) * T + (T - h + i)], p.rw_std), p.rw_mean) : 0.f;
   }
   const double lam = static_cast<double>(p.lmbda);
   const float one_minus = static_cast<float>(1.0 - lam);
@@ -281,7 +285,7 @@ int launch_candidates(const CandParams& p, cudaStream_t st) {
   return M3PC_OK;
 }
 int launch_critic_input(const CriticInParams& p, cudaStream_t st) {
-  const int n = p.N * p.h * (p.obs + p.A);
+  const int n = p.N * p.h * p.ld;
   critic_input_kernel<<<ceil_div(n, 256), 256, 0, st>>>(p);
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;

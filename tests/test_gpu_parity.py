@@ -320,7 +320,7 @@ def test_full_size_properties(env, guidance, temp, N):
 
     ev, sm, d = run(eng, eps, q, N)
     J = d["expect_return"]
-    assert torch.isfinite(J).all() and float(d["candidates"].abs().max()) < 1.0
+    assert torch.isfinite(J).all() and float(d["candidates"].abs().max()) <= 1.0  # tanh saturates to exactly 1 in fp32
     assert int(d["indices"][0]) == int(torch.argmax(J))
     w = torch.exp((J.double() - J.double().max()) * temp)
     np.testing.assert_allclose(ev.cpu().numpy(), ((w[:, None] * d["candidates"][:, 0].double()).sum(0) / w.sum()).cpu().numpy(), atol=2e-5)
@@ -359,7 +359,7 @@ def test_philox_noise_is_shard_invariant_and_seeded():
                   temperature=0.01, lmbda=0.6, debug=True)
     _, _, d = eng.plan(n_cand=512, seed=5, **common)
     c = d["candidates"].clone()
-    assert float(c.abs().max()) < 1.0 and float(c.std()) > 0.01
+    assert float(c.abs().max()) <= 1.0 and float(c.std()) > 0.01
     _, _, d1 = eng.plan(n_cand=256, seed=5, cand_offset=256, **common)
     assert torch.equal(d1["candidates"], c[256:])          # noise is a function of the GLOBAL candidate id
     _, _, d2 = eng.plan(n_cand=512, seed=6, **common)
