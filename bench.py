@@ -208,7 +208,9 @@ def run_ours(args, w, shape, rank, local_rank, world):
     barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
 
     def plan_resident(i, want_partials=False):
-        ws, wa, wr, wt = windows[i]
+        # the window is already in HBM; it is copied (800 B, device to device) into the buffer the engine's CUDA graph reads
+        cur.copy_(windows[i], non_blocking=True)
+        ws, wa, wr, wt = cur_views
         ev, sm, dbg = eng.plan(guidance=w["guidance"], horizon=h, n_cand=n_local, win_states=ws, win_actions=wa, win_rewards=wr,
                                win_returns_tok=wt, discount=0.99, temperature=w["temperature"], lmbda=0.6, seed=7 + i, cand_offset=lo,
                                want_partials=want_partials)
@@ -222,9 +224,10 @@ def run_ours(args, w, shape, rank, local_rank, world):
     for hist in hists:
         ring, slot = L._window_buffers(shape.obs_dim, shape.act_dim)
         L._fill_window(slot.h_states, slot.h_actions, slot.h_rewards, slot.h_returns, hist, h, 1.0, 3.0)
-        t = slot.host.to(dev)
-        o = [0, T * shape.obs_dim, T * (shape.obs_dim + A), T * (shape.obs_dim + A + 1), t.numel()]
-        windows.append((t[o[0]:o[1]].view(T, -1), t[o[1]:o[2]].view(T, -1), t[o[2]:o[3]], t[o[3]:o[4]]))
+        windows.append(slot.host.to(dev))
+    cur = torch.empty_like(windows[0])
+    o = [0, T * shape.obs_dim, T * (shape.obs_dim + A), T * (shape.obs_dim + A + 1), cur.numel()]
+    cur_views = (cur[o[0]:o[1]].view(T, -1), cur[o[1]:o[2]].view(T, -1), cur[o[2]:o[3]], cur[o[3]:o[4]])
 
     # ---- device-resident timing: K plans, one CUDA-event pair each, L2 flushed between plans ----
     for i in range(W):

@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(256) embed_kernel(const __grid_constant__ Embe
       const float* src = tk.src + static_cast<size_t>(b) * tk.bstride;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) acc[j] = __ldg(reinterpret_cast<const float4*>(tk.cvec + j * 128 + lane * 4));
+#pragma unroll 4
       for (int i = 0; i < tk.d; ++i) {
         float xi = __ldg(src + i);
         if (tk.nmean != nullptr) xi = (xi - __ldg(tk.nmean + i)) / __ldg(tk.nstd + i);
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const __grid_constant__ Row
   for (int o0 = 0; o0 < p.d_out; o0 += 32) {
     float mine = 0.f, mine2 = 0.f;
     const int o_end = min(p.d_out, o0 + 32);
+#pragma unroll 4
     for (int o = o0; o < o_end; ++o) {
       float s = 0.f;
 #pragma unroll

@@ -6,6 +6,7 @@
 // or environments) of the current chunk.  A chunk is run through the whole network before the next one starts,
 // so its working set (<= ~80 bytes/feature/row) stays L2-resident; weights (22.7 MB bf16) stay L2-resident too.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -123,6 +124,23 @@ struct m3pc_engine {
   // planner buffers
   DevBuf p1_mu, p1_std, cand, pred_states, pred_rewards, pred_returns, sa, qa, qb1, qb2, qvals, J, filled, e_mu, e_std;
 
+  // CUDA-graph replay of m3pc_plan (production path: on-device Philox noise, no debug outputs)
+  struct PlanKey {
+    int guidance, horizon, n_cand, cand_offset;
+    float discount, temperature, lmbda;
+    const void *ws, *wa, *wr, *wt, *ev, *sm, *pt;
+    bool operator<(const PlanKey& o) const { return std::memcmp(this, &o, sizeof(PlanKey)) < 0; }
+  };
+  struct PlanGraph {
+    cudaGraphExec_t exec = nullptr;
+    int launches = 0;
+    int seen = 0;  // eager calls before capture (lazy one-time initialisation must not happen inside a capture)
+  };
+  std::map<PlanKey, PlanGraph> plan_graphs;
+  bool use_graphs = true;
+  DevBuf seed_scalar;
+  const unsigned long long* seed_ptr_active = nullptr;  // non-null while (re)building / replaying a graph
+
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int last_launches = 0;
   // profiling mode: one event pair per GEMM launch
@@ -132,6 +150,8 @@ struct m3pc_engine {
   size_t prof_used = 0;
 
   ~m3pc_engine() {
+    for (auto& kv : plan_graphs)
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     for (auto& pr : prof_events) {
@@ -827,7 +847,7 @@ void set_window_sources(m3pc_engine* e, FwdIO& io, const float* ws, const float*
   io.src[M3PC_RETURNS] = ModSrc{wrt, stride_mul * T, false};
 }
 
-int plan(m3pc_engine* e, const m3pc_plan_args_t* a, cudaStream_t st) {
+int plan_body(m3pc_engine* e, const m3pc_plan_args_t* a, cudaStream_t st) {
   M3PC_REQUIRE(e->finalized, "plan before m3pc_finalize_params");
   const int T = e->T, h = a->horizon, N = a->n_cand, A = e->act, idx = T - h;
   M3PC_REQUIRE(h >= 1 && h <= T, "horizon must be in [1, traj_length]");
@@ -853,14 +873,15 @@ int plan(m3pc_engine* e, const m3pc_plan_args_t* a, cudaStream_t st) {
   io.need_nt[M3PC_ACTIONS] = h;
   M3PC_TRY(forward(e, io, 1, st));
   if (a->guidance == M3PC_GUIDE_SAMPLING)
-    return launch_sampling_tail(io.out_mu, io.out_std, a->eps, T, h, A, 1, a->out_eval_action, a->out_sample_action, a->seed, st);
+    return launch_sampling_tail(io.out_mu, io.out_std, a->eps, T, h, A, 1, a->out_eval_action, a->out_sample_action, a->seed,
+                                e->seed_ptr_active, st);
 
   // ---- K6: candidates ----
   CandParams cp{};
   cp.mu = io.out_mu; cp.std = io.out_std; cp.eps = a->eps; cp.cand = e->cand.as<float>();
   cp.N = N; cp.h = h; cp.A = A; cp.T = T;
   cp.noise_mode = a->guidance == M3PC_GUIDE_NOISE_CRITIC ? 1 : 0;
-  cp.seed = a->seed; cp.cand_offset = a->cand_offset;
+  cp.seed = a->seed; cp.cand_offset = a->cand_offset; cp.seed_ptr = e->seed_ptr_active;
   M3PC_TRY(launch_candidates(cp, st));
   if (a->dbg_candidates)
     M3PC_CHECK_CUDA(cudaMemcpyAsync(a->dbg_candidates, cp.cand, sizeof(float) * N * h * A, cudaMemcpyDeviceToDevice, st));
@@ -908,10 +929,59 @@ int plan(m3pc_engine* e, const m3pc_plan_args_t* a, cudaStream_t st) {
   SelectParams sl{};
   sl.J = sp.J; sl.cand = cp.cand; sl.expq = a->expq;
   sl.N = N; sl.h = h; sl.A = A;
-  sl.temperature = a->temperature; sl.seed = a->seed; sl.cand_offset = a->cand_offset;
+  sl.temperature = a->temperature; sl.seed = a->seed; sl.cand_offset = a->cand_offset; sl.seed_ptr = e->seed_ptr_active;
   sl.eval_action = a->out_eval_action; sl.sample_action = a->out_sample_action;
   sl.partials = a->out_partials; sl.indices = a->dbg_indices;
   return launch_select(sl, st);
+}
+
+// m3pc_plan: eager for parity / debug calls (injected noise, debug outputs, profiling); otherwise the launch sequence is
+// captured once per (arguments, buffer addresses) into a CUDA graph and replayed -- ~70 dependent launches become one
+// submission, which is what bounds the B = 1 pass.  The Philox key travels through a device scalar so replays differ.
+int plan(m3pc_engine* e, const m3pc_plan_args_t* a, cudaStream_t st) {
+  const bool eager = !e->use_graphs || e->profile || a->eps || a->expq || a->dbg_expect_return || a->dbg_candidates || a->dbg_indices;
+  if (eager) {
+    e->seed_ptr_active = nullptr;
+    return plan_body(e, a, st);
+  }
+  m3pc_engine::PlanKey key;
+  std::memset(&key, 0, sizeof(key));
+  key.guidance = a->guidance; key.horizon = a->horizon; key.n_cand = a->n_cand; key.cand_offset = a->cand_offset;
+  key.discount = a->discount; key.temperature = a->temperature; key.lmbda = a->lmbda;
+  key.ws = a->win_states; key.wa = a->win_actions; key.wr = a->win_rewards; key.wt = a->win_returns_tok;
+  key.ev = a->out_eval_action; key.sm = a->out_sample_action; key.pt = a->out_partials;
+  if (e->plan_graphs.size() > 64) {  // callers that keep changing buffers would otherwise grow the cache without bound
+    for (auto& kv : e->plan_graphs)
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    e->plan_graphs.clear();
+  }
+  m3pc_engine::PlanGraph& pg = e->plan_graphs[key];
+  if (pg.exec == nullptr) {
+    if (pg.seen++ < 1) {  // first sighting: run eagerly (also performs every lazy cudaFuncSetAttribute)
+      e->seed_ptr_active = nullptr;
+      return plan_body(e, a, st);
+    }
+    cudaGraph_t graph = nullptr;
+    e->seed_ptr_active = e->seed_scalar.as<unsigned long long>();
+    M3PC_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int before = g_launch_count;
+    const int rc = plan_body(e, a, st);
+    pg.launches = g_launch_count - before;
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    e->seed_ptr_active = nullptr;
+    if (rc != M3PC_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    M3PC_CHECK_CUDA(ce);
+    M3PC_CHECK_CUDA(cudaGraphInstantiate(&pg.exec, graph, 0));
+    M3PC_CHECK_CUDA(cudaGraphDestroy(graph));
+    g_launch_count = before;
+  }
+  M3PC_TRY(launch_set_seed(e->seed_scalar.as<unsigned long long>(), a->seed, st));
+  M3PC_CHECK_CUDA(cudaGraphLaunch(pg.exec, st));
+  g_launch_count += pg.launches;
+  return M3PC_OK;
 }
 
 int backward_plan(m3pc_engine* e, int mode, int E, int h, const float* ws, const float* wa, const float* wr, const float* wrt,
@@ -954,7 +1024,7 @@ int backward_plan(m3pc_engine* e, int mode, int E, int h, const float* ws, const
     io2.need_nt[M3PC_ACTIONS] = 1;
     M3PC_TRY(forward(e, io2, E, st));
   }
-  return launch_sampling_tail(e->e_mu.as<float>(), e->e_std.as<float>(), eps, T, h, A, E, out_eval, out_sample, 0ull, st);
+  return launch_sampling_tail(e->e_mu.as<float>(), e->e_std.as<float>(), eps, T, h, A, E, out_eval, out_sample, 0ull, nullptr, st);
 }
 
 int create(m3pc_handle_t* out, const m3pc_config_t* cfg) {
@@ -1016,6 +1086,8 @@ int create(m3pc_handle_t* out, const m3pc_config_t* cfg) {
     M3PC_TRY(e->qb2.alloc(N * T * e->QH * 4));
     M3PC_TRY(e->qvals.alloc(N * T * 4));
   }
+  M3PC_TRY(e->seed_scalar.alloc(16));
+  if (const char* g = getenv("M3PC_NO_GRAPHS")) e->use_graphs = !(g[0] == '1');
   M3PC_CHECK_CUDA(cudaEventCreate(&e->ev0));
   M3PC_CHECK_CUDA(cudaEventCreate(&e->ev1));
   M3PC_CHECK_CUDA(cudaDeviceSynchronize());

@@ -15,10 +15,17 @@
 //               (each warp its own 32-lane TMEM quarter and half of the columns), transpose through a padded
 //               smem tile so that global accesses are full 128-byte lines, fused bias / per-token table /
 //               GELU(erf) / ReLU / residual add, 16-byte stores; `acc_empty` hands the accumulator back.
+// Clusters: with CL > 1, CL CTAs of a thread-block cluster work on CL consecutive m-tiles of the same n-tile in lockstep;
+// each loads 1/CL of the W k-block and TMA-multicasts it to all of them, so a W tile crosses the L2 -> SM fabric once per
+// cluster instead of once per CTA (the GEMMs of this model are bound by that traffic, not by the tensor pipe: K is only
+// 512..2048).  Ring slots are released cluster-wide: every CTA's tcgen05.commit multicast-arrives on all `empty` barriers.
 // Both operands are K-major, which is the layout the activations (row-major (rows, K)) and nn.Linear weights
 // ((out, in) row-major) already have -- no transposes anywhere.  Rows beyond M are zero-filled by TMA and masked
 // in the epilogue, so M is arbitrary (ragged candidate counts, B = 1).
 #include <cuda.h>
+
+#include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -38,6 +45,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode_tiled = nullptr;
 int g_num_sms = 0;
+int g_force_bn = 0, g_force_cl = 0;  // M3PC_GEMM_CONFIG="<bn>x<cl>" pins one configuration (tuning / tests)
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -77,6 +85,22 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -111,6 +135,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -150,7 +179,7 @@ __device__ __forceinline__ float apply_act(float v, bool do_gelu, bool do_relu) 
   return v;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                     const __grid_constant__ CUtensorMap tmap_w,
                                                                     void* __restrict__ C, int M, int N, int K, EpiParams ep) {
@@ -168,7 +197,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const __grid
   const int lane = threadIdx.x & 31;
   const int num_kb = K / BK;
   const int n_tiles = N / BN;
-  const int total_tiles = n_tiles * ((M + BM - 1) / BM);
+  // work unit = CL consecutive m-tiles x one n-tile; the CTAs of a cluster walk the same unit sequence in lockstep
+  const int total_tiles = n_tiles * (((M + BM - 1) / BM + CL - 1) / CL);
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  const int unit0 = blockIdx.x / CL, unit_step = gridDim.x / CL;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1u);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -176,7 +209,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const __grid
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);  // one tcgen05.commit arrival from every CTA of the cluster
     }
     mbar_init(&acc_full[0], 1);
     mbar_init(&acc_full[1], 1);
@@ -190,7 +223,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const __grid
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();  // peers must see initialised barriers before any multicast lands
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -198,14 +231,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const __grid
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+        const int m0 = ((tile / n_tiles) * CL + static_cast<int>(crank)) * BM, n0 = (tile % n_tiles) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_wait(&empty_bar[s], ph ^ 1);  // every CTA of the cluster has consumed this slot
           mbar_arrive_expect_tx(&full_bar[s], L::kStageBytes);
           uint8_t* sa = smem + s * L::kStageBytes;
           tma_load_2d(sa, &tmap_a, &full_bar[s], kb * BK, m0);
-          tma_load_2d(sa + L::kABytes, &tmap_w, &full_bar[s], kb * BK, n0);
+          if (CL == 1) {
+            tma_load_2d(sa + L::kABytes, &tmap_w, &full_bar[s], kb * BK, n0);
+          } else {  // my 1/CL slice of the W k-block, delivered to every CTA of the cluster
+            constexpr int kSliceRows = BN / CL;
+            tma_load_2d_mc(sa + L::kABytes + crank * (kSliceRows * BK * 2), &tmap_w, &full_bar[s], kb * BK,
+                           n0 + static_cast<int>(crank) * kSliceRows, kMask);
+          }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -216,7 +255,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const __grid
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = unit0; tile < total_tiles; tile += unit_step, ++it) {
         const int a = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&acc_empty[a], aph ^ 1);  // epilogue has drained this accumulator (first use passes immediately)
@@ -233,7 +272,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const __grid
             umma_bf16(tmem_d, make_smem_desc(a_addr + k * UMMA_K * 2), make_smem_desc(b_addr + k * UMMA_K * 2), idesc,
                       (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);  // slot reusable once these MMAs have read it
+          // slot reusable once these MMAs have read it -- in every CTA of the cluster, since peers multicast into it
+          if (CL == 1) umma_commit(&empty_bar[s]); else umma_commit_mc(&empty_bar[s], kMask);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         umma_commit(&acc_full[a]);  // accumulator complete
@@ -248,8 +288,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const __grid
     const bool do_gelu = ep.flags & EPI_GELU, do_relu = ep.flags & EPI_RELU, do_res = ep.flags & EPI_RESIDUAL;
     const bool out_f32 = do_res || (ep.flags & EPI_OUT_F32);
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+    for (int tile = unit0; tile < total_tiles; tile += unit_step, ++it) {
+      const int m0 = ((tile / n_tiles) * CL + static_cast<int>(crank)) * BM, n0 = (tile % n_tiles) * BN;
       const int a = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(&acc_full[a], aph);
@@ -348,7 +388,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const __grid
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();  // no CTA may exit while a peer can still multicast into / arrive on it
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
@@ -371,23 +411,49 @@ int make_tmap(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, u
   return M3PC_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CL>
 int launch(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, int M, int N, int K, const GemmEpilogue& epi, cudaStream_t st) {
   using L = SmemLayout<BN, STAGES>;
   static_assert(L::kTotal <= 227 * 1024, "shared memory budget exceeded");
   static bool configured = false;
   if (!configured) {
-    M3PC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    M3PC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
   CUtensorMap ta, tw;
   M3PC_TRY(make_tmap(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), BM));
-  M3PC_TRY(make_tmap(&tw, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), BN));
+  M3PC_TRY(make_tmap(&tw, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), BN / CL));
   EpiParams ep{epi.bias, epi.table, epi.rows_per_group > 0 ? epi.rows_per_group : 1, epi.flags};
-  const int tiles = (N / BN) * ceil_div(M, BM);
-  gemm_bf16_kernel<BN, STAGES><<<std::min(tiles, g_num_sms), GEMM_THREADS, L::kTotal, st>>>(ta, tw, C, M, N, K, ep);
+  const int units = (N / BN) * ceil_div(ceil_div(M, BM), CL);
+  const int clusters = std::min(units, g_num_sms / CL);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * CL);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  M3PC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, STAGES, CL>, ta, tw, C, M, N, K, ep));
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
+}
+
+// Modelled time of one configuration: the slower of the tensor pipe (rounds of the persistent grid x MMA cycles per tile)
+// and the L2 -> SM operand stream (measured ~10.5 TB/s on B200 for this access pattern, profiles/README.md).
+double model_time(int M, int N, int K, int bn, int cl) {
+  const int m_tiles = ceil_div(M, BM);
+  const int units = (N / bn) * ceil_div(m_tiles, cl);
+  const int clusters = std::min(units, g_num_sms / cl);
+  const double rounds = std::ceil(static_cast<double>(units) / clusters);
+  const double kb = K / BK;
+  const double t_mma = rounds * kb * 4.0 * (bn / 2.0) / 1.7e9 + 2.0e-6;                          // 64 / 128 cycles per K=16 step
+  const double bytes = static_cast<double>(units) * cl * kb * (BM * BK * 2.0 + bn * BK * 2.0 / cl);  // per CTA: own A + 1/cl of W
+  return std::max(t_mma, bytes / 10.5e12);
 }
 
 }  // namespace
@@ -405,6 +471,10 @@ int gemm_init_driver_api() {
   M3PC_CHECK_CUDA(cudaGetDevice(&dev));
   M3PC_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  if (const char* f = getenv("M3PC_GEMM_CONFIG")) {
+    if (sscanf(f, "%dx%d", &g_force_bn, &g_force_cl) != 2 || (g_force_bn != 128 && g_force_bn != 256) || (g_force_cl != 1 && g_force_cl != 2))
+      g_force_bn = g_force_cl = 0;
+  }
   return M3PC_OK;
 }
 
@@ -418,14 +488,22 @@ int gemm_bf16_tcgen05(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, i
                "gemm_bf16: operands must be 16-byte aligned");
   M3PC_TRY(gemm_init_driver_api());
   if (M <= 32 && static_cast<size_t>(M) * K * 2 <= 160 * 1024) return gemm_bf16_skinny(A, W, C, M, N, K, epi, st);
-  // tile width: minimise (rounds of the persistent grid) x (cost of one tile ~ BN); ties go to the wide tile (less L2 traffic)
-  const int m_tiles = ceil_div(M, BM);
-  if (N % 256 == 0) {
-    const long cost256 = static_cast<long>(ceil_div((N / 256) * m_tiles, g_num_sms)) * 256;
-    const long cost128 = static_cast<long>(ceil_div((N / 128) * m_tiles, g_num_sms)) * 128;
-    if (cost256 <= cost128) return launch<256, 3>(A, W, C, M, N, K, epi, st);
+  // pick tile width and cluster size by the modelled time (ties: wider tile, larger cluster = less L2 traffic)
+  struct Cand { int bn, cl; } cands[] = {{256, 2}, {256, 1}, {128, 2}, {128, 1}};
+  int best = -1;
+  double best_t = 1e30;
+  for (int i = 0; i < 4; ++i) {
+    if (N % cands[i].bn != 0) continue;
+    if (g_force_bn && (cands[i].bn != g_force_bn || cands[i].cl != g_force_cl)) continue;
+    const double t = model_time(M, N, K, cands[i].bn, cands[i].cl);
+    if (t < best_t * 0.98) { best_t = t; best = i; }
   }
-  return launch<128, 4>(A, W, C, M, N, K, epi, st);
+  switch (best) {
+    case 0: return launch<256, 3, 2>(A, W, C, M, N, K, epi, st);
+    case 1: return launch<256, 3, 1>(A, W, C, M, N, K, epi, st);
+    case 2: return launch<128, 4, 2>(A, W, C, M, N, K, epi, st);
+    default: return launch<128, 4, 1>(A, W, C, M, N, K, epi, st);
+  }
 }
 
 }  // namespace m3pc

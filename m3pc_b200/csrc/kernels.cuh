@@ -92,6 +92,7 @@ struct CandParams {
   int noise_mode;    // 0: tanh(mu + std*eps) (learner.py:285-287); 1: clamp(tanh(mu) + 0.09*eps) (learner.py:156-167)
   unsigned long long seed;
   int cand_offset;
+  const unsigned long long* seed_ptr;  // if non-null the Philox key is read from device memory (CUDA-graph replay)
 };
 int launch_candidates(const CandParams& p, cudaStream_t st);
 
@@ -131,6 +132,7 @@ struct SelectParams {
   float temperature;
   unsigned long long seed;
   int cand_offset;
+  const unsigned long long* seed_ptr;  // see CandParams
   float* eval_action;    // (A)
   float* sample_action;  // (A)
   float* partials;       // (M3PC_PARTIAL_FLOATS) or null
@@ -142,7 +144,8 @@ int launch_merge(const float* partials, int n_shards, int A, float temperature, 
 
 // mtm_sampling tail (learner.py:103-115): eval = tanh(mu[T-h]), sample = tanh(mu[T-h] + std[T-h]*eps)
 int launch_sampling_tail(const float* mu, const float* std, const float* eps, int T, int h, int A, int E, float* eval_action,
-                         float* sample_action, unsigned long long seed, cudaStream_t st);
+                         float* sample_action, unsigned long long seed, const unsigned long long* seed_ptr, cudaStream_t st);
+int launch_set_seed(unsigned long long* dst, unsigned long long seed, cudaStream_t st);
 
 // zero-shot piid fill (zeroshot_omtm/learner.py:240-246): states[:, T-h+2:-1] and states[:, :T-h+1] <- decode(pred)
 int launch_piid_fill(const float* win_states, const float* states_pred, const float* tok_mean, const float* tok_std, float* filled, int E,

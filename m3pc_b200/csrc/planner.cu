@@ -42,7 +42,8 @@ __global__ void candidates_kernel(const __grid_constant__ CandParams p) {
   const int per = p.h * p.A;
   if (i >= p.N * per) return;
   const int n = i / per, e = i - n * per, j = e / p.A, a = e - j * p.A;
-  const float eps = p.eps ? p.eps[i] : philox_normal(p.seed, static_cast<unsigned>(p.cand_offset + n), static_cast<unsigned>(e), 0u);
+  const unsigned long long seed = p.seed_ptr ? *p.seed_ptr : p.seed;
+  const float eps = p.eps ? p.eps[i] : philox_normal(seed, static_cast<unsigned>(p.cand_offset + n), static_cast<unsigned>(e), 0u);
   const int t = p.T - p.h + j;
   const float mu = p.mu[t * p.A + a];
   float v;
@@ -168,6 +169,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const __grid_consta
   __shared__ int redi[32];
   const int tid = threadIdx.x;
   const int stride_a0 = p.h * p.A;
+  const unsigned long long seed = p.seed_ptr ? *p.seed_ptr : p.seed;
   // 1. max_n J_n (+ argmax)
   float m = -INFINITY;
   int mi = 0x7fffffff;
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const __grid_consta
   for (int n = tid; n < p.N; n += SEL_THREADS) {
     const float w = expf(__fmul_rn(__fsub_rn(p.J[n], m), p.temperature));
     z += w;
-    const float q = p.expq ? p.expq[n] : philox_exp(p.seed, static_cast<unsigned>(p.cand_offset + n), 1u);
+    const float q = p.expq ? p.expq[n] : philox_exp(seed, static_cast<unsigned>(p.cand_offset + n), 1u);
     const float key = w / q;
     if (key > kbest) { kbest = key; ki = n; }
   }
@@ -254,10 +256,14 @@ __global__ void merge_kernel(const float* __restrict__ partials, int n_shards, i
   }
 }
 
+__global__ void set_seed_kernel(unsigned long long* dst, unsigned long long seed) { *dst = seed; }
+
 __global__ void sampling_tail_kernel(const float* __restrict__ mu, const float* __restrict__ std, const float* __restrict__ eps, int T, int h,
-                                     int A, int E, float* eval_action, float* sample_action, unsigned long long seed) {
+                                     int A, int E, float* eval_action, float* sample_action, unsigned long long seed,
+                                     const unsigned long long* seed_ptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= E * A) return;
+  if (seed_ptr) seed = *seed_ptr;
   const int e = i / A, a = i - e * A;
   const size_t src = (static_cast<size_t>(e) * T + (T - h)) * A + a;
   const float m = mu[src];
@@ -315,8 +321,13 @@ int launch_merge(const float* partials, int n_shards, int A, float temperature, 
   return M3PC_OK;
 }
 int launch_sampling_tail(const float* mu, const float* std, const float* eps, int T, int h, int A, int E, float* eval_action,
-                         float* sample_action, unsigned long long seed, cudaStream_t st) {
-  sampling_tail_kernel<<<ceil_div(E * A, 128), 128, 0, st>>>(mu, std, eps, T, h, A, E, eval_action, sample_action, seed);
+                         float* sample_action, unsigned long long seed, const unsigned long long* seed_ptr, cudaStream_t st) {
+  sampling_tail_kernel<<<ceil_div(E * A, 128), 128, 0, st>>>(mu, std, eps, T, h, A, E, eval_action, sample_action, seed, seed_ptr);
+  M3PC_CHECK_LAUNCH();
+  return M3PC_OK;
+}
+int launch_set_seed(unsigned long long* dst, unsigned long long seed, cudaStream_t st) {
+  set_seed_kernel<<<1, 1, 0, st>>>(dst, seed);
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
 }

@@ -390,15 +390,17 @@ def test_zeroshot_matches_reference_golden(golden_dir, precision):
     np.testing.assert_allclose(L.action_list[0].cpu().numpy(), z["piid_pl50/eval_action"], atol=atol)
 
 
-def test_zeroshot_batch_rows_equal_single_env_calls():
-    """Config-4 extension: E lock-step environments in one call; row e == the B=1 call on history e (bit-exact)."""
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_zeroshot_batch_rows_equal_single_env_calls(precision):
+    """Config-4 extension: E lock-step environments in one call; row e == the B=1 call on history e.  (Not bit-exact: B=1 runs
+    the skinny CUDA-core GEMM, E=37 the tcgen05 tiles -- different fp32 summation orders, re-rounded to bf16 between layers.)"""
     from m3pc_b200.zeroshot_learner import Learner as ZLearner
-    shape, L = _learner("hopper", "rtg_guiding", 1, 0.01, "bf16", cls=ZLearner, max_envs=37)
+    shape, L = _learner("hopper", "rtg_guiding", 1, 0.01, precision, cls=ZLearner, max_envs=37)
     hists = [syn.make_history(shape, seed=20 + e, path_length=40 + e) for e in range(37)]
     batch = L.action_piid_sample_batch(hists, eval=True, rtg=2.0).clone()
     assert batch.shape == (37, shape.act_dim)
     for e in (0, 5, 36):
         single = L.action_piid_sample(hists[e], eval=True, rtg=2.0)
-        assert torch.equal(single[0], batch[e])
+        np.testing.assert_allclose(single[0].cpu().numpy(), batch[e].cpu().numpy(), atol=1e-5 if precision == "fp32" else 1e-2)
     ids = L.action_id_sample_batch(hists, eval=True, rtg=2.0)
     assert ids.shape == (37, shape.act_dim) and torch.isfinite(ids).all()

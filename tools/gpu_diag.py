@@ -96,6 +96,53 @@ def sec_gemm_bf16():
             print("   first bad rows", rows, "cols", cols, flush=True)
 
 
+def sec_gemm_bench():
+    """Time the tensor-core GEMM on the plan's shapes (CUDA events, warm L2, 20 reps) under the current M3PC_GEMM_CONFIG."""
+    import torch
+    from m3pc_b200 import _native as nat
+    L = nat.lib()
+    torch.manual_seed(0)
+    print("M3PC_GEMM_CONFIG =", os.environ.get("M3PC_GEMM_CONFIG", "(model)"))
+    shapes = [("enc qkv", 13312, 1536, 512, 0), ("enc out", 13312, 512, 512, 2), ("enc ffn1", 13312, 2048, 512, 1), ("enc ffn2", 13312, 512, 2048, 2),
+              ("dec kv", 13312, 1024, 512, 0), ("dec ffn1", 7168, 2048, 512, 1), ("dec ffn2", 7168, 512, 2048, 2), ("full dec qkv", 32768, 1536, 512, 0),
+              ("big ffn1", 65536, 2048, 512, 1), ("odd", 625 * 13, 1536, 512, 0)]
+    for name, M, N, K, flags in shapes:
+        A = torch.randn(M, K, device="cuda").bfloat16(); W = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16(); b = torch.randn(N, device="cuda")
+        Cm = torch.randn(M, N, device="cuda") if flags & 2 else torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        ref = A.double() @ W.double().T + b.double()
+        if flags & 1: ref = torch.nn.functional.gelu(ref)
+        if flags & 2: ref = ref + Cm.double()
+        nat.check(L.m3pc_gemm_bf16(A.data_ptr(), W.data_ptr(), b.data_ptr(), Cm.data_ptr(), M, N, K, flags, None))
+        torch.cuda.synchronize()
+        err = rel_err(Cm, ref)[0]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if flags & 2: Cm.zero_()
+        e0.record()
+        for _ in range(20):
+            L.m3pc_gemm_bf16(A.data_ptr(), W.data_ptr(), b.data_ptr(), Cm.data_ptr(), M, N, K, flags, None)
+        e1.record(); torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1000 / 20
+        print(f"gemm {name:12s} M={M:6d} N={N:5d} K={K:5d} flags={flags}: {us:7.1f} us  {2.0*M*N*K/us/1e6:7.1f} TFLOP/s  err={err:.1e}", flush=True)
+
+
+def sec_pass1():
+    """Device time of pass 1 alone (B = 1): mtm_sampling = pass 1 + a 1-thread tail."""
+    import torch
+    from m3pc_b200 import synthetic as syn
+    for prec in ("bf16", "fp32"):
+        shape, sd, stats, csd, on, eng = _setup("walker2d", prec, 16)
+        T = shape.traj_length
+        ws = torch.randn(T, shape.obs_dim, device="cuda"); wa = torch.rand(T, shape.act_dim, device="cuda") * 2 - 1
+        wr = torch.randn(T, device="cuda"); wt = torch.full((T,), 1.0, device="cuda")
+        ts = []
+        for i in range(10):
+            eng.plan(guidance="mtm_sampling", horizon=4, n_cand=1, win_states=ws, win_actions=wa, win_rewards=wr, win_returns_tok=wt,
+                     discount=0.99, temperature=1.0, lmbda=0.6, seed=i)
+            torch.cuda.synchronize()
+            ts.append(eng.last_device_ms())
+        print(f"pass1[{prec}] launches={eng.last_launch_count()} ms median={sorted(ts)[5]:.3f} min={min(ts):.3f}", flush=True)
+
+
 def _setup(env, precision, max_batch, critic=False, chunk=0):
     import torch
     from m3pc_b200 import synthetic as syn
