@@ -142,6 +142,7 @@ struct m3pc_engine {
   const unsigned long long* seed_ptr_active = nullptr;  // non-null while (re)building / replaying a graph
 
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t cap_stream = nullptr;  // private stream the plan graphs are captured on
   int last_launches = 0;
   // profiling mode: one event pair per GEMM launch
   bool profile = false;
@@ -152,6 +153,7 @@ struct m3pc_engine {
   ~m3pc_engine() {
     for (auto& kv : plan_graphs)
       if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    if (cap_stream) cudaStreamDestroy(cap_stream);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     for (auto& pr : prof_events) {
@@ -961,13 +963,16 @@ int plan(m3pc_engine* e, const m3pc_plan_args_t* a, cudaStream_t st) {
       e->seed_ptr_active = nullptr;
       return plan_body(e, a, st);
     }
+    // captured on a private stream: the caller's stream may be the legacy default stream, which cannot be captured;
+    // the instantiated graph is then launched on the caller's stream
     cudaGraph_t graph = nullptr;
+    if (e->cap_stream == nullptr) M3PC_CHECK_CUDA(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
     e->seed_ptr_active = e->seed_scalar.as<unsigned long long>();
-    M3PC_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    M3PC_CHECK_CUDA(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
     const int before = g_launch_count;
-    const int rc = plan_body(e, a, st);
+    const int rc = plan_body(e, a, e->cap_stream);
     pg.launches = g_launch_count - before;
-    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    const cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
     e->seed_ptr_active = nullptr;
     if (rc != M3PC_OK) {
       if (graph) cudaGraphDestroy(graph);
