@@ -45,7 +45,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode_tiled = nullptr;
 int g_num_sms = 0;
-int g_force_bn = 0, g_force_cl = 0;  // M3PC_GEMM_CONFIG="<bn>x<cl>" pins one configuration (tuning / tests)
+int g_force_bn = 0, g_force_cl = 0;  // M3PC_GEMM_CONFIG="<bn>x<cl>" pins one single-CTA configuration (tuning / tests)
+int g_debug_skip_epi = 0;             // M3PC_GEMM_DEBUG_SKIP_EPI=1: tuning experiment, epilogue warps only hand the accumulator back
+constexpr int EPI_DEBUG_SKIP = 1 << 30;
+int g_use_2sm = 1;                   // M3PC_GEMM_2SM=0 disables the CTA-pair kernel
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -155,6 +158,48 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+
+// ---- cta_group::2 (CTA pair) variants --------------------------------------------------------------------------------
+// shared::cta address -> shared::cluster address of the same location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// TMA load into this CTA's shared memory whose completion is signalled on an mbarrier of either CTA of the pair
+// (`bar_cluster_addr` is a shared::cluster address, normally the leader's barrier)
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+// D[tmem, 256 x N split over the pair: 128 lanes in each CTA] (+)= A[256 x 16: 128 rows from each CTA's smem] * B[N x 16: N/2 rows
+// from each CTA's smem]^T; issued by one thread of the leader CTA, descriptors are the leader's (same offsets in the peer).
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all prior MMAs of this thread have completed) on the barrier at the same offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_mn(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
 struct EpiParams {
   const float* bias;
   const float* table;
@@ -177,6 +222,102 @@ __device__ __forceinline__ float apply_act(float v, bool do_gelu, bool do_relu) 
   if (do_gelu) v = gelu_erf_fast(v);
   if (do_relu) v = fmaxf(v, 0.0f);
   return v;
+}
+
+// One epilogue warp's share of a 128 x BN accumulator tile: TMEM lanes [32*quarter, +32) (= rows), columns
+// [half*BN/2, +BN/2), in chunks of 32 columns: tcgen05.ld -> padded smem transpose -> fused epilogue -> 16-byte coalesced stores.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, float* xp, void* C, int M, int N, int m0, int n0, int quarter, int half,
+                                              int lane, const EpiParams& ep) {
+  const bool do_gelu = ep.flags & EPI_GELU, do_relu = ep.flags & EPI_RELU, do_res = ep.flags & EPI_RESIDUAL;
+  const bool out_f32 = do_res || (ep.flags & EPI_OUT_F32);
+  const int row_base = m0 + quarter * 32;
+#pragma unroll 1
+  for (int c = 0; c < BN / 2; c += 32) {
+    const int col_in_tile = half * (BN / 2) + c;
+    const int col0 = n0 + col_in_tile;
+    // residual rows are independent of the accumulator: issue all 8 coalesced loads first so their DRAM/L2 latency
+    // overlaps the TMEM load and the transpose (lane -> 4 consecutive columns, 8 lanes per row, 4 rows per pass)
+    float4 res[8];
+    if (do_res) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = row_base + 4 * i + (lane >> 3);
+        res[i] = (row < M) ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(C) + static_cast<size_t>(row) * N + col0 + 4 * (lane & 7))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    uint32_t r[32];
+    tmem_ld32(tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(col_in_tile), r);
+    tmem_ld_wait();
+    // row-per-lane -> staging tile (lane = row)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<uint4*>(xp + lane * XPOSE_LD + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    __syncwarp();
+    if (out_f32) {
+      // lane -> 4 consecutive columns, 8 lanes per row, 4 rows per pass
+      const int cc = 4 * (lane & 7);
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ep.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + cc));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + (lane >> 3);
+        const int row = row_base + rr;
+        float4 v = *reinterpret_cast<const float4*>(xp + rr * XPOSE_LD + cc);
+        if (row < M) {
+          v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+          if (ep.table != nullptr) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(ep.table + static_cast<size_t>(row / ep.rows_per_group) * N + col0 + cc));
+            v.x += t4.x; v.y += t4.y; v.z += t4.z; v.w += t4.w;
+          }
+          v.x = apply_act(v.x, do_gelu, do_relu); v.y = apply_act(v.y, do_gelu, do_relu);
+          v.z = apply_act(v.z, do_gelu, do_relu); v.w = apply_act(v.w, do_gelu, do_relu);
+          float* cp = reinterpret_cast<float*>(C) + static_cast<size_t>(row) * N + col0 + cc;
+          if (do_res) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
+          *reinterpret_cast<float4*>(cp) = v;
+        }
+      }
+    } else {
+      // lane -> 8 consecutive columns, 4 lanes per row, 8 rows per pass
+      const int cc = 8 * (lane & 3);
+      float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (ep.bias != nullptr) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + cc));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + cc + 4));
+        bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = 8 * i + (lane >> 2);
+        const int row = row_base + rr;
+        const float4 v0 = *reinterpret_cast<const float4*>(xp + rr * XPOSE_LD + cc);
+        const float4 v1 = *reinterpret_cast<const float4*>(xp + rr * XPOSE_LD + cc + 4);
+        if (row < M) {
+          float v[8] = {v0.x + bb[0], v0.y + bb[1], v0.z + bb[2], v0.w + bb[3], v1.x + bb[4], v1.y + bb[5], v1.z + bb[6], v1.w + bb[7]};
+          if (ep.table != nullptr) {
+            const float* tr = ep.table + static_cast<size_t>(row / ep.rows_per_group) * N + col0 + cc;
+            const float4 t0 = __ldg(reinterpret_cast<const float4*>(tr));
+            const float4 t1 = __ldg(reinterpret_cast<const float4*>(tr + 4));
+            v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w; v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], do_gelu, do_relu);
+          uint4 o;
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]);
+          __nv_bfloat162 p1 = __floats2bfloat162_rn(v[2], v[3]);
+          __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]);
+          __nv_bfloat162 p3 = __floats2bfloat162_rn(v[6], v[7]);
+          o.x = *reinterpret_cast<uint32_t*>(&p0);
+          o.y = *reinterpret_cast<uint32_t*>(&p1);
+          o.z = *reinterpret_cast<uint32_t*>(&p2);
+          o.w = *reinterpret_cast<uint32_t*>(&p3);
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(C) + static_cast<size_t>(row) * N + col0 + cc) = o;
+        }
+      }
+    }
+    __syncwarp();  // staging tile is reused by the next chunk
+  }
 }
 
 template <int BN, int STAGES, int CL>
@@ -285,8 +426,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const __grid
     const int quarter = warp & 3;       // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
     const int half = ew >> 2;           // which half of the BN columns
     float* xp = reinterpret_cast<float*>(smem + L::kXposeOffset + ew * L::kXposeBytesPerWarp);
-    const bool do_gelu = ep.flags & EPI_GELU, do_relu = ep.flags & EPI_RELU, do_res = ep.flags & EPI_RESIDUAL;
-    const bool out_f32 = do_res || (ep.flags & EPI_OUT_F32);
     int it = 0;
     for (int tile = unit0; tile < total_tiles; tile += unit_step, ++it) {
       const int m0 = ((tile / n_tiles) * CL + static_cast<int>(crank)) * BM, n0 = (tile % n_tiles) * BN;
@@ -294,93 +433,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const __grid
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(&acc_full[a], aph);
       tc_fence_after();
-      const int row_base = m0 + quarter * 32;
-#pragma unroll 1
-      for (int c = 0; c < BN / 2; c += 32) {
-        const int col_in_tile = half * (BN / 2) + c;
-        const int col0 = n0 + col_in_tile;
-        // residual rows are independent of the accumulator: issue all 8 coalesced loads first so their DRAM/L2 latency
-        // overlaps the TMEM load and the transpose (lane -> 4 consecutive columns, 8 lanes per row, 4 rows per pass)
-        float4 res[8];
-        if (do_res) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = row_base + 4 * i + (lane >> 3);
-            res[i] = (row < M) ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(C) + static_cast<size_t>(row) * N + col0 + 4 * (lane & 7))
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(a * BN + col_in_tile), r);
-        tmem_ld_wait();
-        // row-per-lane -> staging tile (lane = row)
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(xp + lane * XPOSE_LD + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-        __syncwarp();
-        if (out_f32) {
-          // lane -> 4 consecutive columns, 8 lanes per row, 4 rows per pass
-          const int cc = 4 * (lane & 7);
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ep.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + cc));
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = 4 * i + (lane >> 3);
-            const int row = row_base + rr;
-            float4 v = *reinterpret_cast<const float4*>(xp + rr * XPOSE_LD + cc);
-            if (row < M) {
-              v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-              if (ep.table != nullptr) {
-                const float4 t4 = __ldg(reinterpret_cast<const float4*>(ep.table + static_cast<size_t>(row / ep.rows_per_group) * N + col0 + cc));
-                v.x += t4.x; v.y += t4.y; v.z += t4.z; v.w += t4.w;
-              }
-              v.x = apply_act(v.x, do_gelu, do_relu); v.y = apply_act(v.y, do_gelu, do_relu);
-              v.z = apply_act(v.z, do_gelu, do_relu); v.w = apply_act(v.w, do_gelu, do_relu);
-              float* cp = reinterpret_cast<float*>(C) + static_cast<size_t>(row) * N + col0 + cc;
-              if (do_res) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
-              *reinterpret_cast<float4*>(cp) = v;
-            }
-          }
-        } else {
-          // lane -> 8 consecutive columns, 4 lanes per row, 8 rows per pass
-          const int cc = 8 * (lane & 3);
-          float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (ep.bias != nullptr) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + cc));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + cc + 4));
-            bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rr = 8 * i + (lane >> 2);
-            const int row = row_base + rr;
-            const float4 v0 = *reinterpret_cast<const float4*>(xp + rr * XPOSE_LD + cc);
-            const float4 v1 = *reinterpret_cast<const float4*>(xp + rr * XPOSE_LD + cc + 4);
-            if (row < M) {
-              float v[8] = {v0.x + bb[0], v0.y + bb[1], v0.z + bb[2], v0.w + bb[3], v1.x + bb[4], v1.y + bb[5], v1.z + bb[6], v1.w + bb[7]};
-              if (ep.table != nullptr) {
-                const float* tr = ep.table + static_cast<size_t>(row / ep.rows_per_group) * N + col0 + cc;
-                const float4 t0 = __ldg(reinterpret_cast<const float4*>(tr));
-                const float4 t1 = __ldg(reinterpret_cast<const float4*>(tr + 4));
-                v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w; v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
-              }
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], do_gelu, do_relu);
-              uint4 o;
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]);
-              __nv_bfloat162 p1 = __floats2bfloat162_rn(v[2], v[3]);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]);
-              __nv_bfloat162 p3 = __floats2bfloat162_rn(v[6], v[7]);
-              o.x = *reinterpret_cast<uint32_t*>(&p0);
-              o.y = *reinterpret_cast<uint32_t*>(&p1);
-              o.z = *reinterpret_cast<uint32_t*>(&p2);
-              o.w = *reinterpret_cast<uint32_t*>(&p3);
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(C) + static_cast<size_t>(row) * N + col0 + cc) = o;
-            }
-          }
-        }
-        __syncwarp();  // staging tile is reused by the next chunk
-      }
+      epilogue_tile<BN>(tmem_base + static_cast<uint32_t>(a * BN), xp, C, M, N, m0, n0, quarter, half, lane, ep);
       // all of this warp's TMEM reads are complete (tcgen05.wait::ld above): hand the accumulator back
       tc_fence_before();
       if (lane == 0) mbar_arrive(&acc_empty[a]);
@@ -392,6 +445,312 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const __grid
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+  }
+}
+
+
+// ======================================================================================================================
+// CTA-pair kernel (cta_group::2) -- the production path for M > 128, N % 256 == 0.
+// A cluster of two CTAs owns a 256 x 256 output tile: one tcgen05.mma of the leader multiplies the pair's 256 x 16 A slab
+// with a 256-wide W slab of which each CTA holds (and loads) only half, so a CTA stages 32 KB per k-block instead of 48 KB.
+// Epilogue (measured to be what bounds these K = 512 .. 2048 GEMMs, profiles/r1b_*): each of the 8 epilogue warps drains its
+// 32-lane x 128-column share of the accumulator in 32-column chunks -- tcgen05.ld (lane = row) -> bias / row table /
+// activation in registers -> 16-byte shared-memory stores into a hardware-swizzled staging box (conflict free) -> one TMA
+// bulk tensor store per chunk, double buffered.  The residual epilogue never loads C: the staged tile is added to the fp32
+// residual stream in L2 by a TMA reduce-add (cp.reduce.async.bulk.tensor .add), one rounding, same result as load-add-store.
+// The bias of the tile's columns is staged in shared memory once per tile, before the accumulator is waited for.
+constexpr int NUM_EPI_WARPS_2SM = 16;  // 4 per TMEM lane quarter: enough warps per scheduler to hide TMEM / fence / store latencies
+constexpr int GEMM_THREADS_2SM = 32 * (2 + NUM_EPI_WARPS_2SM);
+
+template <int STAGES>
+struct Smem2 {
+  static constexpr int kABlk = BM * BK * 2;   // this CTA's 128 rows of one A k-block
+  static constexpr int kBBlk = 128 * BK * 2;  // this CTA's 128 of the 256 W rows of one k-block
+  static constexpr int kStageBytes = kABlk + kBBlk;
+  static constexpr int kStoreBufBytes = 32 * 64;  // one staged chunk: 32 rows x 64 bytes (16 fp32 or 32 bf16 columns), SWIZZLE_64B
+  static constexpr int kStoreOffset = STAGES * kStageBytes;
+  static constexpr int kBiasOffset = kStoreOffset + NUM_EPI_WARPS_2SM * 2 * kStoreBufBytes;
+  static constexpr int kBarOffset = kBiasOffset + NUM_EPI_WARPS_2SM * 64 * 4;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;
+};
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// arrive on a barrier of the pair's leader CTA (CUTLASS ClusterBarrier::arrive form: no cluster-scope release fence -- the
+// only thing ordered through it are TMEM reads, which tcgen05.wait::ld + tcgen05.fence::before_thread_sync already cover)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// GELU(erf) for the bf16 epilogues in 8 instructions (one MUFU): 0.5 x (1 + tanh(x (c0 + c1 x^2 + c2 x^4))) with x^2 capped at 16;
+// coefficients fitted to the erf form (max |error| 2.5e-5 with an exact tanh; tanh.approx adds <= 2^-11 relative on tanh),
+// an order of magnitude below the bf16 rounding of the stored result.  The fp32 precision mode uses erff().
+__device__ __forceinline__ float gelu_erf_tanh(float x) {
+  const float x2 = fminf(x * x, 16.0f);
+  float q = fmaf(x2, -0.00035151679f, 0.037005646f);
+  q = fmaf(x2, q, 0.79750788f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * q));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS_2SM, 1) gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                                        const __grid_constant__ CUtensorMap tmap_w,
+                                                                        const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K,
+                                                                        EpiParams ep) {
+  constexpr int BN = 256;
+  using L = Smem2<STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);  // waited on by the leader's MMA thread only
+  uint64_t* empty_bar = full_bar + STAGES;                                 // ring slot free (signalled in both CTAs)
+  uint64_t* acc_full = empty_bar + STAGES;
+  uint64_t* acc_empty = acc_full + 2;                                      // leader's copy counts both CTAs' epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int num_kb = K / BK;
+  const int n_tiles = N / BN;
+  const int total_units = n_tiles * ((M + 2 * BM - 1) / (2 * BM));
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  // units are ordered m-major and split contiguously: a pair mostly stays on one row block, whose A slab stays hot in L2
+  const int u_lo = static_cast<int>(static_cast<long long>(pair) * total_units / n_pairs);
+  const int u_hi = static_cast<int>(static_cast<long long>(pair + 1) * total_units / n_pairs);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_w);
+    prefetch_tmap(&tmap_c);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_full[0], 1);
+    mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_empty[0], 2 * NUM_EPI_WARPS_2SM);
+    mbar_init(&acc_empty[1], 2 * NUM_EPI_WARPS_2SM);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {  // the same warp of both CTAs allocates (2 accumulators of 256 fp32 columns = all of TMEM)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- TMA producer (both CTAs): own half of every operand slab, completion signalled on the LEADER's barrier ----
+      const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[0]), 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int u = u_lo; u < u_hi; ++u) {
+        const int mp = u / n_tiles, nt = u - mp * n_tiles;
+        const int m0 = (mp * 2 + static_cast<int>(crank)) * BM, n0 = nt * BN + static_cast<int>(crank) * 128;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2u * L::kStageBytes);
+          uint8_t* dst = smem + s * L::kStageBytes;
+          const uint32_t bar = full_leader + 8u * static_cast<uint32_t>(s);
+          tma_load_2d_2sm(dst, &tmap_a, bar, kb * BK, m0);
+          tma_load_2d_2sm(dst + L::kABlk, &tmap_w, bar, kb * BK, n0);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ---- MMA issuer (leader only) ----
+      constexpr uint32_t idesc = make_idesc_mn(2 * BM, BN);
+      int s = 0, it = 0;
+      uint32_t ph = 0;
+      for (int u = u_lo; u < u_hi; ++u, ++it) {
+        const int a = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&acc_empty[a], aph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(a * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+          const uint32_t b_addr = a_addr + L::kABlk;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16_2sm(tmem_d, make_smem_desc(a_addr + k * UMMA_K * 2), make_smem_desc(b_addr + k * UMMA_K * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit_2sm(&acc_full[a]);
+      }
+    }
+  } else {
+    // ---- epilogue warps (both CTAs): 32 rows (TMEM lane quarter) x 64 columns of this CTA's 128 x 256 tile each ----
+    const int ew = warp - 2;
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp may read
+    const int cgrp = ew >> 2;      // which 64 of the tile's 256 columns
+    uint8_t* sbuf = smem + L::kStoreOffset + ew * 2 * L::kStoreBufBytes;
+    float* sbias = reinterpret_cast<float*>(smem + L::kBiasOffset) + ew * 64;
+    const uint32_t acc_empty_leader = mapa_u32(smem_u32(&acc_empty[0]), 0);
+    const bool do_gelu = ep.flags & EPI_GELU, do_relu = ep.flags & EPI_RELU, do_res = ep.flags & EPI_RESIDUAL;
+    const bool out_f32 = do_res || (ep.flags & EPI_OUT_F32);
+    const bool skip = ep.flags & EPI_DEBUG_SKIP;
+    const int cw = out_f32 ? 16 : 32;  // columns per staged chunk (64 bytes of output)
+    const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);  // SWIZZLE_64B: 16-byte chunk j of row r lives at j ^ ((r >> 1) & 3)
+    int it = 0;
+    uint32_t nstore = 0;  // chunks staged so far (selects the staging buffer)
+    for (int u = u_lo; u < u_hi; ++u, ++it) {
+      const int mp = u / n_tiles, nt = u - mp * n_tiles;
+      const int row0 = (mp * 2 + static_cast<int>(crank)) * BM + quarter * 32;
+      const int colw = nt * BN + cgrp * 64;  // first column of this warp's share
+      // bias of my 64 columns -> shared memory (the previous tile's reads are done: same warp, program order)
+      {
+        float2 b2 = make_float2(0.f, 0.f);
+        if (ep.bias != nullptr) b2 = __ldg(reinterpret_cast<const float2*>(ep.bias + colw + 2 * lane));
+        *reinterpret_cast<float2*>(sbias + 2 * lane) = b2;
+        __syncwarp();
+      }
+      const int a = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&acc_full[a], aph);
+      tc_fence_after();
+      const bool live = row0 < M && !skip;
+      const int row = row0 + lane;
+      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(a * BN + cgrp * 64);
+      if (live) {
+#pragma unroll 1
+        for (int c = 0; c < 64; c += cw) {
+          const int col0 = colw + c;
+          uint32_t r[32];
+          if (out_f32) tmem_ld16(tacc + static_cast<uint32_t>(c), r); else tmem_ld32(tacc + static_cast<uint32_t>(c), r);
+          // the staging buffer about to be overwritten was handed to the TMA two chunks ago: wait until it has been read
+          uint8_t* buf = sbuf + (nstore & 1) * L::kStoreBufBytes;
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+          tmem_ld_wait();
+          if (c + cw == 64) {  // every TMEM read of this tile has landed in registers: hand the accumulator back to the MMA warp
+            tc_fence_before();
+            if (lane == 0) mbar_arrive_remote(acc_empty_leader + 8u * static_cast<uint32_t>(a));
+          }
+          if (out_f32) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sbias + c + 4 * j);
+              v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b4.x;
+              v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
+              v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z;
+              v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
+            }
+            if (ep.table != nullptr && row < M) {
+              const float* tr = ep.table + static_cast<size_t>(row / ep.rows_per_group) * N + col0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(tr + 4 * j));
+                v[4 * j + 0] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
+              }
+            }
+            if (do_gelu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = gelu_erf_tanh(v[j]);
+            }
+            if (do_relu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(buf + lane * 64 + ((static_cast<uint32_t>(j) ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sbias + c + 4 * j);
+              v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b4.x;
+              v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
+              v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z;
+              v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
+            }
+            if (ep.table != nullptr && row < M) {
+              const float* tr = ep.table + static_cast<size_t>(row / ep.rows_per_group) * N + col0;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(tr + 4 * j));
+                v[4 * j + 0] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
+              }
+            }
+            if (do_gelu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_erf_tanh(v[j]);
+            }
+            if (do_relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
+              __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+              __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+              uint4 o;
+              o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+              o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+              *reinterpret_cast<uint4*>(buf + lane * 64 + ((static_cast<uint32_t>(j) ^ sw) << 4)) = o;
+            }
+          }
+          fence_proxy_async();  // my generic-proxy writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            if (do_res) tma_reduce_add_2d(&tmap_c, buf, col0, row0); else tma_store_2d(&tmap_c, buf, col0, row0);
+            bulk_commit();
+          }
+          ++nstore;
+        }
+      } else {  // nothing to store (rows beyond M, or the tuning switch): just release the accumulator
+        tc_fence_before();
+        if (lane == 0) mbar_arrive_remote(acc_empty_leader + 8u * static_cast<uint32_t>(a));
+      }
+    }
+    if (lane == 0) bulk_wait_all();  // all of this warp's stores have been written before the CTA exits
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // no CTA may exit while its peer can still read its shared memory or arrive on its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
   }
 }
 
@@ -443,6 +802,57 @@ int launch(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, int M, int N
   return M3PC_OK;
 }
 
+
+// output tensor map: boxes of 32 rows x 64 bytes (16 fp32 / 32 bf16 columns), SWIZZLE_64B
+int make_tmap_out(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t cols, bool f32) {
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * (f32 ? 4u : 2u)};
+  cuuint32_t box[2] = {f32 ? 16u : 32u, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (output) failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return M3PC_ERR_CUDA;
+  }
+  return M3PC_OK;
+}
+
+template <int STAGES>
+int launch_2sm(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, int M, int N, int K, const GemmEpilogue& epi, cudaStream_t st) {
+  using L = Smem2<STAGES>;
+  static_assert(L::kTotal <= 227 * 1024, "shared memory budget exceeded");
+  static bool configured = false;
+  if (!configured) {
+    M3PC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_2sm_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  const bool out_f32 = (epi.flags & (EPI_RESIDUAL | EPI_OUT_F32)) != 0;
+  CUtensorMap ta, tw, tc;
+  M3PC_TRY(make_tmap(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), BM));
+  M3PC_TRY(make_tmap(&tw, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), 128));
+  M3PC_TRY(make_tmap_out(&tc, C, static_cast<uint64_t>(M), static_cast<uint64_t>(N), out_f32));
+  EpiParams ep{epi.bias, epi.table, epi.rows_per_group > 0 ? epi.rows_per_group : 1, epi.flags | (g_debug_skip_epi ? EPI_DEBUG_SKIP : 0)};
+  const int units = (N / 256) * ceil_div(M, 2 * BM);
+  const int pairs = std::min(units, g_num_sms / 2);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(GEMM_THREADS_2SM);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  M3PC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_2sm_kernel<STAGES>, ta, tw, tc, M, N, K, ep));
+  M3PC_CHECK_LAUNCH();
+  return M3PC_OK;
+}
+
 // Modelled time of one configuration: the slower of the tensor pipe (rounds of the persistent grid x MMA cycles per tile)
 // and the L2 -> SM operand stream (measured ~10.5 TB/s on B200 for this access pattern, profiles/README.md).
 double model_time(int M, int N, int K, int bn, int cl) {
@@ -471,6 +881,8 @@ int gemm_init_driver_api() {
   M3PC_CHECK_CUDA(cudaGetDevice(&dev));
   M3PC_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  if (const char* f = getenv("M3PC_GEMM_2SM")) g_use_2sm = atoi(f);
+  if (const char* f = getenv("M3PC_GEMM_DEBUG_SKIP_EPI")) g_debug_skip_epi = atoi(f);
   if (const char* f = getenv("M3PC_GEMM_CONFIG")) {
     if (sscanf(f, "%dx%d", &g_force_bn, &g_force_cl) != 2 || (g_force_bn != 128 && g_force_bn != 256) || (g_force_cl != 1 && g_force_cl != 2))
       g_force_bn = g_force_cl = 0;
@@ -488,6 +900,10 @@ int gemm_bf16_tcgen05(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, i
                "gemm_bf16: operands must be 16-byte aligned");
   M3PC_TRY(gemm_init_driver_api());
   if (M <= 32 && static_cast<size_t>(M) * K * 2 <= 160 * 1024) return gemm_bf16_skinny(A, W, C, M, N, K, epi, st);
+  // CTA-pair kernel wherever a pair has two row tiles to work on and N splits into 256-wide tiles
+  if (g_use_2sm && !g_force_bn && N % 256 == 0 && M > BM) {
+    return launch_2sm<4>(A, W, C, M, N, K, epi, st);
+  }
   // pick tile width and cluster size by the modelled time (ties: wider tile, larger cluster = less L2 traffic)
   struct Cand { int bn, cl; } cands[] = {{256, 2}, {256, 1}, {128, 2}, {128, 1}};
   int best = -1;

@@ -51,7 +51,10 @@ def test_gemm_fp32(nat, M, N, K, flags):
 
 
 @pytest.mark.parametrize("M,N,K,flags", [(128, 128, 64, 0), (17, 1536, 512, 0), (8125, 512, 512, 2), (1000, 2048, 512, 1), (333, 512, 2048, 2),
-                                         (4096, 1536, 512, 0), (130, 128, 128, 4), (1, 128, 64, 0), (20000, 2048, 512, 1), (32768, 512, 2048, 2)])
+                                         (4096, 1536, 512, 0), (130, 128, 128, 4), (1, 128, 64, 0), (20000, 2048, 512, 1), (32768, 512, 2048, 2),
+                                         # CTA-pair kernel: ragged / odd row-tile counts, one k-block, resident-A and streaming variants
+                                         (13312, 1536, 512, 0), (300, 256, 64, 4), (129, 256, 256, 0), (257, 512, 512, 2), (7168, 2048, 512, 1),
+                                         (385, 256, 1024, 0), (640, 1024, 512, 0), (13312, 512, 2048, 2), (4099, 256, 256, 4)])
 def test_gemm_bf16_tcgen05(nat, M, N, K, flags):
     """The tensor-core GEMM against an fp64 product of the same bf16 operands (operand rounding excluded):
     fp32-output epilogues must be fp32-accurate, bf16 outputs within half a bf16 ulp of the largest value."""
