@@ -25,6 +25,7 @@ constexpr int ATT_THREADS = 128;
 
 // ------------------------------------------------------------------------------------------------ fp32 path
 __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __grid_constant__ AttnParams p) {
+  PDL_PROLOGUE();
   extern __shared__ float sm[];
   const int n_q = p.n_q, S = p.n_kv, B = p.B;
   float* Vs = sm;                 // S x HD (first: keeps its float4 stores 16-byte aligned)
@@ -103,7 +104,7 @@ int launch_simple(const AttnParams& p, cudaStream_t st) {
     M3PC_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
   }
-  attention_kernel<<<p.B * p.n_head, ATT_THREADS, smem, st>>>(p);
+  M3PC_CHECK_CUDA(launch_k(attention_kernel, dim3(p.B * p.n_head), dim3(ATT_THREADS), smem, st, p));
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
 }
@@ -137,6 +138,7 @@ constexpr int MMA_WARPS = 4;  // (b, head) pairs per CTA
 // NTQ = ceil(n_q / 16) query tiles, NTK = ceil(n_kv / 16) key tiles
 template <int NTQ, int NTK>
 __global__ void __launch_bounds__(MMA_WARPS * 32) attention_mma_kernel(const __grid_constant__ AttnParams p) {
+  PDL_PROLOGUE();
   constexpr int QP = NTQ * 16, KP = NTK * 16;
   extern __shared__ __align__(128) uint8_t smem_att[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -269,7 +271,7 @@ int launch_mma(const AttnParams& p, cudaStream_t st) {
     M3PC_CHECK_CUDA(cudaFuncSetAttribute(attention_mma_kernel<NTQ, NTK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  attention_mma_kernel<NTQ, NTK><<<ceil_div(p.B * p.n_head, MMA_WARPS), MMA_WARPS * 32, smem, st>>>(p);
+  M3PC_CHECK_CUDA(launch_k(attention_mma_kernel<NTQ, NTK>, dim3(ceil_div(p.B * p.n_head, MMA_WARPS)), dim3(MMA_WARPS * 32), smem, st, p));
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
 }

@@ -128,6 +128,38 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------------
+// Every kernel of a plan is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it may be scheduled while
+// its predecessor in the stream is still draining, runs its private prologue, and blocks in griddepcontrol.wait until the
+// predecessor has completed and flushed its writes.  Rule: EVERY thread of EVERY kernel executes pdl_wait() before its first
+// global-memory access and before it can exit (a grid that finished without waiting would release ITS dependents early).
+// The trigger is issued right after the wait, so at most one dependent grid is pre-staged at a time.
+extern bool g_use_pdl;  // M3PC_NO_PDL=1 turns the attribute off (the device-side instructions are then no-ops)
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#define PDL_PROLOGUE() \
+  do {                 \
+    pdl_wait();        \
+    pdl_trigger();     \
+  } while (0)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---- kernel launchers implemented across the .cu files -----------------------------------------------
 // gemm_tcgen05.cu
 int gemm_bf16_tcgen05(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, int M, int N, int K,

@@ -47,6 +47,7 @@ __device__ __forceinline__ void warp_layernorm(const float4 (&v)[NJ], const floa
 template <int NJ, typename AT>
 __global__ void __launch_bounds__(256) embed_kernel(const __grid_constant__ EmbedParams p, float* __restrict__ x, AT* __restrict__ y,
                                                     const float* __restrict__ gamma, const float* __restrict__ beta) {
+  PDL_PROLOGUE();
   constexpr int D = NJ * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int s = blockIdx.y;
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(256) embed_kernel(const __grid_constant__ Embe
 
 template <int NJ, typename AT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __grid_constant__ LnParams p) {
+  PDL_PROLOGUE();
   constexpr int D = NJ * 128;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -118,6 +120,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __grid_constant__ 
 
 template <int NJ>
 __global__ void __launch_bounds__(256) fill_rows_kernel(const __grid_constant__ FillParams p, float* __restrict__ x) {
+  PDL_PROLOGUE();
   constexpr int D = NJ * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.y;
@@ -141,6 +144,7 @@ __global__ void __launch_bounds__(256) fill_rows_kernel(const __grid_constant__ 
 
 template <int NJ, typename AT>
 __global__ void __launch_bounds__(256) rowdot_kernel(const __grid_constant__ RowDotParams p) {
+  PDL_PROLOGUE();
   constexpr int D = NJ * 128;
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);  // r = t * B + b
@@ -187,6 +191,7 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const __grid_constant__ Row
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+  PDL_PROLOGUE();
   size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (; i < n; i += stride) out[i] = __float2bfloat16_rn(in[i]);
@@ -215,9 +220,9 @@ int launch_embed(const EmbedParams& p, int D, float* x, void* y, bool y_bf16, co
   return dispatch_d(D, [&](auto nj) -> int {
     constexpr int NJ = decltype(nj)::value;
     if (y_bf16)
-      embed_kernel<NJ, __nv_bfloat16><<<grid, 256, 0, st>>>(p, x, reinterpret_cast<__nv_bfloat16*>(y), gamma, beta);
+      M3PC_CHECK_CUDA(launch_k(embed_kernel<NJ, __nv_bfloat16>, dim3(grid), dim3(256), 0, st, p, x, reinterpret_cast<__nv_bfloat16*>(y), gamma, beta));
     else
-      embed_kernel<NJ, float><<<grid, 256, 0, st>>>(p, x, reinterpret_cast<float*>(y), gamma, beta);
+      M3PC_CHECK_CUDA(launch_k(embed_kernel<NJ, float>, dim3(grid), dim3(256), 0, st, p, x, reinterpret_cast<float*>(y), gamma, beta));
     M3PC_CHECK_LAUNCH();
     return M3PC_OK;
   });
@@ -229,9 +234,9 @@ int launch_layernorm(const LnParams& p, int D, bool out_bf16, cudaStream_t st) {
   return dispatch_d(D, [&](auto nj) -> int {
     constexpr int NJ = decltype(nj)::value;
     if (out_bf16)
-      layernorm_kernel<NJ, __nv_bfloat16><<<grid, 256, 0, st>>>(p);
+      M3PC_CHECK_CUDA(launch_k(layernorm_kernel<NJ, __nv_bfloat16>, dim3(grid), dim3(256), 0, st, p));
     else
-      layernorm_kernel<NJ, float><<<grid, 256, 0, st>>>(p);
+      M3PC_CHECK_CUDA(launch_k(layernorm_kernel<NJ, float>, dim3(grid), dim3(256), 0, st, p));
     M3PC_CHECK_LAUNCH();
     return M3PC_OK;
   });
@@ -242,7 +247,7 @@ int launch_fill_rows(const FillParams& p, int D, float* x, cudaStream_t st) {
   dim3 grid(ceil_div(p.B, 64), p.n);
   return dispatch_d(D, [&](auto nj) -> int {
     constexpr int NJ = decltype(nj)::value;
-    fill_rows_kernel<NJ><<<grid, 256, 0, st>>>(p, x);
+    M3PC_CHECK_CUDA(launch_k(fill_rows_kernel<NJ>, dim3(grid), dim3(256), 0, st, p, x));
     M3PC_CHECK_LAUNCH();
     return M3PC_OK;
   });
@@ -254,9 +259,9 @@ int launch_rowdot(const RowDotParams& p, int D, bool y_bf16, cudaStream_t st) {
   return dispatch_d(D, [&](auto nj) -> int {
     constexpr int NJ = decltype(nj)::value;
     if (y_bf16)
-      rowdot_kernel<NJ, __nv_bfloat16><<<grid, 256, 0, st>>>(p);
+      M3PC_CHECK_CUDA(launch_k(rowdot_kernel<NJ, __nv_bfloat16>, dim3(grid), dim3(256), 0, st, p));
     else
-      rowdot_kernel<NJ, float><<<grid, 256, 0, st>>>(p);
+      M3PC_CHECK_CUDA(launch_k(rowdot_kernel<NJ, float>, dim3(grid), dim3(256), 0, st, p));
     M3PC_CHECK_LAUNCH();
     return M3PC_OK;
   });
@@ -265,7 +270,7 @@ int launch_rowdot(const RowDotParams& p, int D, bool y_bf16, cudaStream_t st) {
 int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t st) {
   if (n == 0) return M3PC_OK;
   const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
-  f32_to_bf16_kernel<<<blocks, 256, 0, st>>>(in, out, n);
+  M3PC_CHECK_CUDA(launch_k(f32_to_bf16_kernel, dim3(blocks), dim3(256), 0, st, in, out, n));
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
 }

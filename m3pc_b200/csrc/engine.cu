@@ -18,6 +18,7 @@
 namespace m3pc {
 
 thread_local int g_launch_count = 0;
+bool g_use_pdl = true;
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 
@@ -121,6 +122,8 @@ struct m3pc_engine {
 
   // workspaces (per chunk)
   DevBuf X, XS, Y, Y2, QKV, QSEL, ATT, HID, ENC;
+  DevBuf fb_xd, fb_bar;  // fused B = 1 path: decoder-embedding scratch, grid-barrier state
+  bool use_fused_b1 = true;
   // planner buffers
   DevBuf p1_mu, p1_std, cand, pred_states, pred_rewards, pred_returns, sa, qa, qb1, qb2, qvals, J, filled, e_mu, e_std;
 
@@ -734,6 +737,82 @@ int forward_chunk(m3pc_engine* e, const FwdIO& io, int b0, int Bc, cudaStream_t 
     }
   M3PC_REQUIRE(S > 0, "forward: every token is masked");
 
+  // ---- which head rows does the caller consume? ----
+  NeedSet need;
+  const float* outp[4] = {io.out_states, io.out_mu, io.out_rewards, io.out_returns};
+  for (int k = 0; k < 4; ++k) {
+    need.q0[k] = need.n;
+    if (outp[k] == nullptr) continue;
+    const int t0 = io.need_nt[k] < 0 ? 0 : io.need_t0[k];
+    const int nt = io.need_nt[k] < 0 ? T : io.need_nt[k];
+    M3PC_REQUIRE(t0 >= 0 && nt >= 0 && t0 + nt <= T, "need range out of bounds");
+    need.t0[k] = t0;
+    need.nt[k] = nt;
+    for (int t = t0; t < t0 + nt; ++t) need.tok[need.n++] = k * T + t;
+  }
+
+  // ---- B = 1: the whole encoder + restricted decoder in one cooperative kernel (fused_b1.cu) ----
+  if (Bc == 1 && e->bf16 && e->use_fused_b1 && e->Ld == 1 && e->Le >= 1 && e->Le <= FB_MAX_LAYERS && need.n >= 1 && need.n < 4 * T &&
+      need.n <= FB_MAX_ROWS && S <= FB_MAX_ROWS && D == 512 && fused_b1_smem_bytes(D, S, need.n) <= 200 * 1024) {
+    FusedB1Params fp{};
+    fp.S = S; fp.n_enc = e->Le; fp.T4 = 4 * T; fp.n_need = need.n;
+    auto fill_layer = [](FusedLayer& f, const LayerW& w) {
+      f.in_w = w.in_w16; f.out_w = w.out_w16; f.l1_w = w.l1_w16; f.l2_w = w.l2_w16;
+      f.in_b = w.in_b; f.out_b = w.out_b; f.l1_b = w.l1_b; f.l2_b = w.l2_b;
+      f.n1_w = w.n1_w; f.n1_b = w.n1_b; f.n2_w = w.n2_w; f.n2_b = w.n2_b;
+    };
+    for (int l = 0; l < e->Le; ++l) fill_layer(fp.enc[l], e->enc.layers[l]);
+    fill_layer(fp.dec, e->dec.layers[0]);
+    fp.enc_norm_w = e->enc.norm_w; fp.enc_norm_b = e->enc.norm_b;
+    fp.fnorm_w = e->dec.norm_w; fp.fnorm_b = e->dec.norm_b;
+    for (int k = 0; k < 4; ++k) {
+      fp.head_g[k] = e->head_ln_w[k]; fp.head_b[k] = e->head_ln_b[k];
+      fp.dec_w[k] = e->dec_w16[k];
+    }
+    fp.dec_cvec = e->dec_cvec; fp.dec_maskrow = e->dec_maskrow;
+    fp.const_qkv = e->const_qkv.as<__nv_bfloat16>();
+    for (int k = 0; k <= 4; ++k) fp.mod_row0[k] = 0;
+    for (int s = 0; s < S; ++s) {
+      const int k = enc_mod[s], t = enc_t[s], d = e->dims[k];
+      const ModSrc& ms = io.src[k];
+      EmbedTok& tk = fp.tok[s];
+      if (ms.base2 != nullptr && t >= ms.t_split) {
+        tk.src = ms.base2 + static_cast<size_t>(b0) * ms.bstride2 + static_cast<size_t>(t - ms.t_split) * d;
+      } else {
+        tk.src = ms.base + static_cast<size_t>(b0) * ms.bstride + static_cast<size_t>(t) * d;
+      }
+      tk.bstride = 0;
+      tk.wt = e->enc_wt[k];
+      tk.cvec = e->enc_cvec + (static_cast<size_t>(k) * T + t) * D;
+      tk.nmean = ms.normalize ? e->tok_mean[k] : nullptr;
+      tk.nstd = ms.normalize ? e->tok_std[k] : nullptr;
+      tk.d = d;
+      fp.enc_dectok[s] = static_cast<unsigned char>(k * T + t);
+      for (int kk = k + 1; kk <= 4; ++kk) fp.mod_row0[kk] = s + 1;
+    }
+    for (int j = 0; j < 4 * T; ++j) fp.dec_src[j] = static_cast<signed char>(dec_src[j]);
+    for (int qi = 0; qi < need.n; ++qi) {
+      fp.need_tok[qi] = static_cast<unsigned char>(need.tok[qi]);
+      fp.need_mod[qi] = static_cast<unsigned char>(need.tok[qi] / T);
+    }
+    fp.X = e->X.as<float>(); fp.Xd = e->fb_xd.as<float>(); fp.XS = e->XS.as<float>();
+    fp.QKV = e->QKV.as<__nv_bfloat16>(); fp.ATT = e->ATT.as<__nv_bfloat16>(); fp.HID = e->HID.as<__nv_bfloat16>();
+    fp.Y = e->Y.as<__nv_bfloat16>(); fp.Y2 = e->Y2.as<__nv_bfloat16>();
+    fp.bar = e->fb_bar.as<unsigned>();
+    { static const bool tr = getenv("M3PC_FB_TRACE") != nullptr; fp.trace = tr ? 1 : 0; }
+    // the actor head is folded into the kernel's last phase; the MLP heads of the other modalities keep their own launches
+    FwdIO io_rest = io;
+    if (io.out_mu != nullptr && need.nt[M3PC_ACTIONS] > 0) {
+      fp.mu_w = e->mu_w; fp.mu_b = e->mu_b; fp.ls_w = e->ls_w; fp.ls_b = e->ls_b;
+      fp.out_mu = io.out_mu + static_cast<size_t>(b0) * T * e->act;
+      fp.out_std = io.out_std + static_cast<size_t>(b0) * T * e->act;
+      fp.act_dim = e->act;
+      io_rest.out_mu = io_rest.out_std = nullptr;
+    }
+    M3PC_TRY(launch_fused_b1(fp, D, st));
+    return heads(e, io_rest, need, e->Y.p, e->Y2.p, b0, 1, st);
+  }
+
   // ---- K1: embed + gather + first LayerNorm ----
   EmbedParams ep{};
   ep.n_tok = S;
@@ -779,19 +858,6 @@ int forward_chunk(m3pc_engine* e, const FwdIO& io, int b0, int Bc, cudaStream_t 
     M3PC_TRY(launch_layernorm(ln, D, e->bf16, st));
   }
 
-  // ---- which head rows does the caller consume? ----
-  NeedSet need;
-  const float* outp[4] = {io.out_states, io.out_mu, io.out_rewards, io.out_returns};
-  for (int k = 0; k < 4; ++k) {
-    need.q0[k] = need.n;
-    if (outp[k] == nullptr) continue;
-    const int t0 = io.need_nt[k] < 0 ? 0 : io.need_t0[k];
-    const int nt = io.need_nt[k] < 0 ? T : io.need_nt[k];
-    M3PC_REQUIRE(t0 >= 0 && nt >= 0 && t0 + nt <= T, "need range out of bounds");
-    need.t0[k] = t0;
-    need.nt[k] = nt;
-    for (int t = t0; t < t0 + nt; ++t) need.tok[need.n++] = k * T + t;
-  }
   if (need.n == 0) return M3PC_OK;
   if (e->Ld == 1 && need.n < 4 * T) return decode_restricted(e, io, enc_out, dec_src, S, need, b0, Bc, st);
   return decode_full(e, io, enc_out, dec_src, need, b0, Bc, st);
@@ -1092,7 +1158,12 @@ int create(m3pc_handle_t* out, const m3pc_config_t* cfg) {
     M3PC_TRY(e->qvals.alloc(N * T * 4));
   }
   M3PC_TRY(e->seed_scalar.alloc(16));
+  M3PC_TRY(e->fb_xd.alloc(static_cast<size_t>(FB_MAX_ROWS) * D * 4));
+  M3PC_TRY(e->fb_bar.alloc(16));
+  M3PC_CHECK_CUDA(cudaMemset(e->fb_bar.p, 0, 16));
+  if (const char* g = getenv("M3PC_NO_FUSED_B1")) e->use_fused_b1 = !(g[0] == '1');
   if (const char* g = getenv("M3PC_NO_GRAPHS")) e->use_graphs = !(g[0] == '1');
+  if (const char* g = getenv("M3PC_NO_PDL")) g_use_pdl = !(g[0] == '1');
   M3PC_CHECK_CUDA(cudaEventCreate(&e->ev0));
   M3PC_CHECK_CUDA(cudaEventCreate(&e->ev1));
   M3PC_CHECK_CUDA(cudaDeviceSynchronize());

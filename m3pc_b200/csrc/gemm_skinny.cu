@@ -27,6 +27,7 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]) {
 __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ W,
                                                                  void* __restrict__ C, int M, int N, int K, const float* __restrict__ bias,
                                                                  const float* __restrict__ table, int rows_per_group, int flags) {
+  PDL_PROLOGUE();
   extern __shared__ __align__(16) uint8_t sk_smem[];
   __nv_bfloat16* As = reinterpret_cast<__nv_bfloat16*>(sk_smem);  // M x K
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -121,8 +122,8 @@ int gemm_bf16_skinny(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, in
     M3PC_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
   }
-  gemm_skinny_kernel<<<ceil_div(N, SK_THREADS / 32), SK_THREADS, smem, st>>>(A, W, C, M, N, K, epi.bias, epi.table,
-                                                                          epi.rows_per_group > 0 ? epi.rows_per_group : 1, epi.flags);
+  M3PC_CHECK_CUDA(launch_k(gemm_skinny_kernel, dim3(ceil_div(N, SK_THREADS / 32)), dim3(SK_THREADS), smem, st, A, W, C, M, N, K, epi.bias, epi.table,
+                                                                          epi.rows_per_group > 0 ? epi.rows_per_group : 1, epi.flags));
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
 }

@@ -367,6 +367,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_kernel(const __grid
   if (CL > 1) cluster_sync_all(); else __syncthreads();  // peers must see initialised barriers before any multicast lands
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  PDL_PROLOGUE();  // everything above is private to this CTA; operands of the previous kernel are touched only below
 
   if (warp == 0) {
     if (lane == 0) {
@@ -568,6 +569,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_2SM, 1) gemm_bf16_2sm_kernel(cons
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  PDL_PROLOGUE();  // everything above is private to this CTA pair; operands of the previous kernel are touched only below
 
   if (warp == 0) {
     if (lane == 0) {
@@ -790,13 +792,15 @@ int launch(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, int M, int N
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = L::kTotal;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_use_pdl ? 2 : 1;
   M3PC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, STAGES, CL>, ta, tw, C, M, N, K, ep));
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
@@ -841,13 +845,15 @@ int launch_2sm(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, int M, i
   cfg.blockDim = dim3(GEMM_THREADS_2SM);
   cfg.dynamicSmemBytes = L::kTotal;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_use_pdl ? 2 : 1;
   M3PC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_2sm_kernel<STAGES>, ta, tw, tc, M, N, K, ep));
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;

@@ -25,6 +25,51 @@ struct EmbedParams {
 // x (n_tok*B, D) fp32 residual stream, y (n_tok*B, D) = LayerNorm(x; gamma, beta) in AT.
 int launch_embed(const EmbedParams& p, int D, float* x, void* y, bool y_bf16, const float* gamma, const float* beta, cudaStream_t st);
 
+// ---- fused B = 1 forward (fused_b1.cu): encoder + restricted single-layer decoder in one cooperative kernel -------
+constexpr int FB_MAX_ROWS = 32;    // encoder tokens / needed decoder rows
+constexpr int FB_MAX_LAYERS = 4;   // encoder layers
+struct FusedLayer {
+  const __nv_bfloat16 *in_w, *out_w, *l1_w, *l2_w;
+  const float *in_b, *out_b, *l1_b, *l2_b, *n1_w, *n1_b, *n2_w, *n2_b;
+};
+struct FusedB1Params {
+  int S, n_enc, T4, n_need;
+  EmbedTok tok[FB_MAX_ROWS];             // encoder (kept) tokens, modality-major
+  FusedLayer enc[FB_MAX_LAYERS];
+  FusedLayer dec;
+  const float *enc_norm_w, *enc_norm_b;  // final encoder norm
+  const float *fnorm_w, *fnorm_b;        // final decoder norm
+  const float* head_g[4];                // head LayerNorm per modality (null: actions, the actor reads the final norm)
+  const float* head_b[4];
+  const __nv_bfloat16* dec_w[4];         // decoder_embed weights per modality
+  const float* dec_cvec;                 // (4T, D) bias + per-dim + pos
+  const float* dec_maskrow;              // (4T, D) decoder input of a masked token
+  const __nv_bfloat16* const_qkv;        // (4T, 3D) [Q | K | V] of the masked-token rows
+  int mod_row0[5];                       // encoder rows of modality k: [mod_row0[k], mod_row0[k + 1])
+  signed char dec_src[MAX_TOK];          // decoder token j -> encoder row, or -1 (masked)
+  unsigned char enc_dectok[FB_MAX_ROWS]; // encoder row -> decoder token
+  unsigned char need_tok[FB_MAX_ROWS];   // needed decoder tokens
+  unsigned char need_mod[FB_MAX_ROWS];   // their modality
+  // scratch (global; every buffer at least 32 rows)
+  float* X;             // (S, D) encoder residual stream
+  float* Xd;            // (S, D) decoder embedding of the kept tokens
+  float* XS;            // (n_need, D) decoder residual stream of the needed rows
+  __nv_bfloat16* QKV;   // (S, 3D)
+  __nv_bfloat16* ATT;   // (max(S, n_need), D)
+  __nv_bfloat16* HID;   // (max(S, n_need), 4D)
+  // outputs
+  __nv_bfloat16* Y;     // (n_need, D) final norm
+  __nv_bfloat16* Y2;    // (n_need, D) head norm
+  // optional fused actor head (DiagGaussianActor) for the needed action rows: out_mu / out_std are (T, A) of this batch row
+  const float *mu_w, *mu_b, *ls_w, *ls_b;
+  float *out_mu, *out_std;
+  int act_dim;
+  unsigned* bar;        // grid barrier state {count, generation}, zero-initialised once
+  int trace;            // debug: CTA 0 prints per-phase cycle counts (M3PC_FB_TRACE=1)
+};
+size_t fused_b1_smem_bytes(int D, int S, int n_need);
+int launch_fused_b1(const FusedB1Params& p, int D, cudaStream_t st);
+
 // ---- LayerNorm family ---------------------------------------------------------------------------------
 // y1 = LN(x; g1, b1) (optional), y2 = LN(y1; g2[grp], b2[grp]) (optional, grp = row / rows_per_group, skipped where g2[grp]==0)
 struct LnParams {

@@ -38,6 +38,7 @@ __device__ __forceinline__ float philox_exp(unsigned long long seed, unsigned gi
 }
 
 __global__ void candidates_kernel(const __grid_constant__ CandParams p) {
+  PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int per = p.h * p.A;
   if (i >= p.N * per) return;
@@ -57,6 +58,7 @@ __global__ void candidates_kernel(const __grid_constant__ CandParams p) {
 }
 
 __global__ void critic_input_kernel(const __grid_constant__ CriticInParams p) {
+  PDL_PROLOGUE();
   const int w = p.ld;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.N * p.h * w) return;
@@ -79,6 +81,7 @@ __global__ void critic_input_kernel(const __grid_constant__ CriticInParams p) {
 __global__ void critic_out_kernel(const float* __restrict__ h1, const float* __restrict__ h2, const float* __restrict__ w1,
                                   const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
                                   float* __restrict__ q, int rows, int H) {
+  PDL_PROLOGUE();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -93,6 +96,7 @@ __global__ void critic_out_kernel(const float* __restrict__ h1, const float* __r
 }
 
 __global__ void score_kernel(const __grid_constant__ ScoreParams p) {
+  PDL_PROLOGUE();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= p.N) return;
   const int T = p.T, h = p.h;
@@ -165,6 +169,7 @@ __device__ __forceinline__ void block_argmax(float& v, int& idx, float* redv, in
 }
 
 __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const __grid_constant__ SelectParams p) {
+  PDL_PROLOGUE();
   __shared__ float redv[32];
   __shared__ int redi[32];
   const int tid = threadIdx.x;
@@ -228,6 +233,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const __grid_consta
 // log-sum-exp merge of per-shard records; one warp is plenty (n_shards <= 32... loop otherwise)
 __global__ void merge_kernel(const float* __restrict__ partials, int n_shards, int A, float temperature, float* eval_action,
                              float* sample_action, int* indices) {
+  PDL_PROLOGUE();
   if (threadIdx.x != 0) return;
   float m = -INFINITY;
   for (int g = 0; g < n_shards; ++g) m = fmaxf(m, partials[g * M3PC_PARTIAL_FLOATS + 0]);
@@ -261,6 +267,7 @@ __global__ void set_seed_kernel(unsigned long long* dst, unsigned long long seed
 __global__ void sampling_tail_kernel(const float* __restrict__ mu, const float* __restrict__ std, const float* __restrict__ eps, int T, int h,
                                      int A, int E, float* eval_action, float* sample_action, unsigned long long seed,
                                      const unsigned long long* seed_ptr) {
+  PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= E * A) return;
   if (seed_ptr) seed = *seed_ptr;
@@ -274,6 +281,7 @@ __global__ void sampling_tail_kernel(const float* __restrict__ mu, const float* 
 
 __global__ void piid_fill_kernel(const float* __restrict__ win_states, const float* __restrict__ states_pred, const float* __restrict__ tok_mean,
                                  const float* __restrict__ tok_std, float* __restrict__ filled, int E, int T, int h, int obs) {
+  PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= E * T * obs) return;
   const int c = i % obs, t = (i / obs) % T;
@@ -286,54 +294,54 @@ __global__ void piid_fill_kernel(const float* __restrict__ win_states, const flo
 
 int launch_candidates(const CandParams& p, cudaStream_t st) {
   const int n = p.N * p.h * p.A;
-  candidates_kernel<<<ceil_div(n, 256), 256, 0, st>>>(p);
+  M3PC_CHECK_CUDA(launch_k(candidates_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, st, p));
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
 }
 int launch_critic_input(const CriticInParams& p, cudaStream_t st) {
   const int n = p.N * p.h * p.ld;
-  critic_input_kernel<<<ceil_div(n, 256), 256, 0, st>>>(p);
+  M3PC_CHECK_CUDA(launch_k(critic_input_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, st, p));
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
 }
 int launch_critic_out(const float* h1, const float* h2, const float* w1, const float* b1, const float* w2, const float* b2, float* q,
                       int rows, int H, cudaStream_t st) {
-  critic_out_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(h1, h2, w1, b1, w2, b2, q, rows, H);
+  M3PC_CHECK_CUDA(launch_k(critic_out_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, st, h1, h2, w1, b1, w2, b2, q, rows, H));
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
 }
 int launch_score(const ScoreParams& p, cudaStream_t st) {
   M3PC_REQUIRE(p.h >= 1 && p.h <= M3PC_MAX_T, "score: bad horizon");
-  score_kernel<<<ceil_div(p.N, 128), 128, 0, st>>>(p);
+  M3PC_CHECK_CUDA(launch_k(score_kernel, dim3(ceil_div(p.N, 128)), dim3(128), 0, st, p));
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
 }
 int launch_select(const SelectParams& p, cudaStream_t st) {
   M3PC_REQUIRE(p.A <= M3PC_MAX_ACT && p.N >= 1, "select: bad shape");
-  select_kernel<<<1, SEL_THREADS, 0, st>>>(p);
+  M3PC_CHECK_CUDA(launch_k(select_kernel, dim3(1), dim3(SEL_THREADS), 0, st, p));
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
 }
 int launch_merge(const float* partials, int n_shards, int A, float temperature, float* eval_action, float* sample_action, int* indices,
                  cudaStream_t st) {
-  merge_kernel<<<1, 32, 0, st>>>(partials, n_shards, A, temperature, eval_action, sample_action, indices);
+  M3PC_CHECK_CUDA(launch_k(merge_kernel, dim3(1), dim3(32), 0, st, partials, n_shards, A, temperature, eval_action, sample_action, indices));
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
 }
 int launch_sampling_tail(const float* mu, const float* std, const float* eps, int T, int h, int A, int E, float* eval_action,
                          float* sample_action, unsigned long long seed, const unsigned long long* seed_ptr, cudaStream_t st) {
-  sampling_tail_kernel<<<ceil_div(E * A, 128), 128, 0, st>>>(mu, std, eps, T, h, A, E, eval_action, sample_action, seed, seed_ptr);
+  M3PC_CHECK_CUDA(launch_k(sampling_tail_kernel, dim3(ceil_div(E * A, 128)), dim3(128), 0, st, mu, std, eps, T, h, A, E, eval_action, sample_action, seed, seed_ptr));
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
 }
 int launch_set_seed(unsigned long long* dst, unsigned long long seed, cudaStream_t st) {
-  set_seed_kernel<<<1, 1, 0, st>>>(dst, seed);
+  M3PC_CHECK_CUDA(launch_k(set_seed_kernel, dim3(1), dim3(1), 0, st, dst, seed));
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
 }
 int launch_piid_fill(const float* win_states, const float* states_pred, const float* tok_mean, const float* tok_std, float* filled, int E,
                      int T, int h, int obs, cudaStream_t st) {
-  piid_fill_kernel<<<ceil_div(E * T * obs, 256), 256, 0, st>>>(win_states, states_pred, tok_mean, tok_std, filled, E, T, h, obs);
+  M3PC_CHECK_CUDA(launch_k(piid_fill_kernel, dim3(ceil_div(E * T * obs, 256)), dim3(256), 0, st, win_states, states_pred, tok_mean, tok_std, filled, E, T, h, obs));
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
 }

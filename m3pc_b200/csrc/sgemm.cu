@@ -14,6 +14,7 @@ constexpr int SB_M = 64, SB_N = 64, SB_K = 16;
 __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, const float* __restrict__ W,
                                                     float* __restrict__ C, int M, int N, int K, const float* __restrict__ bias,
                                                     const float* __restrict__ table, int rows_per_group, int flags) {
+  PDL_PROLOGUE();
   __shared__ float As[SB_K][SB_M + 4];
   __shared__ float Ws[SB_K][SB_N + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -97,7 +98,7 @@ int gemm_fp32(const float* A, const float* W, float* C, int M, int N, int K, con
   M3PC_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_fp32: empty problem");
   M3PC_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, "gemm_fp32: operands must be 16-byte aligned");
   dim3 grid(ceil_div(N, SB_N), ceil_div(M, SB_M));
-  sgemm_kernel<<<grid, 256, 0, st>>>(A, W, C, M, N, K, epi.bias, epi.table, epi.rows_per_group > 0 ? epi.rows_per_group : 1, epi.flags);
+  M3PC_CHECK_CUDA(launch_k(sgemm_kernel, dim3(grid), dim3(256), 0, st, A, W, C, M, N, K, epi.bias, epi.table, epi.rows_per_group > 0 ? epi.rows_per_group : 1, epi.flags));
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
 }
