@@ -124,6 +124,7 @@ struct m3pc_engine {
   DevBuf X, XS, Y, Y2, QKV, QSEL, ATT, HID, ENC;
   DevBuf fb_xd, fb_bar;  // fused B = 1 path: decoder-embedding scratch, grid-barrier state
   bool use_fused_b1 = true;
+  bool use_mega = false;  // encoder megakernel: measured slower than the per-op path at <= 1024 rows per chunk; M3PC_MEGA=1 enables
   // planner buffers
   DevBuf p1_mu, p1_std, cand, pred_states, pred_rewards, pred_returns, sa, qa, qb1, qb2, qvals, J, filled, e_mu, e_std;
 
@@ -835,12 +836,34 @@ int forward_chunk(m3pc_engine* e, const FwdIO& io, int b0, int Bc, cudaStream_t 
     tk.d = d;
   }
   const LayerW& first = e->Le > 0 ? e->enc.layers[0] : e->dec.layers[0];
+  // big batches: candidate-major tiles + the encoder megakernel (encoder_mega.cu); otherwise one launch per op
+  const int cpt = encoder_mega_cpt(S);
+  const bool mega = e->bf16 && e->use_mega && D == 512 && cpt > 0 && e->Le >= 1 && e->Le <= 4 && Bc >= 32 &&
+                    static_cast<size_t>(ceil_div(ceil_div(Bc, cpt), 2)) * 256 <= static_cast<size_t>(4) * T * e->chunk + 128;
+  ep.cpt = mega ? cpt : 0;
   M3PC_TRY(launch_embed(ep, D, e->X.as<float>(), e->Y.p, e->bf16, e->Le > 0 ? first.n1_w : e->enc.norm_w,
                         e->Le > 0 ? first.n1_b : e->enc.norm_b, st));
   void* enc_out = e->Le > 0 ? e->ENC.p : e->Y.p;
 
+  if (mega) {
+    EncoderMegaArgs ma{};
+    ma.D = D; ma.S = S; ma.B = Bc; ma.n_layers = e->Le;
+    for (int l = 0; l < e->Le; ++l) {
+      const LayerW& w = e->enc.layers[l];
+      EncoderMegaLayer& m = ma.layer[l];
+      m.in_w = w.in_w16; m.out_w = w.out_w16; m.l1_w = w.l1_w16; m.l2_w = w.l2_w16;
+      m.in_b = w.in_b; m.out_b = w.out_b; m.l1_b = w.l1_b; m.l2_b = w.l2_b;
+      m.n2_w = w.n2_w; m.n2_b = w.n2_b;
+      m.post_w = l + 1 < e->Le ? e->enc.layers[l + 1].n1_w : e->enc.norm_w;
+      m.post_b = l + 1 < e->Le ? e->enc.layers[l + 1].n1_b : e->enc.norm_b;
+    }
+    ma.X = e->X.as<float>(); ma.Y = e->Y.as<__nv_bfloat16>(); ma.QKV = e->QKV.as<__nv_bfloat16>();
+    ma.ATT = e->ATT.as<__nv_bfloat16>(); ma.HID = e->HID.as<__nv_bfloat16>(); ma.ENC = e->ENC.as<__nv_bfloat16>();
+    M3PC_TRY(launch_encoder_mega(ma, st));
+  }
+
   // ---- encoder stack (mtm_model.py:379-391, 619-644) ----
-  for (int l = 0; l < e->Le; ++l) {
+  for (int l = 0; l < (mega ? 0 : e->Le); ++l) {
     M3PC_TRY(block(e, e->enc.layers[l], Bc, S, st));
     LnParams ln{};
     ln.x = e->X.as<float>();
@@ -1162,6 +1185,7 @@ int create(m3pc_handle_t* out, const m3pc_config_t* cfg) {
   M3PC_TRY(e->fb_bar.alloc(16));
   M3PC_CHECK_CUDA(cudaMemset(e->fb_bar.p, 0, 16));
   if (const char* g = getenv("M3PC_NO_FUSED_B1")) e->use_fused_b1 = !(g[0] == '1');
+  if (const char* g = getenv("M3PC_MEGA")) e->use_mega = g[0] == '1';
   if (const char* g = getenv("M3PC_NO_GRAPHS")) e->use_graphs = !(g[0] == '1');
   if (const char* g = getenv("M3PC_NO_PDL")) g_use_pdl = !(g[0] == '1');
   M3PC_CHECK_CUDA(cudaEventCreate(&e->ev0));
