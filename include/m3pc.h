@@ -162,6 +162,13 @@ int m3pc_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int
                    int32_t flags, void* stream);
 int m3pc_gemm_fp32(const float* A, const float* W, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
                    int32_t flags, void* stream);
+/* n independent bf16 GEMMs (arrays of n operands / shapes / flags as in m3pc_gemm_bf16; bias may be NULL or hold NULLs)
+ * in as few launches as possible: up to 4 problems whose N are multiples of 256 share one launch of the CTA-pair
+ * tensor-core kernel -- how the engine issues the decoder-embedding runs, the decoder K/V + Q projections, the
+ * per-modality output heads (mtm_model.py:646-661, :428-433) and the two critics (finetune_omtm/model.py:146-171). */
+int m3pc_gemm_bf16_grouped(int32_t n, const void* const* A, const void* const* W, const float* const* bias,
+                           void* const* C, const int32_t* M, const int32_t* N, const int32_t* K, const int32_t* flags,
+                           void* stream);
 /* y = LayerNorm(x) over the last dim (eps 1e-5); x fp32 (M,D); y bf16 (out_bf16=1) or fp32. */
 int m3pc_layernorm(const float* x, const float* gamma, const float* beta, void* y, int32_t M, int32_t D,
                    int32_t out_bf16, void* stream);

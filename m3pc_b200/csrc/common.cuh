@@ -165,6 +165,15 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
 int gemm_bf16_tcgen05(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, int M, int N, int K,
                       const GemmEpilogue& epi, cudaStream_t st);
 int gemm_init_driver_api();
+// several independent bf16 GEMMs in one launch of the CTA-pair kernel (decoder embedding runs, K/V + Q, heads, twin critics)
+struct GemmProblem {
+  const __nv_bfloat16* A;
+  const __nv_bfloat16* W;
+  void* C;
+  int M, N, K;
+  GemmEpilogue epi;
+};
+int gemm_bf16_grouped(const GemmProblem* probs, int n, cudaStream_t st);
 // gemm_skinny.cu: M <= 32 rows (B = 1 passes): a latency-optimised CUDA-core kernel, same epilogues
 int gemm_bf16_skinny(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, int M, int N, int K, const GemmEpilogue& epi, cudaStream_t st);
 // sgemm.cu

@@ -468,6 +468,49 @@ int gemm(m3pc_engine* e, const void* A, const float* w32, const __nv_bfloat16* w
   return rc;
 }
 
+// Several independent GEMMs as ONE launch where the CTA-pair tensor-core kernel applies (bf16 mode), else one launch each.
+struct GemmJob {
+  const void* A;
+  const float* w32;
+  const __nv_bfloat16* w16;
+  void* C;
+  int M, N, K;
+  GemmEpilogue epi;
+};
+int gemm_group(m3pc_engine* e, const GemmJob* jobs, int n, cudaStream_t st) {
+  if (!e->bf16 || n == 1) {
+    for (int i = 0; i < n; ++i) M3PC_TRY(gemm(e, jobs[i].A, jobs[i].w32, jobs[i].w16, jobs[i].C, jobs[i].M, jobs[i].N, jobs[i].K, jobs[i].epi, st));
+    return M3PC_OK;
+  }
+  constexpr int kMax = 4;
+  for (int i0 = 0; i0 < n; i0 += kMax) {
+    const int m = std::min(kMax, n - i0);
+    GemmProblem pr[kMax];
+    double flops = 0.0;
+    for (int i = 0; i < m; ++i) {
+      const GemmJob& j = jobs[i0 + i];
+      pr[i] = GemmProblem{reinterpret_cast<const __nv_bfloat16*>(j.A), j.w16, j.C, j.M, j.N, j.K, j.epi};
+      flops += 2.0 * j.M * static_cast<double>(j.N) * j.K;
+    }
+    size_t slot = 0;
+    if (e->profile) {
+      slot = e->prof_used++;
+      if (slot >= e->prof_events.size()) {
+        cudaEvent_t a, b;
+        M3PC_CHECK_CUDA(cudaEventCreate(&a));
+        M3PC_CHECK_CUDA(cudaEventCreate(&b));
+        e->prof_events.push_back({a, b});
+        e->prof_flops.push_back(0.0);
+      }
+      e->prof_flops[slot] = flops;
+      M3PC_CHECK_CUDA(cudaEventRecord(e->prof_events[slot].first, st));
+    }
+    M3PC_TRY(gemm_bf16_grouped(pr, m, st));
+    if (e->profile) M3PC_CHECK_CUDA(cudaEventRecord(e->prof_events[slot].second, st));
+  }
+  return M3PC_OK;
+}
+
 // one pre-LN transformer block on `rows` = S * Bc token-major rows; expects Y = LN1(X) on entry
 int block(m3pc_engine* e, const LayerW& w, int Bc, int S, cudaStream_t st) {
   const int D = e->D, F = e->F, rows = S * Bc;
@@ -510,6 +553,8 @@ struct NeedSet {
 int decoder_embed(m3pc_engine* e, const void* enc_out, const int* dec_src, int Bc, bool compact, cudaStream_t st) {
   const int D = e->D, T = e->T;
   const size_t ab = act_bytes(e);
+  GemmJob jobs[MAX_TOK];
+  int n = 0;
   for (int j = 0; j < 4 * T;) {
     if (dec_src[j] < 0) { ++j; continue; }
     const int k = j / T;
@@ -521,10 +566,10 @@ int decoder_embed(m3pc_engine* e, const void* enc_out, const int* dec_src, int B
     ge.flags = EPI_OUT_F32 | EPI_ROWTABLE;
     const char* a = reinterpret_cast<const char*>(enc_out) + static_cast<size_t>(dec_src[j]) * Bc * D * ab;
     float* c = e->X.as<float>() + static_cast<size_t>(compact ? dec_src[j] : j) * Bc * D;
-    M3PC_TRY(gemm(e, a, e->dec_w[k], e->dec_w16[k], c, len * Bc, D, D, ge, st));
+    jobs[n++] = GemmJob{a, e->dec_w[k], e->dec_w16[k], c, len * Bc, D, D, ge};
     j += len;
   }
-  return M3PC_OK;
+  return gemm_group(e, jobs, n, st);  // the runs of all modalities in one launch
 }
 
 // K5: per-modality output heads on `y2` (head-LayerNorm'ed) / `y1` (final-norm only, for the actor), whose row blocks are
@@ -533,16 +578,27 @@ int heads(m3pc_engine* e, const FwdIO& io, const NeedSet& need, const void* y1, 
   const int D = e->D, T = e->T;
   const size_t ab = act_bytes(e);
   float* outs[4] = {io.out_states, nullptr, io.out_rewards, io.out_returns};
+  // hidden layers of all consumed modalities in one grouped launch, each into its own row range of HID
+  GemmJob jobs[4];
+  char* hid[4] = {nullptr, nullptr, nullptr, nullptr};
+  int nj = 0;
+  size_t hid_rows = 0;
   for (int k = 0; k < 4; ++k) {
     if (k == M3PC_ACTIONS || outs[k] == nullptr || need.nt[k] == 0) continue;
-    const int d = e->dims[k];
     GemmEpilogue ge;
     ge.bias = e->head_b1[k];
     ge.flags = EPI_GELU;
     const char* a = reinterpret_cast<const char*>(y2) + static_cast<size_t>(need.q0[k]) * Bc * D * ab;
-    M3PC_TRY(gemm(e, a, e->head_w1[k], e->head_w1_16[k], e->HID.p, need.nt[k] * Bc, D, D, ge, st));
+    hid[k] = reinterpret_cast<char*>(e->HID.p) + hid_rows * D * ab;
+    jobs[nj++] = GemmJob{a, e->head_w1[k], e->head_w1_16[k], hid[k], need.nt[k] * Bc, D, D, ge};
+    hid_rows += static_cast<size_t>(need.nt[k]) * Bc + 128;  // slack rows: tile tails of one problem never touch the next one's rows
+  }
+  if (nj > 0) M3PC_TRY(gemm_group(e, jobs, nj, st));
+  for (int k = 0; k < 4; ++k) {
+    if (hid[k] == nullptr) continue;
+    const int d = e->dims[k];
     RowDotParams rp{};
-    rp.y = e->HID.p;
+    rp.y = hid[k];
     rp.B = Bc; rp.tok0 = 0; rp.n_t = need.nt[k]; rp.t_out0 = need.t0[k]; rp.T_out = T; rp.d_out = d;
     rp.w = e->head_w3[k];
     rp.b = e->head_b3[k];
@@ -640,9 +696,10 @@ int decode_restricted(m3pc_engine* e, const FwdIO& io, const void* enc_out, cons
   // (c) K, V of the kept tokens: rows D..3D of in_proj -> QKV as (S*Bc, 2D)
   GemmEpilogue ge;
   ge.bias = w.in_b + D;
-  M3PC_TRY(gemm(e, e->Y.p, w.in_w + static_cast<size_t>(D) * D, e->bf16 ? w.in_w16 + static_cast<size_t>(D) * D : nullptr, e->QKV.p, S * Bc, 2 * D, D,
-                ge, st));
-  // (d) Q of needed tokens that are kept (per-batch) tokens -> QSEL row block qi
+  GemmJob kvq[MAX_TOK + 1];
+  int nkvq = 0;
+  kvq[nkvq++] = GemmJob{e->Y.p, w.in_w + static_cast<size_t>(D) * D, e->bf16 ? w.in_w16 + static_cast<size_t>(D) * D : nullptr, e->QKV.p, S * Bc, 2 * D, D, ge};
+  // (d) Q of needed tokens that are kept (per-batch) tokens -> QSEL row block qi (same launch as the K/V projection)
   for (int qi = 0; qi < need.n; ++qi) {
     const int src = dec_src[need.tok[qi]];
     if (src < 0) continue;
@@ -650,8 +707,9 @@ int decode_restricted(m3pc_engine* e, const FwdIO& io, const void* enc_out, cons
     gq.bias = w.in_b;
     const char* a = reinterpret_cast<const char*>(e->Y.p) + static_cast<size_t>(src) * Bc * D * ab;
     char* c = reinterpret_cast<char*>(e->QSEL.p) + static_cast<size_t>(qi) * Bc * D * ab;
-    M3PC_TRY(gemm(e, a, w.in_w, w.in_w16, c, Bc, D, D, gq, st));
+    kvq[nkvq++] = GemmJob{a, w.in_w, w.in_w16, c, Bc, D, D, gq};
   }
+  M3PC_TRY(gemm_group(e, kvq, nkvq, st));
   // (e) attention: needed queries x all 4T keys
   AttnParams ap{};
   ap.n_q = need.n;
@@ -912,6 +970,23 @@ int critic(m3pc_engine* e, int N, int h, cudaStream_t st) {
   ci.out_bf16 = e->critic_tc;
   M3PC_TRY(launch_critic_input(ci, st));
   float* outs[2] = {e->qb1.as<float>(), e->qb2.as<float>()};
+  if (e->critic_tc) {  // both nets per layer in one grouped launch (qa holds two bf16 activations side by side)
+    char* qa2 = reinterpret_cast<char*>(e->qa.p) + (static_cast<size_t>(rows) + 128) * Hq * 2;
+    void* qa[2] = {e->qa.p, qa2};
+    GemmJob l1[2], l2[2];
+    for (int q = 0; q < 2; ++q) {
+      GemmEpilogue g1, g2;
+      g1.bias = e->q_b[q][0];
+      g1.flags = EPI_RELU;
+      g2.bias = e->q_b[q][1];
+      g2.flags = EPI_RELU | EPI_OUT_F32;
+      l1[q] = GemmJob{e->sa.p, nullptr, e->q_w16[q][0], qa[q], rows, Hq, e->q_kp, g1};
+      l2[q] = GemmJob{qa[q], nullptr, e->q_w16[q][1], outs[q], rows, Hq, Hq, g2};
+    }
+    M3PC_TRY(gemm_group(e, l1, 2, st));
+    M3PC_TRY(gemm_group(e, l2, 2, st));
+    return launch_critic_out(outs[0], outs[1], e->q_w[0][2], e->q_b[0][2], e->q_w[1][2], e->q_b[1][2], e->qvals.as<float>(), rows, Hq, st);
+  }
   for (int q = 0; q < 2; ++q) {
     GemmEpilogue ge;
     ge.bias = e->q_b[q][0];
@@ -1145,7 +1220,7 @@ int create(m3pc_handle_t* out, const m3pc_config_t* cfg) {
   e->obs = cfg->obs_dim; e->act = cfg->act_dim; e->Le = cfg->n_enc_layer; e->Ld = cfg->n_dec_layer; e->QH = cfg->critic_hidden;
   e->dims[0] = e->obs; e->dims[1] = e->act; e->dims[2] = 1; e->dims[3] = 1;
   e->bf16 = cfg->precision == M3PC_PREC_BF16;
-  e->chunk = cfg->chunk > 0 ? cfg->chunk : 1024;
+  e->chunk = cfg->chunk > 0 ? cfg->chunk : 4096;  // measured (profiles/r1b_*): 16384 candidates take 7.0 ms in chunks of 1024, 5.9 ms in chunks of 4096
   e->chunk = std::min(e->chunk, cfg->max_batch);
   if (e->bf16) M3PC_TRY(gemm_init_driver_api());
   const size_t rows = static_cast<size_t>(4) * e->T * e->chunk + 128;  // +128: slack rows for tile tails
@@ -1291,6 +1366,23 @@ int m3pc_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int
   ep.flags = flags;
   return m3pc::gemm_bf16_tcgen05(reinterpret_cast<const __nv_bfloat16*>(A), reinterpret_cast<const __nv_bfloat16*>(W), C, M, N, K, ep,
                                  reinterpret_cast<cudaStream_t>(stream));
+}
+
+int m3pc_gemm_bf16_grouped(int32_t n, const void* const* A, const void* const* W, const float* const* bias, void* const* C, const int32_t* M,
+                           const int32_t* N, const int32_t* K, const int32_t* flags, void* stream) {
+  M3PC_REQUIRE(n >= 1 && n <= 16 && A && W && C && M && N && K && flags, "bad argument");
+  m3pc::GemmProblem pr[16];
+  for (int i = 0; i < n; ++i) {
+    M3PC_REQUIRE(A[i] && W[i] && C[i], "null operand");
+    M3PC_REQUIRE((flags[i] & ~7) == 0, "unknown flag");
+    m3pc::GemmEpilogue ep;
+    ep.bias = bias ? bias[i] : nullptr;
+    ep.flags = flags[i];
+    pr[i] = m3pc::GemmProblem{reinterpret_cast<const __nv_bfloat16*>(A[i]), reinterpret_cast<const __nv_bfloat16*>(W[i]), C[i], M[i], N[i], K[i], ep};
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int i0 = 0; i0 < n; i0 += 4) M3PC_TRY(m3pc::gemm_bf16_grouped(pr + i0, std::min(4, n - i0), st));
+  return M3PC_OK;
 }
 
 int m3pc_gemm_fp32(const float* A, const float* W, const float* bias, float* C, int32_t M, int32_t N, int32_t K, int32_t flags, void* stream) {

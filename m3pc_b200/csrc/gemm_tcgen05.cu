@@ -323,11 +323,44 @@ struct Smem2 {
   static constexpr int kTotal = kBarOffset + 256 + 1024;
 };
 
+// Grouped launches: up to MAX_GROUP independent problems (own operands, output, epilogue, shapes) share one launch; the pair's
+// unit range simply runs across problem boundaries, so several small GEMMs of the decoder / heads / critic cost one kernel
+// boundary instead of one each.  Split-K (ksplit = 2, residual epilogue only): a unit is one K half of an output tile and
+// both halves are reduce-added into the fp32 residual stream by the TMA (bias / row table ride on half 0) -- used where
+// whole tiles would leave most pairs idle in the last round (N = D GEMMs with K = 4 D at ~1024 batch rows).
+constexpr int MAX_GROUP = 4;
+struct alignas(64) GroupProblem {
+  CUtensorMap ta, tw, tc;
+  const float* bias;
+  const float* table;
+  int rows_per_group, flags;
+  int M, n_tiles;  // rows; N / 256
+  int num_kb;      // k-blocks per unit (K / 64 / ksplit)
+  int ksplit;      // 1 or 2
+  int unit0;       // first unit of this problem in the launch-wide unit order
+};
+struct GroupParams {
+  GroupProblem p[MAX_GROUP];
+  int n, total_units;
+};
+struct UnitCoord { int g, mp, nt, ks; };
+__device__ __forceinline__ UnitCoord decode_unit(const GroupParams& gp, int u) {
+  UnitCoord c;
+  c.g = 0;
+#pragma unroll
+  for (int i = 1; i < MAX_GROUP; ++i)
+    if (i < gp.n && u >= gp.p[i].unit0) c.g = i;
+  const GroupProblem& P = gp.p[c.g];
+  int lu = u - P.unit0;
+  c.ks = 0;
+  if (P.ksplit == 2) { c.ks = lu & 1; lu >>= 1; }
+  c.mp = lu / P.n_tiles;
+  c.nt = lu - c.mp * P.n_tiles;
+  return c;
+}
+
 template <int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS_2SM, 1) gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                                                                        const __grid_constant__ CUtensorMap tmap_w,
-                                                                        const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K,
-                                                                        EpiParams ep) {
+__global__ void __launch_bounds__(GEMM_THREADS_2SM, 1) gemm_bf16_2sm_kernel(const __grid_constant__ GroupParams gp) {
   constexpr int BN = 256;
   using L = Smem2<STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -342,18 +375,18 @@ __global__ void __launch_bounds__(GEMM_THREADS_2SM, 1) gemm_bf16_2sm_kernel(cons
   const int lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
   const bool leader = crank == 0;
-  const int num_kb = K / BK;
-  const int n_tiles = N / BN;
-  const int total_units = n_tiles * ((M + 2 * BM - 1) / (2 * BM));
+  const int total_units = gp.total_units;
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   // units are ordered m-major and split contiguously: a pair mostly stays on one row block, whose A slab stays hot in L2
   const int u_lo = static_cast<int>(static_cast<long long>(pair) * total_units / n_pairs);
   const int u_hi = static_cast<int>(static_cast<long long>(pair + 1) * total_units / n_pairs);
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmap_a);
-    prefetch_tmap(&tmap_w);
-    prefetch_tmap(&tmap_c);
+    for (int g = 0; g < gp.n; ++g) {
+      prefetch_tmap(&gp.p[g].ta);
+      prefetch_tmap(&gp.p[g].tw);
+      prefetch_tmap(&gp.p[g].tc);
+    }
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -383,15 +416,17 @@ __global__ void __launch_bounds__(GEMM_THREADS_2SM, 1) gemm_bf16_2sm_kernel(cons
       int s = 0;
       uint32_t ph = 0;
       for (int u = u_lo; u < u_hi; ++u) {
-        const int mp = u / n_tiles, nt = u - mp * n_tiles;
-        const int m0 = (mp * 2 + static_cast<int>(crank)) * BM, n0 = nt * BN + static_cast<int>(crank) * 128;
+        const UnitCoord uc = decode_unit(gp, u);
+        const GroupProblem& P = gp.p[uc.g];
+        const int m0 = (uc.mp * 2 + static_cast<int>(crank)) * BM, n0 = uc.nt * BN + static_cast<int>(crank) * 128;
+        const int num_kb = P.num_kb, k0 = uc.ks * num_kb;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           if (leader) mbar_arrive_expect_tx(&full_bar[s], 2u * L::kStageBytes);
           uint8_t* dst = smem + s * L::kStageBytes;
           const uint32_t bar = full_leader + 8u * static_cast<uint32_t>(s);
-          tma_load_2d_2sm(dst, &tmap_a, bar, kb * BK, m0);
-          tma_load_2d_2sm(dst + L::kABlk, &tmap_w, bar, kb * BK, n0);
+          tma_load_2d_2sm(dst, &P.ta, bar, (k0 + kb) * BK, m0);
+          tma_load_2d_2sm(dst + L::kABlk, &P.tw, bar, (k0 + kb) * BK, n0);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -408,6 +443,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_2SM, 1) gemm_bf16_2sm_kernel(cons
         mbar_wait(&acc_empty[a], aph ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(a * BN);
+        const int num_kb = gp.p[decode_unit(gp, u).g].num_kb;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
@@ -430,17 +466,22 @@ __global__ void __launch_bounds__(GEMM_THREADS_2SM, 1) gemm_bf16_2sm_kernel(cons
     uint8_t* sbuf = smem + L::kStoreOffset + ew * 2 * L::kStoreBufBytes;
     float* sbias = reinterpret_cast<float*>(smem + L::kBiasOffset) + ew * 64;
     const uint32_t acc_empty_leader = mapa_u32(smem_u32(&acc_empty[0]), 0);
-    const bool do_gelu = ep.flags & EPI_GELU, do_relu = ep.flags & EPI_RELU, do_res = ep.flags & EPI_RESIDUAL;
-    const bool out_f32 = do_res || (ep.flags & EPI_OUT_F32);
-    const bool skip = ep.flags & EPI_DEBUG_SKIP;
-    const int cw = out_f32 ? 16 : 32;  // columns per staged chunk (64 bytes of output)
     const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);  // SWIZZLE_64B: 16-byte chunk j of row r lives at j ^ ((r >> 1) & 3)
     int it = 0;
     uint32_t nstore = 0;  // chunks staged so far (selects the staging buffer)
     for (int u = u_lo; u < u_hi; ++u, ++it) {
-      const int mp = u / n_tiles, nt = u - mp * n_tiles;
-      const int row0 = (mp * 2 + static_cast<int>(crank)) * BM + quarter * 32;
-      const int colw = nt * BN + cgrp * 64;  // first column of this warp's share
+      const UnitCoord uc = decode_unit(gp, u);
+      const GroupProblem& P = gp.p[uc.g];
+      const CUtensorMap* tmap_c = &P.tc;
+      const int M = P.M, N = P.n_tiles * BN;
+      const bool first_k = uc.ks == 0;  // split-K: bias and row table are added by the first K half only
+      EpiParams ep{first_k ? P.bias : nullptr, first_k ? P.table : nullptr, P.rows_per_group, P.flags};
+      const bool do_gelu = ep.flags & EPI_GELU, do_relu = ep.flags & EPI_RELU, do_res = ep.flags & EPI_RESIDUAL;
+      const bool out_f32 = do_res || (ep.flags & EPI_OUT_F32);
+      const bool skip = ep.flags & EPI_DEBUG_SKIP;
+      const int cw = out_f32 ? 16 : 32;  // columns per staged chunk (64 bytes of output)
+      const int row0 = (uc.mp * 2 + static_cast<int>(crank)) * BM + quarter * 32;
+      const int colw = uc.nt * BN + cgrp * 64;  // first column of this warp's share
       // bias of my 64 columns -> shared memory (the previous tile's reads are done: same warp, program order)
       {
         float2 b2 = make_float2(0.f, 0.f);
@@ -540,7 +581,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_2SM, 1) gemm_bf16_2sm_kernel(cons
           fence_proxy_async();  // my generic-proxy writes -> visible to the TMA (async proxy)
           __syncwarp();
           if (lane == 0) {
-            if (do_res) tma_reduce_add_2d(&tmap_c, buf, col0, row0); else tma_store_2d(&tmap_c, buf, col0, row0);
+            if (do_res) tma_reduce_add_2d(tmap_c, buf, col0, row0); else tma_store_2d(tmap_c, buf, col0, row0);
             bulk_commit();
           }
           ++nstore;
@@ -632,23 +673,52 @@ int make_tmap_out(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t cols, boo
 }
 namespace {
 
+int g_use_splitk = 0;  // M3PC_GEMM_SPLITK=1 enables split-K (measured +0.4% plans/s at 1024 candidates; off by default: the reduce-add order of the two halves is not reproducible run to run)
+
+// One launch of the CTA-pair kernel over `n` problems (n <= MAX_GROUP; every N a multiple of 256).
 template <int STAGES>
-int launch_2sm(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, int M, int N, int K, const GemmEpilogue& epi, cudaStream_t st) {
+int launch_2sm(const GemmProblem* probs, int n, cudaStream_t st) {
   using L = Smem2<STAGES>;
   static_assert(L::kTotal <= 227 * 1024, "shared memory budget exceeded");
+  static_assert(sizeof(GroupParams) <= 4000, "kernel parameter space");
   static bool configured = false;
   if (!configured) {
     M3PC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_2sm_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
-  const bool out_f32 = (epi.flags & (EPI_RESIDUAL | EPI_OUT_F32)) != 0;
-  CUtensorMap ta, tw, tc;
-  M3PC_TRY(make_tmap(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), BM));
-  M3PC_TRY(make_tmap(&tw, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), 128));
-  M3PC_TRY(make_tmap_out(&tc, C, static_cast<uint64_t>(M), static_cast<uint64_t>(N), out_f32));
-  EpiParams ep{epi.bias, epi.table, epi.rows_per_group > 0 ? epi.rows_per_group : 1, epi.flags | (g_debug_skip_epi ? EPI_DEBUG_SKIP : 0)};
-  const int units = (N / 256) * ceil_div(M, 2 * BM);
-  const int pairs = std::min(units, g_num_sms / 2);
+  const int n_pairs_max = g_num_sms / 2;
+  GroupParams gp{};
+  gp.n = n;
+  int units = 0;
+  for (int g = 0; g < n; ++g) {
+    const GemmProblem& q = probs[g];
+    GroupProblem& P = gp.p[g];
+    const bool res = (q.epi.flags & EPI_RESIDUAL) != 0;
+    const bool out_f32 = res || (q.epi.flags & EPI_OUT_F32) != 0;
+    M3PC_TRY(make_tmap(&P.ta, q.A, static_cast<uint64_t>(q.M), static_cast<uint64_t>(q.K), BM));
+    M3PC_TRY(make_tmap(&P.tw, q.W, static_cast<uint64_t>(q.N), static_cast<uint64_t>(q.K), 128));
+    M3PC_TRY(make_tmap_out(&P.tc, q.C, static_cast<uint64_t>(q.M), static_cast<uint64_t>(q.N), out_f32));
+    P.bias = q.epi.bias;
+    P.table = q.epi.table;
+    P.rows_per_group = q.epi.rows_per_group > 0 ? q.epi.rows_per_group : 1;
+    P.flags = q.epi.flags | (g_debug_skip_epi ? EPI_DEBUG_SKIP : 0);
+    P.M = q.M;
+    P.n_tiles = q.N / 256;
+    const int tiles = P.n_tiles * ceil_div(q.M, 2 * BM);
+    // split K in two where whole tiles quantise badly: single-problem residual GEMMs with a long K whose last round would
+    // leave most pairs idle (e.g. 104 tiles on 74 pairs: 2 rounds of whole tiles vs 3 rounds of half tiles)
+    P.ksplit = 1;
+    if (g_use_splitk && n == 1 && res && q.K >= 1024 && (q.K / BK) % 2 == 0) {
+      const double r1 = std::ceil(static_cast<double>(tiles) / n_pairs_max);
+      const double r2 = 0.5 * std::ceil(2.0 * tiles / n_pairs_max);
+      if (r2 + 0.25 <= r1) P.ksplit = 2;
+    }
+    P.num_kb = q.K / BK / P.ksplit;
+    P.unit0 = units;
+    units += tiles * P.ksplit;
+  }
+  gp.total_units = units;
+  const int pairs = std::min(units, n_pairs_max);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(GEMM_THREADS_2SM);
@@ -663,7 +733,7 @@ int launch_2sm(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, int M, i
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = g_use_pdl ? 2 : 1;
-  M3PC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_2sm_kernel<STAGES>, ta, tw, tc, M, N, K, ep));
+  M3PC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_2sm_kernel<STAGES>, gp));
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
 }
@@ -699,6 +769,7 @@ int gemm_init_driver_api() {
   M3PC_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
   if (const char* f = getenv("M3PC_GEMM_2SM")) g_use_2sm = atoi(f);
+  if (const char* f = getenv("M3PC_GEMM_SPLITK")) g_use_splitk = atoi(f);
   if (const char* f = getenv("M3PC_GEMM_DEBUG_SKIP_EPI")) g_debug_skip_epi = atoi(f);
   if (const char* f = getenv("M3PC_GEMM_CONFIG")) {
     if (sscanf(f, "%dx%d", &g_force_bn, &g_force_cl) != 2 || (g_force_bn != 128 && g_force_bn != 256) || (g_force_cl != 1 && g_force_cl != 2))
@@ -719,7 +790,8 @@ int gemm_bf16_tcgen05(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, i
   if (M <= 32 && static_cast<size_t>(M) * K * 2 <= 160 * 1024) return gemm_bf16_skinny(A, W, C, M, N, K, epi, st);
   // CTA-pair kernel wherever a pair has two row tiles to work on and N splits into 256-wide tiles
   if (g_use_2sm && !g_force_bn && N % 256 == 0 && M > BM) {
-    return launch_2sm<4>(A, W, C, M, N, K, epi, st);
+    const GemmProblem q{A, W, C, M, N, K, epi};
+    return launch_2sm<4>(&q, 1, st);
   }
   // pick tile width and cluster size by the modelled time (ties: wider tile, larger cluster = less L2 traffic)
   struct Cand { int bn, cl; } cands[] = {{256, 2}, {256, 1}, {128, 2}, {128, 1}};
@@ -737,6 +809,24 @@ int gemm_bf16_tcgen05(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, i
     case 2: return launch<128, 4, 2>(A, W, C, M, N, K, epi, st);
     default: return launch<128, 4, 1>(A, W, C, M, N, K, epi, st);
   }
+}
+
+// Several independent GEMMs in one launch (see GroupParams).  Falls back to one launch per problem where the CTA-pair
+// kernel does not apply (a problem with N % 256 != 0, only tiny M, pinned tuning configurations).
+int gemm_bf16_grouped(const GemmProblem* probs, int n, cudaStream_t st) {
+  M3PC_REQUIRE(n >= 1, "gemm_bf16_grouped: no problems");
+  M3PC_TRY(gemm_init_driver_api());
+  bool ok = g_use_2sm && !g_force_bn && n <= MAX_GROUP;
+  int max_m = 0;
+  for (int g = 0; g < n && ok; ++g) {
+    const GemmProblem& q = probs[g];
+    ok = q.M > 0 && q.N > 0 && q.K > 0 && q.N % 256 == 0 && q.K % BK == 0 && (reinterpret_cast<uintptr_t>(q.A) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(q.W) & 15) == 0 && (reinterpret_cast<uintptr_t>(q.C) & 15) == 0;
+    max_m = std::max(max_m, q.M);
+  }
+  if (ok && max_m > BM && n > 1) return launch_2sm<4>(probs, n, st);
+  for (int g = 0; g < n; ++g) M3PC_TRY(gemm_bf16_tcgen05(probs[g].A, probs[g].W, probs[g].C, probs[g].M, probs[g].N, probs[g].K, probs[g].epi, st));
+  return M3PC_OK;
 }
 
 }  // namespace m3pc

@@ -76,6 +76,44 @@ def test_gemm_bf16_tcgen05(nat, M, N, K, flags):
     assert rel(Cm, ref) < (2e-5 if flags & 2 else 4e-3)
 
 
+@pytest.mark.parametrize("probs", [
+    # decoder-embedding runs (two modalities), K/V + Q, heads (two modalities), twin critics, and a 5-problem list (two launches)
+    [(5120, 512, 512, 0), (8192, 512, 512, 0)],
+    [(13312, 1024, 512, 0), (1024, 512, 512, 0)],
+    [(4096, 512, 512, 1), (3072, 512, 512, 1)],
+    [(4096, 256, 64, 4), (4096, 256, 64, 4)],
+    [(4099, 256, 256, 4), (37, 512, 512, 0), (300, 256, 64, 4), (257, 512, 1024, 2)],
+    [(640, 1024, 512, 0), (129, 256, 256, 0), (1000, 2048, 512, 1), (333, 512, 2048, 2), (2000, 256, 128, 4)],
+])
+def test_gemm_bf16_grouped(nat, probs):
+    """Several independent GEMMs in one launch of the CTA-pair kernel: every problem against its own fp64 product."""
+    import ctypes as C
+    torch.manual_seed(2)
+    n = len(probs)
+    As, Ws, bs, Cs, refs = [], [], [], [], []
+    for (M, N, K, flags) in probs:
+        A = torch.randn(M, K, device="cuda").bfloat16()
+        W = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+        b = torch.randn(N, device="cuda")
+        ref = A.double() @ W.double().T + b.double()
+        if flags & 1: ref = torch.nn.functional.gelu(ref)
+        if flags & 4: ref = torch.relu(ref)
+        if flags & 2:
+            Cm = torch.randn(M, N, device="cuda")
+            ref = ref + Cm.double()
+        else:
+            Cm = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+        As.append(A); Ws.append(W); bs.append(b); Cs.append(Cm); refs.append(ref)
+    vp = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+    i32 = lambda xs: (C.c_int32 * n)(*xs)
+    nat.check(nat.lib().m3pc_gemm_bf16_grouped(n, vp(As), vp(Ws), vp(bs), vp(Cs), i32([p[0] for p in probs]), i32([p[1] for p in probs]),
+                                               i32([p[2] for p in probs]), i32([p[3] for p in probs]), None))
+    torch.cuda.synchronize()
+    for (M, N, K, flags), Cm, ref in zip(probs, Cs, refs):
+        assert torch.isfinite(Cm.float()).all(), (M, N, K, flags)
+        assert rel(Cm, ref) < (2e-5 if flags & 2 else 4e-3), (M, N, K, flags)
+
+
 def test_gemm_rejects_bad_shapes(nat):
     A = torch.zeros(128, 100, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(ValueError):
