@@ -209,7 +209,7 @@ def run_ours(args, w, shape, rank, local_rank, world):
 
     def plan_resident(i, want_partials=False):
         # the window is already in HBM; it is copied (800 B, device to device) into the buffer the engine's CUDA graph reads
-        cur.copy_(windows[i], non_blocking=True)
+        cur.copy_(windows[i % len(windows)], non_blocking=True)
         ws, wa, wr, wt = cur_views
         ev, sm, dbg = eng.plan(guidance=w["guidance"], horizon=h, n_cand=n_local, win_states=ws, win_actions=wa, win_rewards=wr,
                                win_returns_tok=wt, discount=0.99, temperature=w["temperature"], lmbda=0.6, seed=7 + i, cand_offset=lo,
