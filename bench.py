@@ -193,105 +193,127 @@ def run_ours(args, w, shape, rank, local_rank, world):
     cfg = SimpleNamespace(traj_length=T, device=str(dev), action_samples=n_local, discount=0.99, temperature=w["temperature"], horizon=h,
                           plan_guidance=w["guidance"], lmbda=0.6)
     mcfg = omtmConfig(n_embd=shape.n_embd, n_head=shape.n_head, n_enc_layer=shape.n_enc_layer, n_dec_layer=shape.n_dec_layer, dropout=0.1,
-                      norm="none", precision=args.precision, max_batch=n_local, chunk=args.chunk)
+                      norm="none", precision=args.precision, max_batch=n_local * (1 if args.mode == "cand" and world > 1 else max(1, args.envs)),
+                      chunk=args.chunk)
     om, os_ = syn.make_obs_norm(shape)
-    L = Learner(cfg, None, shape.data_shapes, mcfg, None, om, os_, manager_from_stats(stats), {k: False for k in shape.data_shapes})
+    E_head = 1 if cand_mode else max(1, args.envs)
+    L = Learner(cfg, None, shape.data_shapes, mcfg, None, om, os_, manager_from_stats(stats), {k: False for k in shape.data_shapes},
+                max_envs=E_head)
     L.mtm.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
     if crit:
         L.iql.qf.load_state_dict({k: torch.from_numpy(v) for k, v in syn.make_critic_state_dict(shape).items()})
     L.seed, L.cand_offset = 1234, lo
     eng = L._engine()
     K, W = args.steps, args.warmup
-    # env mode: every rank plans for its own environment(s); cand mode: all ranks share the environment
-    hists = [syn.make_history(shape, seed=1000 + (0 if cand_mode else rank) * 10007 + i, path_length=50 + i) for i in range(K + W)]
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
+    obs = shape.obs_dim
 
-    def plan_resident(i, want_partials=False):
-        # the window is already in HBM; it is copied (800 B, device to device) into the buffer the engine's CUDA graph reads
-        cur.copy_(windows[i % len(windows)], non_blocking=True)
-        ws, wa, wr, wt = cur_views
-        ev, sm, dbg = eng.plan(guidance=w["guidance"], horizon=h, n_cand=n_local, win_states=ws, win_actions=wa, win_rewards=wr,
-                               win_returns_tok=wt, discount=0.99, temperature=w["temperature"], lmbda=0.6, seed=7 + i, cand_offset=lo,
-                               want_partials=want_partials)
-        if cand_mode and want_partials:
-            g = mdist.gather_partials(dbg["partials"])
-            ev, sm, _ = eng.merge_partials(g, w["temperature"])
-        return ev
+    def measure(E):
+        """K timed steps of E lock-step environments each (E = 1: the reference's one-window call), device-resident and e2e."""
+        # env mode: every rank plans for its own environment(s); cand mode: all ranks share the environment
+        base = 1000 + (0 if cand_mode else rank) * 10007
+        pool = [syn.make_history(shape, seed=base + j) for j in range(61)]  # distinct episodes; every (step, env) reads a different window of one
+        hists = [[dict(pool[(i * E + e) % 61], path_length=50 + (i * E + e) % 900) for e in range(E)] for i in range(K + W)]
+        # windows resident in HBM (built by the same host code the public API uses)
+        windows = []
+        for hs in hists:
+            ring, slot = L._window_buffers(obs, A, n_env=E)
+            for e, hist in enumerate(hs):
+                v = (slot.h_states, slot.h_actions, slot.h_rewards, slot.h_returns) if E == 1 else \
+                    (slot.h_states[e], slot.h_actions[e], slot.h_rewards[e], slot.h_returns[e])
+                L._fill_window(*v, hist, h, 1.0, 3.0)
+            windows.append(slot.host.to(dev))
+        cur = torch.empty_like(windows[0])
+        o = [0, E * T * obs, E * T * (obs + A), E * T * (obs + A + 1), cur.numel()]
+        lead = (E,) if E > 1 else ()
+        cur_views = (cur[o[0]:o[1]].view(*lead, T, obs), cur[o[1]:o[2]].view(*lead, T, A), cur[o[2]:o[3]].view(*lead, T), cur[o[3]:o[4]].view(*lead, T))
 
-    # windows resident in HBM (built by the same host code the public API uses)
-    windows = []
-    for hist in hists:
-        ring, slot = L._window_buffers(shape.obs_dim, shape.act_dim)
-        L._fill_window(slot.h_states, slot.h_actions, slot.h_rewards, slot.h_returns, hist, h, 1.0, 3.0)
-        windows.append(slot.host.to(dev))
-    cur = torch.empty_like(windows[0])
-    o = [0, T * shape.obs_dim, T * (shape.obs_dim + A), T * (shape.obs_dim + A + 1), cur.numel()]
-    cur_views = (cur[o[0]:o[1]].view(T, -1), cur[o[1]:o[2]].view(T, -1), cur[o[2]:o[3]], cur[o[3]:o[4]])
+        def plan_resident(i, want_partials=False):
+            # the windows are already in HBM; they are copied (E x 800 B, device to device) into the buffer the engine's CUDA graph reads
+            cur.copy_(windows[i % len(windows)], non_blocking=True)
+            ws, wa, wr, wt = cur_views
+            ev, sm, dbg = eng.plan(guidance=w["guidance"], horizon=h, n_cand=n_local, win_states=ws, win_actions=wa, win_rewards=wr,
+                                   win_returns_tok=wt, discount=0.99, temperature=w["temperature"], lmbda=0.6, seed=7 + i, cand_offset=lo,
+                                   want_partials=want_partials, n_env=E)
+            if cand_mode and want_partials:
+                g = mdist.gather_partials(dbg["partials"])
+                ev, sm, _ = eng.merge_partials(g, w["temperature"])
+            return ev
 
-    # ---- device-resident timing: K plans, one CUDA-event pair each, L2 flushed between plans ----
-    for i in range(W):
-        plan_resident(i, cand_mode)
+        # ---- device-resident timing: K steps, one CUDA-event pair each, L2 flushed between steps ----
+        for i in range(W):
+            plan_resident(i, cand_mode)
+        torch.cuda.synchronize(); barrier()
+        pairs = []
+        t_wall0 = time.perf_counter()
+        for i in range(K):
+            flush.fill_(float(i))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            plan_resident(W + i, cand_mode)
+            e1.record()
+            pairs.append((e0, e1))
+        torch.cuda.synchronize(); barrier()
+        wall_resident = time.perf_counter() - t_wall0
+        per_step_ms = [a.elapsed_time(b) for a, b in pairs]
+        launches = eng.last_launch_count() + (1 if cand_mode else 0)
+
+        # ---- e2e: public API with host histories (pinned H2D + D2H inside the timed region) ----
+        def api_step(i):
+            if cand_mode:
+                ring, slot = L._window_buffers(obs, A)
+                L._fill_window(slot.h_states, slot.h_actions, slot.h_rewards, slot.h_returns, hists[i][0], h, 1.0, 3.0)
+                L._upload_window(ring, slot)
+                ev, sm, dbg = eng.plan(guidance=w["guidance"], horizon=h, n_cand=n_local, win_states=ring.d_states, win_actions=ring.d_actions,
+                                       win_rewards=ring.d_rewards, win_returns_tok=ring.d_returns, discount=0.99, temperature=w["temperature"],
+                                       lmbda=0.6, seed=7 + i, cand_offset=lo, want_partials=True)
+                ev, sm, _ = eng.merge_partials(mdist.gather_partials(dbg["partials"]), w["temperature"])
+                return ev.cpu()
+            if E == 1:
+                return L.action_sample(hists[i][0], plan=True, eval=True, rtg=3.0).cpu()
+            return L.action_sample_batch(hists[i], plan=True, eval=True, rtg=3.0).cpu()
+
+        for i in range(W):
+            api_step(i)
+        torch.cuda.synchronize(); barrier()
+        t0 = time.perf_counter()
+        lat = []
+        for i in range(K):
+            t1 = time.perf_counter()
+            api_step(W + i)
+            lat.append(time.perf_counter() - t1)
+        torch.cuda.synchronize(); barrier()
+        e2e_s = time.perf_counter() - t0
+        return SimpleNamespace(E=E, dev_s=sum(per_step_ms) / 1e3, per_step_ms=per_step_ms, wall=wall_resident, launches=launches, e2e_s=e2e_s,
+                               lat=lat, plan_resident=plan_resident)
+
     torch.cuda.synchronize(); barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    pairs = []
-    torch.cuda.synchronize(); barrier()
-    t_wall0 = time.perf_counter()
-    for i in range(K):
-        flush.fill_(float(i))
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        plan_resident(W + i, cand_mode)
-        e1.record()
-        pairs.append((e0, e1))
-    torch.cuda.synchronize(); barrier()
-    wall_resident = time.perf_counter() - t_wall0
-    per_plan_ms = [a.elapsed_time(b) for a, b in pairs]
-    launches = eng.last_launch_count() + (1 if cand_mode else 0)
-    dev_s = sum(per_plan_ms) / 1e3
-
-    # ---- e2e: public API with host histories (pinned H2D + D2H inside the timed region) ----
-    for i in range(W):
-        L.action_sample(hists[i], plan=True, eval=True, rtg=3.0).cpu()
-    torch.cuda.synchronize(); barrier()
-    t0 = time.perf_counter()
-    lat = []
-    for i in range(K):
-        t1 = time.perf_counter()
-        if cand_mode:
-            ring, slot = L._window_buffers(shape.obs_dim, shape.act_dim)
-            L._fill_window(slot.h_states, slot.h_actions, slot.h_rewards, slot.h_returns, hists[W + i], h, 1.0, 3.0)
-            L._upload_window(ring, slot)
-            ev, sm, dbg = eng.plan(guidance=w["guidance"], horizon=h, n_cand=n_local, win_states=ring.d_states, win_actions=ring.d_actions,
-                                   win_rewards=ring.d_rewards, win_returns_tok=ring.d_returns, discount=0.99, temperature=w["temperature"],
-                                   lmbda=0.6, seed=7 + i, cand_offset=lo, want_partials=True)
-            ev, sm, _ = eng.merge_partials(mdist.gather_partials(dbg["partials"]), w["temperature"])
-            a = ev.cpu()
-        else:
-            a = L.action_sample(hists[W + i], plan=True, eval=True, rtg=3.0).cpu()
-        lat.append(time.perf_counter() - t1)
-    torch.cuda.synchronize(); barrier()
-    e2e_s = time.perf_counter() - t0
+    single = measure(1)                      # the reference's call shape: one window per plan (latency figure)
+    head = measure(E_head) if E_head > 1 else single
     clocks = sampler.stop() if rank == 0 else None
+    dev_s, e2e_s, wall_resident, launches, per_plan_ms, lat = head.dev_s, head.e2e_s, head.wall, head.launches, head.per_step_ms, head.lat
 
-    # ---- roofline pass: same plan with one event pair per GEMM launch ----
+    # ---- roofline pass: same step with one event pair per GEMM launch ----
     eng.set_profile(True)
     g_ms, g_fl, g_n = 0.0, 0.0, 0
     for i in range(3):
-        plan_resident(W + i)
+        head.plan_resident(W + i)
         torch.cuda.synchronize()
         ms, fl, n = eng.get_profile()
         g_ms, g_fl, g_n = g_ms + ms, g_fl + fl, g_n + n
     eng.set_profile(False)
 
     # ---- max over ranks ----
-    stats_t = torch.tensor([dev_s, e2e_s, wall_resident], device=dev, dtype=torch.float64)
+    stats_t = torch.tensor([dev_s, e2e_s, wall_resident, single.dev_s, single.e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(stats_t, op=dist.ReduceOp.MAX)
-    dev_s, e2e_s, wall_resident = [float(x) for x in stats_t.tolist()]
-    plans_per_step = 1 if (cand_mode or world == 1) else world
+    dev_s, e2e_s, wall_resident, single_dev_s, single_e2e_s = [float(x) for x in stats_t.tolist()]
+    plans_per_step = E_head * (1 if (cand_mode or world == 1) else world)
+    ranks_planning = 1 if cand_mode else world
     value = plans_per_step * K / dev_s
     e2e_value = plans_per_step * K / e2e_s
     if rank != 0:
@@ -315,7 +337,7 @@ def run_ours(args, w, shape, rank, local_rank, world):
         cval, ctimes, threads = time_cpu(w, shape, steps=8, warmup=1, budget_s=25.0)
         cpu = {"value": cval, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{len(ctimes)} full plans of the same workload (oracle port of Learner.action_sample, torch CPU fp32, {threads} threads of {os.cpu_count()} host cpus)"}
-    win_bytes = 4 * T * (shape.obs_dim + A + 2)
+    win_bytes = 4 * T * (shape.obs_dim + A + 2) * E_head
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * dev_s / K,
         "higher_is_better": True, "scaling": "strong" if cand_mode else "weak", "vs_baseline": None,
@@ -323,14 +345,21 @@ def run_ours(args, w, shape, rank, local_rank, world):
         "config": {"workload": args.workload, "candidates": n_total, "horizon": h, "guidance": w["guidance"], "env_shapes": w["env"],
                    "model": f"D={shape.n_embd},heads={shape.n_head},enc={shape.n_enc_layer},dec={shape.n_dec_layer},T={shape.traj_length}",
                    "parallelism": (f"cand-shard x{world} + allgather(72 floats)" if cand_mode else f"env-parallel x{world} (independent plans, no collective)"),
-                   "plans_per_step": plans_per_step, "l2": "256 MiB flush write between timed plans (outside the per-plan event pairs)",
+                   "envs_per_gpu": E_head, "plans_per_step": plans_per_step,
+                   "step": (f"{E_head} lock-step environments x {n_total} candidates planned by ONE m3pc_plan launch sequence per GPU "
+                            f"(Learner.action_sample_batch); the one-window call of the reference is reported under single_env") if E_head > 1 else
+                           "one window per plan (Learner.action_sample)", "l2": "256 MiB flush write between timed plans (outside the per-plan event pairs)",
                    "weights": "random-init (numpy seed 0), reference state_dict layout", "chunk": args.chunk},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": win_bytes, "d2h_bytes_per_step": 4 * A,
-                "p50_latency_ms": 1e3 * statistics.median(lat), "api": "Learner.action_sample(host numpy history) -> .cpu()"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": win_bytes, "d2h_bytes_per_step": 4 * A * E_head,
+                "p50_latency_ms": 1e3 * statistics.median(lat),
+                "api": ("Learner.action_sample_batch(E host numpy histories) -> .cpu()" if E_head > 1 else "Learner.action_sample(host numpy history) -> .cpu()")},
+        "single_env": {"value": ranks_planning * K / single_dev_s, "e2e_value": ranks_planning * K / single_e2e_s, "unit": UNIT,
+                       "p50_ms_device": statistics.median(single.per_step_ms), "p50_latency_ms_e2e": 1e3 * statistics.median(single.lat),
+                       "launches_per_plan": single.launches, "api": "Learner.action_sample(host numpy history) -> .cpu()"},
         "gpu_launches": launches * K,
         "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None,
-                     "traffic": traffic, "kernel": "gemm_bf16_kernel (tcgen05)", "launches_per_plan": g_n // 3, "gemm_ms_per_plan": g_ms / 3,
-                     "gemm_flops_per_plan": g_fl / 3, "peak_source": peak_src,
+                     "traffic": traffic, "kernel": "gemm_bf16_2sm_kernel (tcgen05 cta_group::2)", "launches_per_step": g_n // 3, "gemm_ms_per_step": g_ms / 3,
+                     "gemm_flops_per_step": g_fl / 3, "gemm_flops_per_plan": g_fl / 3 / E_head, "peak_source": peak_src,
                      "whole_plan_dense_frac": fl_plan * value / (world * peak_tf * 1e12)},
         "flops_per_plan_dense": fl_plan, "flops_per_candidate_row": fl_row,
         "p50_ms": statistics.median(per_plan_ms), "wall_s_resident_loop": wall_resident,
@@ -349,6 +378,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="walker2d_critic_1024", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="env", choices=["env", "cand"])
+    ap.add_argument("--envs", type=int, default=1, help="lock-step environments planned per step on each GPU (one m3pc_plan launch sequence)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -119,7 +119,12 @@ typedef struct {
   float discount;       /* cfg.discount */
   float temperature;    /* cfg.temperature */
   float lmbda;          /* cfg.lmbda (rtg_guiding: the reference hard-codes 0.6, learner.py:272,405-407) */
-  int32_t reserved0;
+  int32_t n_env;        /* 0 or 1: one window (the reference's call).  E > 1: E lock-step environments planned in ONE launch
+                           sequence (pass 1 at B = E, pass 2 at B = E*n_cand): every win_* pointer
+                           gains a leading E axis, eps is (E*n_cand,h,A), expq (E*n_cand), out_*_action (E,A),
+                           dbg_expect_return (E*n_cand), dbg_candidates (E*n_cand,h,A), dbg_indices (E,2) with indices local
+                           to the environment; out_partials must be NULL.  Needs E*n_cand <= cfg.max_batch.  Row e of the
+                           result equals the single-window call on window e with the same injected noise. */
   const float* win_states;      /* device (T,obs) RAW window (zero padded), learner.py:348-366 */
   const float* win_actions;     /* device (T,act) RAW */
   const float* win_rewards;     /* device (T) RAW */

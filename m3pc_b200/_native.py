@@ -50,7 +50,7 @@ class Config(C.Structure):
 class PlanArgs(C.Structure):
     _fields_ = [
         ("guidance", C.c_int32), ("horizon", C.c_int32), ("n_cand", C.c_int32), ("cand_offset", C.c_int32),
-        ("discount", C.c_float), ("temperature", C.c_float), ("lmbda", C.c_float), ("reserved0", C.c_int32),
+        ("discount", C.c_float), ("temperature", C.c_float), ("lmbda", C.c_float), ("n_env", C.c_int32),
         ("win_states", C.c_void_p), ("win_actions", C.c_void_p), ("win_rewards", C.c_void_p), ("win_returns_tok", C.c_void_p),
         ("eps", C.c_void_p), ("expq", C.c_void_p), ("seed", C.c_uint64),
         ("out_eval_action", C.c_void_p), ("out_sample_action", C.c_void_p), ("out_partials", C.c_void_p),

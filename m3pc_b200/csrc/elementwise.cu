@@ -53,11 +53,16 @@ __global__ void __launch_bounds__(256) embed_kernel(const __grid_constant__ Embe
   const int s = blockIdx.y;
   const EmbedTok& tk = p.tok[s];
   const int b_end = min(p.B, (static_cast<int>(blockIdx.x) + 1) * 64);
-  const bool shared_tok = tk.bstride == 0;  // history token: identical for every batch row -> embed + normalise once
+  // source row of batch row b: its own (bstride > 0), one shared by every row (bstride == 0: history tokens of a single
+  // window), or one per group of bdiv global rows (the window of the row's environment).  A warp walks b upwards, so the
+  // embedding + LayerNorm are recomputed only when the source row changes.
+  long cur = -1;
   float4 acc[NJ], o[NJ];
   for (int b = blockIdx.x * 64 + warp; b < b_end; b += 8) {
-    if (!shared_tok || b == blockIdx.x * 64 + warp) {
-      const float* src = tk.src + static_cast<size_t>(b) * tk.bstride;
+    const long srow = tk.bdiv > 0 ? (p.b0 + b) / tk.bdiv : (tk.bstride == 0 ? 0 : b);
+    if (srow != cur) {
+      cur = srow;
+      const float* src = tk.src + static_cast<size_t>(srow) * tk.bstride;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) acc[j] = __ldg(reinterpret_cast<const float4*>(tk.cvec + j * 128 + lane * 4));
 #pragma unroll 4

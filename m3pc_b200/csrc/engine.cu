@@ -63,6 +63,8 @@ struct ModSrc {
   const float* base2 = nullptr; // tokens t >= t_split come from base2 + b*bstride2 + (t-t_split)*d
   long bstride2 = 0;
   int t_split = 1 << 30;
+  int bdiv = 0;                 // > 0: `base` rows are shared by groups of bdiv consecutive batch rows (row b reads
+                                // base + (b / bdiv)*bstride + t*d): the E windows of an n_env > 1 plan
 };
 
 struct FwdIO {
@@ -130,7 +132,7 @@ struct m3pc_engine {
 
   // CUDA-graph replay of m3pc_plan (production path: on-device Philox noise, no debug outputs)
   struct PlanKey {
-    int guidance, horizon, n_cand, cand_offset;
+    int guidance, horizon, n_cand, cand_offset, n_env;
     float discount, temperature, lmbda;
     const void *ws, *wa, *wr, *wt, *ev, *sm, *pt;
     bool operator<(const PlanKey& o) const { return std::memcmp(this, &o, sizeof(PlanKey)) < 0; }
@@ -811,7 +813,9 @@ int forward_chunk(m3pc_engine* e, const FwdIO& io, int b0, int Bc, cudaStream_t 
   }
 
   // ---- B = 1: the whole encoder + restricted decoder in one cooperative kernel (fused_b1.cu) ----
-  if (Bc == 1 && e->bf16 && e->use_fused_b1 && e->Ld == 1 && e->Le >= 1 && e->Le <= FB_MAX_LAYERS && need.n >= 1 && need.n < 4 * T &&
+  bool grouped_src = false;
+  for (int k = 0; k < 4; ++k) grouped_src = grouped_src || io.src[k].bdiv > 0;
+  if (Bc == 1 && !grouped_src && e->bf16 && e->use_fused_b1 && e->Ld == 1 && e->Le >= 1 && e->Le <= FB_MAX_LAYERS && need.n >= 1 && need.n < 4 * T &&
       need.n <= FB_MAX_ROWS && S <= FB_MAX_ROWS && D == 512 && fused_b1_smem_bytes(D, S, need.n) <= 200 * 1024) {
     FusedB1Params fp{};
     fp.S = S; fp.n_enc = e->Le; fp.T4 = 4 * T; fp.n_need = need.n;
@@ -876,6 +880,7 @@ int forward_chunk(m3pc_engine* e, const FwdIO& io, int b0, int Bc, cudaStream_t 
   EmbedParams ep{};
   ep.n_tok = S;
   ep.B = Bc;
+  ep.b0 = b0;
   for (int s = 0; s < S; ++s) {
     const int k = enc_mod[s], t = enc_t[s], d = e->dims[k];
     const ModSrc& ms = io.src[k];
@@ -883,6 +888,10 @@ int forward_chunk(m3pc_engine* e, const FwdIO& io, int b0, int Bc, cudaStream_t 
     if (ms.base2 != nullptr && t >= ms.t_split) {
       tk.src = ms.base2 + static_cast<size_t>(b0) * ms.bstride2 + static_cast<size_t>(t - ms.t_split) * d;
       tk.bstride = static_cast<int>(ms.bstride2);
+    } else if (ms.bdiv > 0) {
+      tk.src = ms.base + static_cast<size_t>(t) * d;  // the kernel adds ((b0 + b) / bdiv) * bstride
+      tk.bstride = static_cast<int>(ms.bstride);
+      tk.bdiv = ms.bdiv;
     } else {
       tk.src = ms.base + static_cast<size_t>(b0) * ms.bstride + static_cast<size_t>(t) * d;
       tk.bstride = static_cast<int>(ms.bstride);
@@ -1016,45 +1025,53 @@ void set_window_sources(m3pc_engine* e, FwdIO& io, const float* ws, const float*
 int plan_body(m3pc_engine* e, const m3pc_plan_args_t* a, cudaStream_t st) {
   M3PC_REQUIRE(e->finalized, "plan before m3pc_finalize_params");
   const int T = e->T, h = a->horizon, N = a->n_cand, A = e->act, idx = T - h;
+  const int E = a->n_env > 1 ? a->n_env : 1;  // lock-step environments planned by this call
+  const long R = static_cast<long>(E) * N;    // pass-2 rows: environment-major, candidate-minor
+  M3PC_REQUIRE(a->n_env >= 0, "n_env must be >= 0");
+  M3PC_REQUIRE(E == 1 || (a->out_partials == nullptr && a->cand_offset == 0), "n_env > 1 cannot be combined with candidate sharding");
+  M3PC_REQUIRE(E <= e->cfg.max_batch, "n_env exceeds cfg.max_batch");
   M3PC_REQUIRE(h >= 1 && h <= T, "horizon must be in [1, traj_length]");
   M3PC_REQUIRE(a->guidance >= 0 && a->guidance <= 3, "unknown guidance");
   M3PC_REQUIRE(a->win_states && a->win_actions && a->win_rewards && a->win_returns_tok, "window pointers must be set");
   M3PC_REQUIRE(a->out_eval_action && a->out_sample_action, "output pointers must be set");
   const bool needs_critic = a->guidance == M3PC_GUIDE_CRITIC || a->guidance == M3PC_GUIDE_NOISE_CRITIC;
   M3PC_REQUIRE(!needs_critic || e->has_critic, "critic guidance requested but no critic parameters were loaded");
-  if (a->guidance != M3PC_GUIDE_SAMPLING) M3PC_REQUIRE(N >= 1 && N <= e->cfg.max_batch, "n_cand exceeds cfg.max_batch");
+  if (a->guidance != M3PC_GUIDE_SAMPLING) M3PC_REQUIRE(N >= 1 && R <= e->cfg.max_batch, "n_env * n_cand exceeds cfg.max_batch");
 
   // ---- pass 1: B = 1, rcbc mask (finetune_omtm/masks.py:7-27) -> action distribution ----
   FwdIO io{};
-  set_window_sources(e, io, a->win_states, a->win_actions, a->win_rewards, a->win_returns_tok, 0);
+  set_window_sources(e, io, a->win_states, a->win_actions, a->win_rewards, a->win_returns_tok, E > 1 ? 1 : 0);
   for (int t = 0; t < T; ++t) {
     io.mask[M3PC_STATES * T + t] = t <= idx;
     io.mask[M3PC_ACTIONS * T + t] = t < idx;
     io.mask[M3PC_REWARDS * T + t] = 0;
     io.mask[M3PC_RETURNS * T + t] = 1;
   }
-  io.out_mu = e->p1_mu.as<float>();
-  io.out_std = e->p1_std.as<float>();
+  io.out_mu = E > 1 ? e->e_mu.as<float>() : e->p1_mu.as<float>();  // (E, T, A)
+  io.out_std = E > 1 ? e->e_std.as<float>() : e->p1_std.as<float>();
   io.need_t0[M3PC_ACTIONS] = idx;  // only the planned steps of the action head are consumed
   io.need_nt[M3PC_ACTIONS] = h;
-  M3PC_TRY(forward(e, io, 1, st));
+  M3PC_TRY(forward(e, io, E, st));
   if (a->guidance == M3PC_GUIDE_SAMPLING)
-    return launch_sampling_tail(io.out_mu, io.out_std, a->eps, T, h, A, 1, a->out_eval_action, a->out_sample_action, a->seed,
+    return launch_sampling_tail(io.out_mu, io.out_std, a->eps, T, h, A, E, a->out_eval_action, a->out_sample_action, a->seed,
                                 e->seed_ptr_active, st);
 
   // ---- K6: candidates ----
   CandParams cp{};
   cp.mu = io.out_mu; cp.std = io.out_std; cp.eps = a->eps; cp.cand = e->cand.as<float>();
-  cp.N = N; cp.h = h; cp.A = A; cp.T = T;
+  cp.N = static_cast<int>(R); cp.h = h; cp.A = A; cp.T = T;
+  cp.n_per_env = E > 1 ? N : 0;
   cp.noise_mode = a->guidance == M3PC_GUIDE_NOISE_CRITIC ? 1 : 0;
   cp.seed = a->seed; cp.cand_offset = a->cand_offset; cp.seed_ptr = e->seed_ptr_active;
   M3PC_TRY(launch_candidates(cp, st));
   if (a->dbg_candidates)
-    M3PC_CHECK_CUDA(cudaMemcpyAsync(a->dbg_candidates, cp.cand, sizeof(float) * N * h * A, cudaMemcpyDeviceToDevice, st));
+    M3PC_CHECK_CUDA(cudaMemcpyAsync(a->dbg_candidates, cp.cand, sizeof(float) * R * h * A, cudaMemcpyDeviceToDevice, st));
 
   // ---- pass 2: B = N, fd mask (finetune_omtm/masks.py:30-44); history shared, planned actions per candidate ----
   FwdIO io2{};
-  set_window_sources(e, io2, a->win_states, a->win_actions, a->win_rewards, a->win_returns_tok, 0);
+  set_window_sources(e, io2, a->win_states, a->win_actions, a->win_rewards, a->win_returns_tok, E > 1 ? 1 : 0);
+  if (E > 1)
+    for (int k = 0; k < 4; ++k) io2.src[k].bdiv = N;  // rows [e*N, (e+1)*N) share window e
   io2.src[M3PC_ACTIONS].base2 = cp.cand;
   io2.src[M3PC_ACTIONS].bstride2 = static_cast<long>(h) * A;
   io2.src[M3PC_ACTIONS].t_split = idx;
@@ -1077,10 +1094,10 @@ int plan_body(m3pc_engine* e, const m3pc_plan_args_t* a, cudaStream_t st) {
     io2.need_t0[M3PC_RETURNS] = idx;
     io2.need_nt[M3PC_RETURNS] = h;
   }
-  M3PC_TRY(forward(e, io2, N, st));
+  M3PC_TRY(forward(e, io2, static_cast<int>(R), st));
 
   // ---- K7 + K8 ----
-  if (needs_critic) M3PC_TRY(critic(e, N, h, st));
+  if (needs_critic) M3PC_TRY(critic(e, static_cast<int>(R), h, st));
   ScoreParams sp{};
   sp.rewards_pred = io2.out_rewards;
   sp.returns_pred = needs_critic ? nullptr : io2.out_returns;
@@ -1088,13 +1105,13 @@ int plan_body(m3pc_engine* e, const m3pc_plan_args_t* a, cudaStream_t st) {
   sp.rw_mean = e->h_tok_mean[M3PC_REWARDS]; sp.rw_std = e->h_tok_std[M3PC_REWARDS];
   sp.rt_mean = e->h_tok_mean[M3PC_RETURNS]; sp.rt_std = e->h_tok_std[M3PC_RETURNS];
   sp.discount = a->discount; sp.lmbda = a->lmbda;
-  sp.N = N; sp.h = h; sp.T = T;
+  sp.N = static_cast<int>(R); sp.h = h; sp.T = T;
   sp.J = e->J.as<float>();
   M3PC_TRY(launch_score(sp, st));
-  if (a->dbg_expect_return) M3PC_CHECK_CUDA(cudaMemcpyAsync(a->dbg_expect_return, sp.J, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+  if (a->dbg_expect_return) M3PC_CHECK_CUDA(cudaMemcpyAsync(a->dbg_expect_return, sp.J, sizeof(float) * R, cudaMemcpyDeviceToDevice, st));
   SelectParams sl{};
   sl.J = sp.J; sl.cand = cp.cand; sl.expq = a->expq;
-  sl.N = N; sl.h = h; sl.A = A;
+  sl.n_env = E; sl.N = N; sl.h = h; sl.A = A;
   sl.temperature = a->temperature; sl.seed = a->seed; sl.cand_offset = a->cand_offset; sl.seed_ptr = e->seed_ptr_active;
   sl.eval_action = a->out_eval_action; sl.sample_action = a->out_sample_action;
   sl.partials = a->out_partials; sl.indices = a->dbg_indices;
@@ -1112,7 +1129,7 @@ int plan(m3pc_engine* e, const m3pc_plan_args_t* a, cudaStream_t st) {
   }
   m3pc_engine::PlanKey key;
   std::memset(&key, 0, sizeof(key));
-  key.guidance = a->guidance; key.horizon = a->horizon; key.n_cand = a->n_cand; key.cand_offset = a->cand_offset;
+  key.guidance = a->guidance; key.horizon = a->horizon; key.n_cand = a->n_cand; key.cand_offset = a->cand_offset; key.n_env = a->n_env > 1 ? a->n_env : 1;
   key.discount = a->discount; key.temperature = a->temperature; key.lmbda = a->lmbda;
   key.ws = a->win_states; key.wa = a->win_actions; key.wr = a->win_rewards; key.wt = a->win_returns_tok;
   key.ev = a->out_eval_action; key.sm = a->out_sample_action; key.pt = a->out_partials;

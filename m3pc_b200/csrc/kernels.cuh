@@ -16,11 +16,14 @@ struct EmbedTok {
   const float* nstd;   // (d)
   int bstride;         // floats between consecutive batch rows (0 = shared by all rows)
   int d;               // feature dim
+  int bdiv;            // > 0: rows come in groups of bdiv consecutive GLOBAL batch rows (one group per environment) that share
+                       // one source row; bstride is then the stride between groups (m3pc_plan with n_env > 1)
 };
 struct EmbedParams {
   EmbedTok tok[MAX_TOK];
   int n_tok;
   int B;
+  int b0;   // global batch row of this chunk's row 0 (only read for tokens with bdiv > 0)
   int cpt;  // 0: token-major output rows (row = token * B + b); > 0: candidate-major 128-row tiles holding cpt batch rows each
             // (row = (b / cpt) * 128 + (b % cpt) * n_tok + token) -- the layout of the encoder megakernel
 };
@@ -153,6 +156,7 @@ struct CandParams {
   const float* eps;  // (N, h, A) injected noise or null (Philox)
   float* cand;       // (N, h, A)
   int N, h, A, T;
+  int n_per_env;     // > 0: candidate n belongs to environment n / n_per_env and mu / std are (E, T, A)
   int noise_mode;    // 0: tanh(mu + std*eps) (learner.py:285-287); 1: clamp(tanh(mu) + 0.09*eps) (learner.py:156-167)
   unsigned long long seed;
   int cand_offset;
@@ -188,7 +192,9 @@ struct ScoreParams {
 };
 int launch_score(const ScoreParams& p, cudaStream_t st);
 
+// One thread block per environment e (grid = n_env): J, cand, expq are offset by e*N, the outputs by e*A (indices by 2e).
 struct SelectParams {
+  int n_env;          // >= 1
   const float* J;     // (N)
   const float* cand;  // (N, h, A): a0 = cand[n, 0, :]
   const float* expq;  // (N) or null

@@ -46,10 +46,11 @@ __global__ void candidates_kernel(const __grid_constant__ CandParams p) {
   const unsigned long long seed = p.seed_ptr ? *p.seed_ptr : p.seed;
   const float eps = p.eps ? p.eps[i] : philox_normal(seed, static_cast<unsigned>(p.cand_offset + n), static_cast<unsigned>(e), 0u);
   const int t = p.T - p.h + j;
-  const float mu = p.mu[t * p.A + a];
+  const int ms = ((p.n_per_env > 0 ? n / p.n_per_env : 0) * p.T + t) * p.A + a;  // pass-1 distribution of the candidate's environment
+  const float mu = p.mu[ms];
   float v;
   if (p.noise_mode == 0) {
-    v = tanhf(__fadd_rn(mu, __fmul_rn(p.std[t * p.A + a], eps)));
+    v = tanhf(__fadd_rn(mu, __fmul_rn(p.std[ms], eps)));
   } else {
     v = __fadd_rn(tanhf(mu), __fmul_rn(eps, 0.09f));
     v = fminf(fmaxf(v, -0.99999f), 0.99999f);
@@ -175,11 +176,18 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const __grid_consta
   const int tid = threadIdx.x;
   const int stride_a0 = p.h * p.A;
   const unsigned long long seed = p.seed_ptr ? *p.seed_ptr : p.seed;
+  // one block per environment: this block's slice of every per-candidate array
+  const int env = blockIdx.x, row0 = env * p.N;
+  const float* __restrict__ Jv = p.J + row0;
+  const float* __restrict__ candv = p.cand + static_cast<size_t>(row0) * stride_a0;
+  const float* __restrict__ expq = p.expq ? p.expq + row0 : nullptr;
+  float* eval_action = p.eval_action + env * p.A;
+  float* sample_action = p.sample_action + env * p.A;
   // 1. max_n J_n (+ argmax)
   float m = -INFINITY;
   int mi = 0x7fffffff;
   for (int n = tid; n < p.N; n += SEL_THREADS) {
-    const float j = p.J[n];
+    const float j = Jv[n];
     if (j > m) { m = j; mi = n; }
   }
   block_argmax(m, mi, redv, redi);
@@ -187,9 +195,9 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const __grid_consta
   float z = 0.f, kbest = -INFINITY;
   int ki = 0x7fffffff;
   for (int n = tid; n < p.N; n += SEL_THREADS) {
-    const float w = expf(__fmul_rn(__fsub_rn(p.J[n], m), p.temperature));
+    const float w = expf(__fmul_rn(__fsub_rn(Jv[n], m), p.temperature));
     z += w;
-    const float q = p.expq ? p.expq[n] : philox_exp(seed, static_cast<unsigned>(p.cand_offset + n), 1u);
+    const float q = expq ? expq[n] : philox_exp(seed, static_cast<unsigned>(p.cand_offset + row0 + n), 1u);
     const float key = w / q;
     if (key > kbest) { kbest = key; ki = n; }
   }
@@ -199,16 +207,16 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const __grid_consta
   for (int a = 0; a < p.A; ++a) {
     float u = 0.f;
     for (int n = tid; n < p.N; n += SEL_THREADS) {
-      const float w = expf(__fmul_rn(__fsub_rn(p.J[n], m), p.temperature));
-      u = fmaf(w, p.cand[static_cast<size_t>(n) * stride_a0 + a], u);
+      const float w = expf(__fmul_rn(__fsub_rn(Jv[n], m), p.temperature));
+      u = fmaf(w, candv[static_cast<size_t>(n) * stride_a0 + a], u);
     }
     const float U = block_sum(u, redv);
     if (tid == 0) {
-      p.eval_action[a] = U / Z;
-      p.sample_action[a] = p.cand[static_cast<size_t>(ki) * stride_a0 + a];
+      eval_action[a] = U / Z;
+      sample_action[a] = candv[static_cast<size_t>(ki) * stride_a0 + a];
       if (p.partials) {
         p.partials[8 + a] = U;
-        p.partials[8 + p.A + a] = p.cand[static_cast<size_t>(ki) * stride_a0 + a];
+        p.partials[8 + p.A + a] = candv[static_cast<size_t>(ki) * stride_a0 + a];
       }
     }
   }
@@ -224,8 +232,8 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const __grid_consta
       p.partials[7] = 0.f;
     }
     if (p.indices) {
-      p.indices[0] = p.cand_offset + mi;
-      p.indices[1] = p.cand_offset + ki;
+      p.indices[2 * env + 0] = p.cand_offset + mi;
+      p.indices[2 * env + 1] = p.cand_offset + ki;
     }
   }
 }
@@ -317,8 +325,9 @@ int launch_score(const ScoreParams& p, cudaStream_t st) {
   return M3PC_OK;
 }
 int launch_select(const SelectParams& p, cudaStream_t st) {
-  M3PC_REQUIRE(p.A <= M3PC_MAX_ACT && p.N >= 1, "select: bad shape");
-  M3PC_CHECK_CUDA(launch_k(select_kernel, dim3(1), dim3(SEL_THREADS), 0, st, p));
+  M3PC_REQUIRE(p.A <= M3PC_MAX_ACT && p.N >= 1 && p.n_env >= 1, "select: bad shape");
+  M3PC_REQUIRE(p.n_env == 1 || p.partials == nullptr, "select: per-shard records are single-environment only");
+  M3PC_CHECK_CUDA(launch_k(select_kernel, dim3(p.n_env), dim3(SEL_THREADS), 0, st, p));
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
 }

@@ -60,6 +60,7 @@ class PlanEngine:
         self._sample = torch.empty(act_dim, device=self.device)
         self._partials = torch.zeros(nat.PARTIAL_FLOATS, device=self.device)
         self._indices = torch.zeros(2, dtype=torch.int32, device=self.device)
+        self._env_out = {}  # n_env -> (eval (E,A), sample (E,A), indices (E,2))
 
     # ------------------------------------------------------------------ parameters
     def set_param(self, name: str, value) -> None:
@@ -137,12 +138,34 @@ class PlanEngine:
     def plan(self, *, guidance: str, horizon: int, n_cand: int, win_states: torch.Tensor, win_actions: torch.Tensor,
              win_rewards: torch.Tensor, win_returns_tok: torch.Tensor, discount: float, temperature: float, lmbda: float,
              eps: Optional[torch.Tensor] = None, expq: Optional[torch.Tensor] = None, seed: int = 0, cand_offset: int = 0,
-             debug: bool = False, want_partials: bool = False):
+             debug: bool = False, want_partials: bool = False, n_env: int = 1):
         """One M^3PC plan on one window (learner.py:103-327).  All tensors are CUDA fp32, contiguous.
-        Returns (eval_action, sample_action, dbg) -- the action tensors are engine-owned and overwritten by the next call."""
+        Returns (eval_action, sample_action, dbg) -- the action tensors are engine-owned and overwritten by the next call.
+
+        ``n_env = E > 1`` plans E lock-step environments in the same launch sequence: windows carry a leading E axis,
+        ``eps`` is (E*n_cand, h, A), ``expq`` (E*n_cand,), and the returned actions are (E, A); row e equals the
+        single-window call on window e."""
         if not self.finalized:
             self.finalize()
+        E = int(n_env)
+        if E < 1:
+            raise ValueError("n_env must be >= 1")
+        if E > 1 and (want_partials or cand_offset):
+            raise ValueError("n_env > 1 cannot be combined with candidate sharding")
+        if E > 1:
+            for t, d in ((win_states, self.obs), (win_actions, self.act), (win_rewards, 1), (win_returns_tok, 1)):
+                if t.numel() != E * self.T * d:
+                    raise ValueError(f"window tensor of {t.numel()} elements, expected (E={E}, T={self.T}, {d})")
+        ev_out, sm_out = self._eval, self._sample
+        if E > 1:
+            if E not in self._env_out:  # persistent, so the plan's CUDA graph (keyed on buffer addresses) is reused
+                self._env_out[E] = (torch.empty(E, self.act, device=self.device), torch.empty(E, self.act, device=self.device),
+                                    torch.zeros(E, 2, dtype=torch.int32, device=self.device))
+            ev_out, sm_out, idx_out = self._env_out[E]
+        else:
+            idx_out = self._indices
         a = nat.PlanArgs()
+        a.n_env = E
         a.guidance = nat.GUIDANCE[guidance]
         a.horizon, a.n_cand, a.cand_offset = int(horizon), int(n_cand), int(cand_offset)
         a.discount, a.temperature, a.lmbda = float(discount), float(temperature), float(lmbda)
@@ -156,20 +179,20 @@ class PlanEngine:
             expq = _dev_f32(expq, "expq")
             a.expq = expq.data_ptr()
         a.seed = int(seed) & (2 ** 64 - 1)
-        a.out_eval_action, a.out_sample_action = self._eval.data_ptr(), self._sample.data_ptr()
+        a.out_eval_action, a.out_sample_action = ev_out.data_ptr(), sm_out.data_ptr()
         dbg = {}
-        if want_partials or debug:
+        if (want_partials or debug) and E == 1:
             a.out_partials = self._partials.data_ptr()
             dbg["partials"] = self._partials
         if debug and guidance != "mtm_sampling":
-            dbg["expect_return"] = torch.empty(n_cand, device=self.device)
-            dbg["candidates"] = torch.empty(n_cand, horizon, self.act, device=self.device)
-            dbg["indices"] = self._indices
+            dbg["expect_return"] = torch.empty(E * n_cand, device=self.device)
+            dbg["candidates"] = torch.empty(E * n_cand, horizon, self.act, device=self.device)
+            dbg["indices"] = idx_out
             a.dbg_expect_return, a.dbg_candidates = dbg["expect_return"].data_ptr(), dbg["candidates"].data_ptr()
-            a.dbg_indices = self._indices.data_ptr()
+            a.dbg_indices = idx_out.data_ptr()
         with torch.cuda.device(self.device):
             nat.check(self.lib.m3pc_plan(self._h, C.byref(a), _stream()), "m3pc_plan")
-        return self._eval, self._sample, dbg
+        return ev_out, sm_out, dbg
 
     def merge_partials(self, gathered: torch.Tensor, temperature: float):
         """Combine per-shard records (n_shards, PARTIAL_FLOATS) -> (eval_action, sample_action, indices)."""

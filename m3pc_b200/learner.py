@@ -48,7 +48,10 @@ class PlannerMixin:
     def _engine(self):
         if self.__dict__.get("_planner_bound") is not self.mtm:
             critic = getattr(getattr(self, "iql", None), "qf", None)
-            max_batch = max(int(getattr(self.cfg, "action_samples", 1)), int(getattr(self, "max_envs", 1)))
+            # forward planners batch max_envs windows x action_samples candidates; the backward planners batch max_envs rows
+            max_envs = int(getattr(self, "max_envs", 1))
+            max_batch = int(getattr(self.cfg, "action_samples", 1)) * (max_envs if getattr(self, "_envs_times_candidates", False) else 1)
+            max_batch = max(max_batch, max_envs)
             self.mtm.bind_planner(self.tokenizer_manager, critic, max_batch=max_batch)
             self.__dict__["_planner_bound"] = self.mtm
             self.__dict__["_plan_counter"] = 0
@@ -70,13 +73,13 @@ class PlannerMixin:
         self.__dict__["_plan_counter"] = c + 1
         return (int(self.seed) << 32) ^ c
 
-    def _plan_device(self, guidance: str, h: int, lmbda: float, ws, wa, wr, wt):
+    def _plan_device(self, guidance: str, h: int, lmbda: float, ws, wa, wr, wt, n_env: int = 1):
         eng = self._engine()
         eps, q = self.injected_noise if self.injected_noise is not None else (None, None)
         ev, sm, dbg = eng.plan(guidance=guidance, horizon=h, n_cand=int(self.cfg.action_samples), win_states=ws, win_actions=wa,
                                win_rewards=wr, win_returns_tok=wt, discount=float(self.cfg.discount), temperature=float(self.cfg.temperature),
                                lmbda=float(lmbda), eps=eps, expq=q, seed=self._next_seed(), cand_offset=int(self.cand_offset),
-                               debug=self.debug_plans)
+                               debug=self.debug_plans, n_env=n_env)
         if self.debug_plans:
             self.last_plan_debug = {k: v.clone() for k, v in dbg.items()}
         return ev, sm
@@ -198,14 +201,54 @@ class PlannerMixin:
         ev, sm = self._plan_device("mtm_sampling", horizon, 0.0, wb.d_states, wb.d_actions, wb.d_rewards, wb.d_returns)
         return ev.clone()[None, :] if eval else sm.clone()[None, :]
 
+    @torch.no_grad()
+    def action_sample_batch(self, histories, percentage=1.0, horizon=4, plan=True, eval=False, rtg=None):
+        """``action_sample`` for E lock-step environments in one ``m3pc_plan`` launch sequence (SURVEY.md section 8f rank 1;
+        the reference plans one environment per call, learner.py:329-417).  ``histories`` is a sequence of E history dicts that
+        share the planning-horizon regime; ``rtg`` a scalar or one value per environment.  Returns (E, act): row e is what
+        ``action_sample(histories[e], ...)`` returns (``eval_action`` if ``eval`` else ``sample_action``).  The E windows are
+        built in one pinned staging buffer and travel in one H2D copy; E * act floats come back."""
+        if eval == True:  # noqa: E712
+            assert rtg is not None
+        E = len(histories)
+        if E < 1:
+            raise ValueError("action_sample_batch needs at least one history")
+        if E > int(getattr(self, "max_envs", 1)):
+            raise ValueError(f"{E} environments but the Learner was built with max_envs={getattr(self, 'max_envs', 1)}")
+        if E == 1:
+            out = self.action_sample(histories[0], percentage, horizon, plan, eval, rtg if not isinstance(rtg, (list, tuple)) else rtg[0])
+            return out.reshape(1, -1)
+        self._engine()
+        horizons = {self._clamped_horizon(hist) for hist in histories}
+        if len(horizons) != 1:
+            raise ValueError("lock-step environments must share the planning horizon (same path_length regime)")
+        horizon = horizons.pop()
+        h0 = histories[0]
+        wb, slot = self._window_buffers(h0["observations"].shape[-1], h0["actions"].shape[-1], n_env=E)
+        for e_, hist in enumerate(histories):
+            self._fill_window(slot.h_states[e_], slot.h_actions[e_], slot.h_rewards[e_], slot.h_returns[e_], hist, horizon, percentage,
+                              rtg[e_] if isinstance(rtg, (list, tuple)) else rtg)
+        self._upload_window(wb, slot)
+        if plan:
+            assert self.cfg.plan_guidance in _PLAN_GUIDANCE
+            lmbda = 0.6 if self.cfg.plan_guidance == "rtg_guiding" else self.cfg.lmbda
+            guidance = self.cfg.plan_guidance
+        else:
+            lmbda, guidance = 0.0, "mtm_sampling"
+        ev, sm = self._plan_device(guidance, horizon, lmbda, wb.d_states, wb.d_actions, wb.d_rewards, wb.d_returns, n_env=E)
+        return ev.clone() if eval else sm.clone()
+
 
 class Learner(PlannerMixin):
     """Constructor-compatible with finetune_omtm/learner.py:17-101 (the optimiser / IQL-trainer halves are not built)."""
 
+    _envs_times_candidates = True  # engine capacity = max_envs * cfg.action_samples rows
+
     def __init__(self, cfg, env, data_shapes, model_config, pretrain_model_path, obs_mean, obs_std,
-                 tokenizer_manager: TokenizerManager, discrete_map: Dict[str, bool]):
+                 tokenizer_manager: TokenizerManager, discrete_map: Dict[str, bool], max_envs: int = 1):
         self.cfg = cfg
         self.env = env
+        self.max_envs = int(max_envs)  # largest E ``action_sample_batch`` will be given (1 = the reference's behaviour)
         self.mtm: omtm = model_config.create(data_shapes, cfg.traj_length, discrete_map)
         if pretrain_model_path is not None:
             self.mtm.load_state_dict(torch.load(pretrain_model_path, map_location="cpu")["model"])

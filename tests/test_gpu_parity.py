@@ -410,6 +410,80 @@ def test_philox_noise_is_shard_invariant_and_seeded():
     assert abs(float(zs.mean())) < 0.05 and abs(float((zs ** 2).mean()) - 1.0) < 0.05 and abs(float((zs ** 3).mean())) < 0.3
 
 
+# ------------------------------------------------------------------------------------------------ E lock-step environments per plan
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("env,guidance,temp,N,E,chunk", [("walker2d", "critic_lambda_guiding", 1.0, 96, 5, 0), ("hopper", "rtg_guiding", 0.01, 130, 3, 128),
+                                                         ("halfcheetah", "noise_adding_lambda", 1.0, 64, 4, 100)])
+def test_env_batched_plan_rows_equal_single_env_plans(precision, env, guidance, temp, N, E, chunk):
+    """m3pc_plan with n_env = E: row e of every output equals the single-window plan on window e
+    with the same injected noise.  Pass 2 is row-independent and bit-identical; pass 1 runs at B = E instead of B = 1 (tensor-core
+    tiles instead of the fused B = 1 kernel), so the candidates differ by bf16 rounding of mu / std.  chunk values that do not
+    divide N make a chunk straddle two environments."""
+    shape, L = _learner(env, guidance, N, temp, precision, chunk=chunk, max_envs=E)
+    T, A, h = shape.traj_length, shape.act_dim, 4
+    hists = [syn.make_history(shape, seed=30 + e, path_length=50 + 3 * e) for e in range(E)]
+    g = torch.Generator(device="cuda").manual_seed(1)
+    eps = torch.randn(E * N, h, A, device="cuda", generator=g)
+    q = torch.empty(E * N, device="cuda").exponential_(1.0, generator=g)
+    L.debug_plans = True
+    L.injected_noise = (eps, q)
+    rtgs = [2.0 + 0.25 * e for e in range(E)]
+    ev_b = L.action_sample_batch(hists, plan=True, eval=True, rtg=rtgs).clone()
+    db = L.last_plan_debug
+    sm_b = L.action_sample_batch(hists, plan=True, eval=False, rtg=rtgs).clone()
+    assert ev_b.shape == (E, A) and sm_b.shape == (E, A)
+    assert db["expect_return"].shape == (E * N,) and db["candidates"].shape == (E * N, h, A) and db["indices"].shape == (E, 2)
+    tol = TOL[precision]
+    for e in range(E):
+        L.injected_noise = (eps[e * N:(e + 1) * N].contiguous(), q[e * N:(e + 1) * N].contiguous())
+        ev = L.action_sample(hists[e], plan=True, eval=True, rtg=rtgs[e])
+        d = L.last_plan_debug
+        Jb, Js = db["expect_return"][e * N:(e + 1) * N].double(), d["expect_return"].double()
+        assert rel(db["candidates"][e * N:(e + 1) * N], d["candidates"]) < 3.5 * tol
+        errJ = float((Jb - Js).abs().max())
+        assert errJ <= tol * max(1.0, float(Js.abs().max()))
+        assert rel(ev_b[e], ev) < (1e-4 if precision == "fp32" else 2e-2)
+        # selection inside the batched call is consistent with its own scores, per environment
+        amax, sidx = [int(v) for v in db["indices"][e].tolist()]
+        assert amax == int(torch.argmax(Jb))
+        w = torch.exp((Jb - Jb.max()) * temp)
+        assert sidx == int(torch.argmax(w / q[e * N:(e + 1) * N].double()))
+        assert torch.equal(sm_b[e], db["candidates"][e * N + sidx, 0])
+        top2 = torch.topk(Js, 2).values
+        if float(top2[0] - top2[1]) > 2 * errJ:
+            assert amax == int(d["indices"][0])
+    # mtm_sampling (plan=False) on E windows
+    eps_s = torch.randn(E, A, device="cuda", generator=g)
+    L.injected_noise = (eps_s, None)
+    sm_all = L.action_sample_batch(hists, plan=False, eval=False, rtg=rtgs).clone()
+    assert sm_all.shape == (E, A)
+    for e in (0, E - 1):
+        L.injected_noise = (eps_s[e].contiguous(), None)
+        single = L.action_sample(hists[e], plan=False, eval=False, rtg=rtgs[e])
+        np.testing.assert_allclose(single[0].cpu().numpy(), sm_all[e].cpu().numpy(), atol=1e-4 if precision == "fp32" else 3e-2)
+
+
+def test_env_batched_plan_philox_and_graph_replay():
+    """Production path of the batched plan: on-device Philox noise, CUDA-graph replay; environments draw different noise,
+    identical windows with identical seeds reproduce, and E * n_cand above the engine capacity is rejected."""
+    E, N = 4, 256
+    shape, L = _learner("walker2d", "critic_lambda_guiding", N, 1.0, "bf16", max_envs=E)
+    hist = syn.make_history(shape, seed=5, path_length=60)
+    L._engine()  # binds the engine (and resets the plan counter) before the seeds are pinned below
+    outs = []
+    for _ in range(4):  # eager, capture, replay, replay
+        L.__dict__["_plan_counter"] = 7
+        outs.append(L.action_sample_batch([hist] * E, plan=True, eval=False, rtg=3.0).clone())
+    assert torch.isfinite(outs[0]).all() and float(outs[0].abs().max()) <= 1.0
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])            # same seed -> same draw, eager == replayed graph
+    assert not torch.equal(outs[0][0], outs[0][1])  # same window, different environment -> different noise stream
+    ev = L.action_sample_batch([hist] * E, plan=True, eval=True, rtg=3.0)
+    assert float((ev - ev[0:1]).abs().max()) < 0.25  # softmax-weighted means of 256 draws from the same distribution agree loosely
+    with pytest.raises(ValueError):
+        L.action_sample_batch([hist] * (E + 1), plan=True, eval=True, rtg=3.0)
+
+
 # ------------------------------------------------------------------------------------------------ zero-shot backward planners
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_zeroshot_matches_reference_golden(golden_dir, precision):
