@@ -1,17 +1,20 @@
 #!/usr/bin/env python
 """bench.py -- M^3PC plans/sec on B200 (BASELINE.json metric), one JSON line on rank 0.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--mode env|cand]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--mode env|cand] [--envs E]
 
-A "step" is one plan: one pass of the hot path (pass 1 at B=1, candidate sampling, pass 2 at B=candidates, critic /
-return scoring, softmax selection) for one environment state.  Default workload = BASELINE.json configs[1]: walker2d
-shapes (obs 17 / act 6), critic_lambda_guiding, 1024 candidates, horizon 4, shipped MTM (D=512, 4 heads, 2+1 layers,
-T=8), random-init weights, synthetic history.
+A plan is one pass of the hot path (pass 1, candidate sampling, pass 2 at B=candidates, critic / return scoring, softmax
+selection) for one environment state.  A "step" plans ``--envs`` E lock-step environments (default 8, each with its own
+history window and its own 1024 candidates) in ONE ``m3pc_plan`` launch sequence -- E plans per step; ``value`` counts plans.
+The reference's call shape (one window per call, E = 1) is always measured too and reported under ``single_env`` with its
+p50 latency.  Default workload = BASELINE.json configs[1]: walker2d shapes (obs 17 / act 6), critic_lambda_guiding, 1024
+candidates per plan, horizon 4, shipped MTM (D=512, 4 heads, 2+1 layers, T=8), random-init weights, synthetic histories.
 
   value     device-resident throughput: window already in HBM, K plans timed with CUDA events (one event pair per plan on
             the launching stream; a 256 MiB L2 flush between plans sits outside the pairs), max over ranks.
-  e2e       the same K plans through the public API ``Learner.action_sample`` with HOST numpy histories: pinned H2D of
-            the window and a D2H read of the action inside the timed region (host wall clock, max over ranks).
+  e2e       the same K steps through the public API ``Learner.action_sample_batch`` (``action_sample`` at E = 1) with HOST numpy
+            histories: window building, one pinned H2D of the E windows and a D2H read of the E actions inside the timed
+            region (host wall clock, max over ranks).
   roofline  tensor-core GEMMs (the dominant kernel): algorithmic FLOPs of the GEMM launches / their summed per-launch
             CUDA-event time in a profiling pass of the same plan, against MEASURED_PEAKS.json (sustained bf16).
   cpu_baseline  the oracle port of the reference planner (torch CPU fp32, all host threads), same workload, bounded sample.
@@ -378,7 +381,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="walker2d_critic_1024", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="env", choices=["env", "cand"])
-    ap.add_argument("--envs", type=int, default=1, help="lock-step environments planned per step on each GPU (one m3pc_plan launch sequence)")
+    ap.add_argument("--envs", type=int, default=8, help="lock-step environments planned per step on each GPU (one m3pc_plan launch sequence)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

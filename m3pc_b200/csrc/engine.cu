@@ -1237,7 +1237,7 @@ int create(m3pc_handle_t* out, const m3pc_config_t* cfg) {
   e->obs = cfg->obs_dim; e->act = cfg->act_dim; e->Le = cfg->n_enc_layer; e->Ld = cfg->n_dec_layer; e->QH = cfg->critic_hidden;
   e->dims[0] = e->obs; e->dims[1] = e->act; e->dims[2] = 1; e->dims[3] = 1;
   e->bf16 = cfg->precision == M3PC_PREC_BF16;
-  e->chunk = cfg->chunk > 0 ? cfg->chunk : 4096;  // measured (profiles/r1b_*): 16384 candidates take 7.0 ms in chunks of 1024, 5.9 ms in chunks of 4096
+  e->chunk = cfg->chunk > 0 ? cfg->chunk : 8192;  // measured (profiles/r1e_chunk_sweep.txt, 8 x 1024 rows per step): 3.86 ms in chunks of 1024, 3.28 ms at 4096, 3.20 ms at 8192
   e->chunk = std::min(e->chunk, cfg->max_batch);
   if (e->bf16) M3PC_TRY(gemm_init_driver_api());
   const size_t rows = static_cast<size_t>(4) * e->T * e->chunk + 128;  // +128: slack rows for tile tails

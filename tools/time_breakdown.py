@@ -68,6 +68,37 @@ def sec_plan():
             del eng
 
 
+def sec_envs():
+    """pass 1 alone (mtm_sampling) and the whole plan at E lock-step environments x 1024 candidates"""
+    import bench
+    from m3pc_b200 import synthetic as syn
+    from m3pc_b200.engine import engine_from_synthetic
+    flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
+    name = "walker2d_critic_1024"
+    w = bench.WORKLOADS[name]
+    shape = bench.model_shape(w)
+    T, N, h = shape.traj_length, 1024, 4
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for E in (1, 2, 4, 8, 16, 32):
+        ws, wa = torch.randn(E, T, shape.obs_dim, device="cuda", generator=g), torch.rand(E, T, shape.act_dim, device="cuda", generator=g) * 2 - 1
+        wr, wt = torch.randn(E, T, device="cuda", generator=g), torch.full((E, T), 0.7, device="cuda")
+        eng = engine_from_synthetic(shape, syn.make_state_dict(shape, 0), syn.make_tokenizer_stats(shape, 1), precision="bf16", max_batch=N * E,
+                                    critic_sd=syn.make_critic_state_dict(shape), obs_norm=syn.make_obs_norm(shape))
+        for guid in ("mtm_sampling", w["guidance"]):
+            seed = [0]
+
+            def fn():
+                seed[0] += 1
+                eng.plan(guidance=guid, horizon=h, n_cand=N, win_states=ws, win_actions=wa, win_rewards=wr, win_returns_tok=wt,
+                         discount=0.99, temperature=w["temperature"], lmbda=0.6, seed=seed[0], n_env=E)
+
+            m_warm, mn_warm = time_calls(fn)
+            m_cold, mn_cold = time_calls(fn, flush=flush)
+            print(f"envs {name} E={E} N={N} guidance={guid} launches={eng.last_launch_count()} warm-L2 med {m_warm:.1f} us (min {mn_warm:.1f}) | "
+                  f"L2-flushed med {m_cold:.1f} us (min {mn_cold:.1f}) = {m_cold / E:.1f} us per plan", flush=True)
+        del eng
+
+
 def sec_gemm():
     from m3pc_b200 import _native as nat
     L = nat.lib()
