@@ -342,6 +342,7 @@ struct alignas(64) GroupProblem {
 struct GroupParams {
   GroupProblem p[MAX_GROUP];
   int n, total_units;
+  int strided;  // 1: pair p works on units p, p + n_pairs, ... (see launch_2sm) instead of one contiguous range
 };
 struct UnitCoord { int g, mp, nt, ks; };
 __device__ __forceinline__ UnitCoord decode_unit(const GroupParams& gp, int u) {
@@ -378,8 +379,11 @@ __global__ void __launch_bounds__(GEMM_THREADS_2SM, 1) gemm_bf16_2sm_kernel(cons
   const int total_units = gp.total_units;
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   // units are ordered m-major and split contiguously: a pair mostly stays on one row block, whose A slab stays hot in L2
-  const int u_lo = static_cast<int>(static_cast<long long>(pair) * total_units / n_pairs);
-  const int u_hi = static_cast<int>(static_cast<long long>(pair + 1) * total_units / n_pairs);
+  // strided (N = 512 problems with a long K): neighbouring pairs take the two column tiles of the SAME row block at the same
+  // time, so its A slab is fetched from HBM once and the second reader hits L2 (contiguous ranges re-read it ~150 MB later)
+  const int u_step = gp.strided ? n_pairs : 1;
+  const int u_lo = gp.strided ? pair : static_cast<int>(static_cast<long long>(pair) * total_units / n_pairs);
+  const int u_hi = gp.strided ? total_units : static_cast<int>(static_cast<long long>(pair + 1) * total_units / n_pairs);
 
   if (warp == 0 && lane == 0) {
     for (int g = 0; g < gp.n; ++g) {
@@ -415,7 +419,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_2SM, 1) gemm_bf16_2sm_kernel(cons
       const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[0]), 0);
       int s = 0;
       uint32_t ph = 0;
-      for (int u = u_lo; u < u_hi; ++u) {
+      for (int u = u_lo; u < u_hi; u += u_step) {
         const UnitCoord uc = decode_unit(gp, u);
         const GroupProblem& P = gp.p[uc.g];
         const int m0 = (uc.mp * 2 + static_cast<int>(crank)) * BM, n0 = uc.nt * BN + static_cast<int>(crank) * 128;
@@ -437,7 +441,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_2SM, 1) gemm_bf16_2sm_kernel(cons
       constexpr uint32_t idesc = make_idesc_mn(2 * BM, BN);
       int s = 0, it = 0;
       uint32_t ph = 0;
-      for (int u = u_lo; u < u_hi; ++u, ++it) {
+      for (int u = u_lo; u < u_hi; u += u_step, ++it) {
         const int a = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&acc_empty[a], aph ^ 1);
@@ -469,7 +473,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_2SM, 1) gemm_bf16_2sm_kernel(cons
     const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);  // SWIZZLE_64B: 16-byte chunk j of row r lives at j ^ ((r >> 1) & 3)
     int it = 0;
     uint32_t nstore = 0;  // chunks staged so far (selects the staging buffer)
-    for (int u = u_lo; u < u_hi; ++u, ++it) {
+    for (int u = u_lo; u < u_hi; u += u_step, ++it) {
       const UnitCoord uc = decode_unit(gp, u);
       const GroupProblem& P = gp.p[uc.g];
       const CUtensorMap* tmap_c = &P.tc;
@@ -673,6 +677,7 @@ int make_tmap_out(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t cols, boo
 }
 namespace {
 
+int g_use_strided = 1;  // M3PC_GEMM_STRIDED=0 restores contiguous unit ranges for every problem
 int g_use_splitk = 0;  // M3PC_GEMM_SPLITK=1 enables split-K (measured +0.4% plans/s at 1024 candidates; off by default: the reduce-add order of the two halves is not reproducible run to run)
 
 // One launch of the CTA-pair kernel over `n` problems (n <= MAX_GROUP; every N a multiple of 256).
@@ -719,6 +724,7 @@ int launch_2sm(const GemmProblem* probs, int n, cudaStream_t st) {
   }
   gp.total_units = units;
   const int pairs = std::min(units, n_pairs_max);
+  gp.strided = g_use_strided && n == 1 && gp.p[0].n_tiles == 2 && gp.p[0].ksplit == 1 && probs[0].K >= 1024 && pairs % 2 == 0 && units >= 2 * pairs;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(GEMM_THREADS_2SM);
@@ -770,6 +776,7 @@ int gemm_init_driver_api() {
   g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
   if (const char* f = getenv("M3PC_GEMM_2SM")) g_use_2sm = atoi(f);
   if (const char* f = getenv("M3PC_GEMM_SPLITK")) g_use_splitk = atoi(f);
+  if (const char* f = getenv("M3PC_GEMM_STRIDED")) g_use_strided = atoi(f);
   if (const char* f = getenv("M3PC_GEMM_DEBUG_SKIP_EPI")) g_debug_skip_epi = atoi(f);
   if (const char* f = getenv("M3PC_GEMM_CONFIG")) {
     if (sscanf(f, "%dx%d", &g_force_bn, &g_force_cl) != 2 || (g_force_bn != 128 && g_force_bn != 256) || (g_force_cl != 1 && g_force_cl != 2))

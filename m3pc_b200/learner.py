@@ -121,8 +121,9 @@ class PlannerMixin:
         its H2D copy is still queued) and one device buffer, laid out [states | actions | rewards | returns_tok]."""
         T = self.cfg.traj_length
         key = (obs_dim, act_dim, T, n_env)
-        ring = self.__dict__.get("_win")
-        if ring is None or ring.key != key:
+        rings = self.__dict__.setdefault("_win", {})  # one ring per window geometry: groups of different sizes do not evict each other
+        ring = rings.get(key)
+        if ring is None:
             n = n_env * T * (obs_dim + act_dim + 2)
             dev = torch.zeros(n, dtype=torch.float32, device=self.mtm.pos_embed.device)
             o = [0, n_env * T * obs_dim, n_env * T * (obs_dim + act_dim), n_env * T * (obs_dim + act_dim + 1), n]
@@ -139,7 +140,7 @@ class PlannerMixin:
             ring = SimpleNamespace(key=key, slots=slots, turn=0, dev=dev,
                                    d_states=dev[o[0]:o[1]].view(shp[0]), d_actions=dev[o[1]:o[2]].view(shp[1]),
                                    d_rewards=dev[o[2]:o[3]].view(shp[2]), d_returns=dev[o[3]:o[4]].view(shp[3]))
-            self.__dict__["_win"] = ring
+            rings[key] = ring
         slot = ring.slots[ring.turn]
         ring.turn ^= 1
         if slot.used:
@@ -237,6 +238,72 @@ class PlannerMixin:
             lmbda, guidance = 0.0, "mtm_sampling"
         ev, sm = self._plan_device(guidance, horizon, lmbda, wb.d_states, wb.d_actions, wb.d_rewards, wb.d_returns, n_env=E)
         return ev.clone() if eval else sm.clone()
+
+
+    @torch.no_grad()
+    def action_sample_async(self, histories, percentage=1.0, plan=True, eval=False, rtg=None) -> "PlanTicket":
+        """``action_sample_batch`` without the host synchronisation: the window upload, the plan and
+        the device-to-host copy of the E actions are enqueued on the current stream and a ticket is returned at once;
+        ``ticket.result()`` waits for that copy only.  The reference's callers block in ``action.cpu()`` every step
+        (replay_buffer.py:211-214, learner.py:681-689); with a ticket the caller can step other environments meanwhile
+        (``m3pc_b200.rollout``)."""
+        if eval == True:  # noqa: E712
+            assert rtg is not None
+        E = len(histories)
+        if E < 1 or E > int(getattr(self, "max_envs", 1)):
+            raise ValueError(f"{E} environments but the Learner was built with max_envs={getattr(self, 'max_envs', 1)}")
+        self._engine()
+        horizons = {self._clamped_horizon(hist) for hist in histories}
+        if len(horizons) != 1:
+            raise ValueError("lock-step environments must share the planning horizon (same path_length regime)")
+        horizon = horizons.pop()
+        h0 = histories[0]
+        wb, slot = self._window_buffers(h0["observations"].shape[-1], h0["actions"].shape[-1], n_env=E)
+        for e_, hist in enumerate(histories):
+            v = (slot.h_states, slot.h_actions, slot.h_rewards, slot.h_returns) if E == 1 else \
+                (slot.h_states[e_], slot.h_actions[e_], slot.h_rewards[e_], slot.h_returns[e_])
+            self._fill_window(*v, hist, horizon, percentage, rtg[e_] if isinstance(rtg, (list, tuple, np.ndarray)) else rtg)
+        self._upload_window(wb, slot)
+        if plan:
+            assert self.cfg.plan_guidance in _PLAN_GUIDANCE
+            lmbda = 0.6 if self.cfg.plan_guidance == "rtg_guiding" else self.cfg.lmbda
+            guidance = self.cfg.plan_guidance
+        else:
+            lmbda, guidance = 0.0, "mtm_sampling"
+        ev, sm = self._plan_device(guidance, horizon, lmbda, wb.d_states, wb.d_actions, wb.d_rewards, wb.d_returns, n_env=E)
+        pool = self.__dict__.setdefault("_tickets", {})
+        free = pool.setdefault(E, [])
+        ticket = free.pop() if free else PlanTicket(E, ev.shape[-1], free)
+        ticket._submit(ev if eval else sm)
+        return ticket
+
+
+class PlanTicket:
+    """Pinned landing buffer + CUDA event of one in-flight ``action_sample_async``; recycled through the Learner's pool."""
+
+    def __init__(self, n_env: int, act_dim: int, pool: list):
+        self._host = torch.empty(n_env, act_dim, dtype=torch.float32).pin_memory()
+        self._event = torch.cuda.Event()
+        self._pool = pool
+        self._pending = False
+
+    def _submit(self, actions: torch.Tensor) -> None:
+        self._host.copy_(actions.reshape(self._host.shape), non_blocking=True)
+        self._event.record()
+        self._pending = True
+
+    def done(self) -> bool:
+        return self._event.query()
+
+    def result(self) -> np.ndarray:
+        """(E, act) float32; blocks until the device-to-host copy of THIS plan has landed (not a device-wide sync)."""
+        if not self._pending:
+            raise RuntimeError("PlanTicket.result() called twice")
+        self._event.synchronize()
+        out = self._host.numpy().copy()
+        self._pending = False
+        self._pool.append(self)
+        return out
 
 
 class Learner(PlannerMixin):

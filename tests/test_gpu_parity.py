@@ -484,6 +484,44 @@ def test_env_batched_plan_philox_and_graph_replay():
         L.action_sample_batch([hist] * (E + 1), plan=True, eval=True, rtg=3.0)
 
 
+# ------------------------------------------------------------------------------------------------ checkpoints in the reference's formats
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_plan_from_reference_format_checkpoints(golden_dir, precision):
+    """mtm_<step>.pt + iql_<step>.pt + d4rl_statistics_*.pkl written by the reference's classes (tests/golden/ckpt) ->
+    m3pc_b200.checkpoint.build_learner -> plan on the GPU == the float64 oracle fed the same tensors.  Also exercises a
+    non-shipped geometry (D=128, one head, T=4, obs 3 / act 2)."""
+    from m3pc_b200 import checkpoint as ck
+    from m3pc_b200.mtm_model import omtmConfig
+    from oracle import planner_oracle as po
+    d = os.path.join(golden_dir, "ckpt")
+    N, T, h = 48, 4, 2
+    cfg = SimpleNamespace(traj_length=T, device="cuda", action_samples=N, discount=0.99, temperature=1.0, horizon=h,
+                          plan_guidance="critic_lambda_guiding", lmbda=0.6)
+    mcfg = omtmConfig(n_embd=128, n_head=1, n_enc_layer=1, n_dec_layer=1, dropout=0.1, norm="none", precision=precision, max_batch=N)
+    L = ck.build_learner(cfg, mcfg, os.path.join(d, "mtm_7.pt"), os.path.join(d, "d4rl_statistics_tiny.pkl"), iql_path=os.path.join(d, "iql_7.pt"))
+    stats = ck.load_trajectory_statistics(os.path.join(d, "d4rl_statistics_tiny.pkl"))
+    tm = ck.tokenizer_manager_from_statistics(stats)
+    stats_np = {k: {"mean": tm.tokenizers[k]._data_mean.numpy(), "std": tm.tokenizers[k]._data_std.numpy(), "min": stats[k].min, "max": stats[k].max}
+                for k in stats}
+    shape = syn.ModelShape(obs_dim=3, act_dim=2, n_embd=128, n_head=1, n_enc_layer=1, n_dec_layer=1, traj_length=T)
+    P = po.from_synthetic(shape, {k: v.numpy() for k, v in ck.load_mtm_checkpoint(os.path.join(d, "mtm_7.pt")).items()}, stats_np, dtype=torch.float64,
+                          critic_np={k: v.numpy() for k, v in ck.load_iql_checkpoint(os.path.join(d, "iql_7.pt")).items()},
+                          obs_norm=(stats["states"].mean, stats["states"].std), action_samples=N, temperature=1.0,
+                          plan_guidance="critic_lambda_guiding", horizon=h)
+    hist = syn.make_history(shape, seed=3, path_length=20)
+    rs = np.random.RandomState(5)
+    eps, q = torch.from_numpy(rs.randn(N, 1, T, 1, 2)), torch.from_numpy(rs.exponential(1.0, N))
+    L.injected_noise = (eps[:, 0, T - h:, 0, :].float().contiguous().cuda(), q.float().cuda())
+    L.debug_plans = True
+    ev = L.action_sample(hist, plan=True, eval=True, rtg=1.5)
+    _, ref = P.action_sample(hist, plan=True, eval=True, rtg=1.5, eps=eps, q=q)
+    tol = TOL[precision]
+    J, Jr = L.last_plan_debug["expect_return"].double().cpu(), ref["expect_return"]
+    assert float((J - Jr).abs().max()) <= tol * max(1.0, float(Jr.abs().max()))
+    assert rel(L.last_plan_debug["candidates"], ref["candidates"]) < 3.5 * tol
+    assert rel(ev, ref["eval_action"]) < (1e-4 if precision == "fp32" else 2e-2)
+
+
 # ------------------------------------------------------------------------------------------------ zero-shot backward planners
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_zeroshot_matches_reference_golden(golden_dir, precision):
