@@ -196,10 +196,10 @@ def run_ours(args, w, shape, rank, local_rank, world):
     cfg = SimpleNamespace(traj_length=T, device=str(dev), action_samples=n_local, discount=0.99, temperature=w["temperature"], horizon=h,
                           plan_guidance=w["guidance"], lmbda=0.6)
     mcfg = omtmConfig(n_embd=shape.n_embd, n_head=shape.n_head, n_enc_layer=shape.n_enc_layer, n_dec_layer=shape.n_dec_layer, dropout=0.1,
-                      norm="none", precision=args.precision, max_batch=n_local * (1 if args.mode == "cand" and world > 1 else max(1, args.envs)),
+                      norm="none", precision=args.precision, max_batch=n_local * (1 if args.mode == "cand" else max(1, args.envs)),
                       chunk=args.chunk)
     om, os_ = syn.make_obs_norm(shape)
-    E_head = 1 if cand_mode else max(1, args.envs)
+    E_head = 1 if args.mode == "cand" else max(1, args.envs)  # candidate sharding splits ONE plan across ranks
     L = Learner(cfg, None, shape.data_shapes, mcfg, None, om, os_, manager_from_stats(stats), {k: False for k in shape.data_shapes},
                 max_envs=E_head)
     L.mtm.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
@@ -394,6 +394,7 @@ def main():
         run_reference(args, w, shape, rank)
         return
     from m3pc_b200 import dist as mdist
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # a box-level NCCL_DEBUG=VERSION would otherwise print to stdout, next to the JSON line
     mdist.init_from_env("nccl")
     try:
         run_ours(args, w, shape, rank, local_rank, world)

@@ -159,6 +159,17 @@ int m3pc_backward_plan(m3pc_handle_t h, int32_t mode, int32_t n_env, int32_t hor
                        const float* eps, float* out_eval_action, float* out_sample_action, float* dbg_states_filled,
                        void* stream);
 
+/* m3pc_backward_plan with C action draws per environment (BASELINE.json config 4: "256 parallel envs x 512 candidates").
+ * The reference draws ONE action per call, ``action_dist.sample()`` at step T-h of the last pass
+ * (zeroshot_omtm/learner.py:136-147, :248-259); C calls on the same history draw C i.i.d. actions from the same
+ * distribution.  Here the (one or two) forward passes run once per environment and all C draws come from their action
+ * head:   out_sample_actions[e, c, :] = tanh(mu_e + std_e * eps[e, c, :]),   out_eval_action[e, :] = tanh(mu_e).
+ *   eps   device (E, C, A) injected N(0,1) noise, or NULL: Philox keyed by (seed, environment, draw)
+ *   out_sample_actions device (E, C, A);  n_draws = 1 with the same eps is exactly m3pc_backward_plan. */
+int m3pc_backward_plan_draws(m3pc_handle_t h, int32_t mode, int32_t n_env, int32_t horizon, int32_t n_draws, const float* win_states,
+                             const float* win_actions, const float* win_rewards, const float* win_returns_tok, const float* eps,
+                             uint64_t seed, float* out_eval_action, float* out_sample_actions, void* stream);
+
 /* ---- kernel-level entry points (unit parity tests and profiling; same kernels the calls above launch) ---- */
 
 /* C[M,N] = epilogue(A[M,K] * W[N,K]^T): flags bit0 = GELU(erf), bit1 = C += residual (fp32 in place, C is fp32),

@@ -1171,7 +1171,8 @@ int plan(m3pc_engine* e, const m3pc_plan_args_t* a, cudaStream_t st) {
 }
 
 int backward_plan(m3pc_engine* e, int mode, int E, int h, const float* ws, const float* wa, const float* wr, const float* wrt,
-                  const float* eps, float* out_eval, float* out_sample, float* dbg_filled, cudaStream_t st) {
+                  const float* eps, float* out_eval, float* out_sample, float* dbg_filled, cudaStream_t st, int n_draws = 1,
+                  unsigned long long seed = 0ull) {
   M3PC_REQUIRE(e->finalized, "backward_plan before m3pc_finalize_params");
   const int T = e->T, idx = T - h, A = e->act;
   M3PC_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (id) or 1 (piid)");
@@ -1210,7 +1211,7 @@ int backward_plan(m3pc_engine* e, int mode, int E, int h, const float* ws, const
     io2.need_nt[M3PC_ACTIONS] = 1;
     M3PC_TRY(forward(e, io2, E, st));
   }
-  return launch_sampling_tail(e->e_mu.as<float>(), e->e_std.as<float>(), eps, T, h, A, E, out_eval, out_sample, 0ull, nullptr, st);
+  return launch_sampling_tail(e->e_mu.as<float>(), e->e_std.as<float>(), eps, T, h, A, E, out_eval, out_sample, seed, nullptr, st, n_draws);
 }
 
 int create(m3pc_handle_t* out, const m3pc_config_t* cfg) {
@@ -1372,6 +1373,19 @@ int m3pc_backward_plan(m3pc_handle_t h, int32_t mode, int32_t n_env, int32_t hor
   return m3pc::timed(h, st, [&] {
     return m3pc::backward_plan(h, mode, n_env, horizon, win_states, win_actions, win_rewards, win_returns_tok, eps, out_eval_action,
                                out_sample_action, dbg_states_filled, st);
+  });
+}
+
+int m3pc_backward_plan_draws(m3pc_handle_t h, int32_t mode, int32_t n_env, int32_t horizon, int32_t n_draws, const float* win_states,
+                             const float* win_actions, const float* win_rewards, const float* win_returns_tok, const float* eps,
+                             uint64_t seed, float* out_eval_action, float* out_sample_actions, void* stream) {
+  M3PC_REQUIRE(h != nullptr && win_states && win_actions && win_rewards && win_returns_tok && out_eval_action && out_sample_actions,
+               "null argument");
+  M3PC_REQUIRE(n_draws >= 1 && n_draws <= (1 << 20), "n_draws out of range");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return m3pc::timed(h, st, [&] {
+    return m3pc::backward_plan(h, mode, n_env, horizon, win_states, win_actions, win_rewards, win_returns_tok, eps, out_eval_action,
+                               out_sample_actions, nullptr, st, n_draws, seed);
   });
 }
 

@@ -213,8 +213,9 @@ int launch_merge(const float* partials, int n_shards, int A, float temperature, 
                  cudaStream_t st);
 
 // mtm_sampling tail (learner.py:103-115): eval = tanh(mu[T-h]), sample = tanh(mu[T-h] + std[T-h]*eps)
+// C > 1: C draws per environment, sample_action is (E, C, A) and eps (E, C, A)
 int launch_sampling_tail(const float* mu, const float* std, const float* eps, int T, int h, int A, int E, float* eval_action,
-                         float* sample_action, unsigned long long seed, const unsigned long long* seed_ptr, cudaStream_t st);
+                         float* sample_action, unsigned long long seed, const unsigned long long* seed_ptr, cudaStream_t st, int C = 1);
 int launch_set_seed(unsigned long long* dst, unsigned long long seed, cudaStream_t st);
 
 // zero-shot piid fill (zeroshot_omtm/learner.py:240-246): states[:, T-h+2:-1] and states[:, :T-h+1] <- decode(pred)

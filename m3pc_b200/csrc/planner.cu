@@ -272,18 +272,19 @@ __global__ void merge_kernel(const float* __restrict__ partials, int n_shards, i
 
 __global__ void set_seed_kernel(unsigned long long* dst, unsigned long long seed) { *dst = seed; }
 
+// C draws per environment: i = (e * C + c) * A + a.  C = 1 is the reference's single draw (zeroshot_omtm/learner.py:136-147).
 __global__ void sampling_tail_kernel(const float* __restrict__ mu, const float* __restrict__ std, const float* __restrict__ eps, int T, int h,
-                                     int A, int E, float* eval_action, float* sample_action, unsigned long long seed,
+                                     int A, int E, int C, float* eval_action, float* sample_action, unsigned long long seed,
                                      const unsigned long long* seed_ptr) {
   PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= E * A) return;
+  if (i >= E * C * A) return;
   if (seed_ptr) seed = *seed_ptr;
-  const int e = i / A, a = i - e * A;
+  const int a = i % A, c = (i / A) % C, e = i / (A * C);
   const size_t src = (static_cast<size_t>(e) * T + (T - h)) * A + a;
   const float m = mu[src];
-  const float z = eps ? eps[i] : philox_normal(seed, static_cast<unsigned>(e), static_cast<unsigned>(a), 2u);
-  eval_action[i] = tanhf(m);
+  const float z = eps ? eps[i] : philox_normal(seed, static_cast<unsigned>(e), static_cast<unsigned>(c * A + a), 2u);
+  if (c == 0) eval_action[e * A + a] = tanhf(m);
   sample_action[i] = tanhf(__fadd_rn(m, __fmul_rn(std[src], z)));
 }
 
@@ -338,8 +339,9 @@ int launch_merge(const float* partials, int n_shards, int A, float temperature, 
   return M3PC_OK;
 }
 int launch_sampling_tail(const float* mu, const float* std, const float* eps, int T, int h, int A, int E, float* eval_action,
-                         float* sample_action, unsigned long long seed, const unsigned long long* seed_ptr, cudaStream_t st) {
-  M3PC_CHECK_CUDA(launch_k(sampling_tail_kernel, dim3(ceil_div(E * A, 128)), dim3(128), 0, st, mu, std, eps, T, h, A, E, eval_action, sample_action, seed, seed_ptr));
+                         float* sample_action, unsigned long long seed, const unsigned long long* seed_ptr, cudaStream_t st, int C) {
+  M3PC_REQUIRE(C >= 1, "sampling tail: n_draws must be >= 1");
+  M3PC_CHECK_CUDA(launch_k(sampling_tail_kernel, dim3(ceil_div(E * C * A, 128)), dim3(128), 0, st, mu, std, eps, T, h, A, E, C, eval_action, sample_action, seed, seed_ptr));
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
 }

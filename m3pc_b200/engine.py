@@ -204,13 +204,28 @@ class PlanEngine:
         return self._eval, self._sample, self._indices
 
     def backward_plan(self, *, mode: str, horizon: int, win_states: torch.Tensor, win_actions: torch.Tensor, win_rewards: torch.Tensor,
-                      win_returns_tok: torch.Tensor, eps: Optional[torch.Tensor] = None, debug: bool = False):
-        """Zero-shot backward planners on E environments (zeroshot_omtm/learner.py:60-261). Windows have a leading E axis."""
+                      win_returns_tok: torch.Tensor, eps: Optional[torch.Tensor] = None, debug: bool = False, n_draws: Optional[int] = None,
+                      seed: int = 0):
+        """Zero-shot backward planners on E environments (zeroshot_omtm/learner.py:60-261). Windows have a leading E axis.
+        ``n_draws = C``: C action draws per environment from one set of forward passes -> sample actions (E, C, A); eps (E, C, A)."""
         if not self.finalized:
             self.finalize()
         ws = _dev_f32(win_states, "win_states")
         E = ws.shape[0]
         wa, wr, wt = _dev_f32(win_actions, "win_actions"), _dev_f32(win_rewards, "win_rewards"), _dev_f32(win_returns_tok, "win_returns_tok")
+        if n_draws is not None:
+            Cn = int(n_draws)
+            ev = torch.empty(E, self.act, device=self.device)
+            sm = torch.empty(E, Cn, self.act, device=self.device)
+            if eps is not None:
+                eps = _dev_f32(eps, "eps")
+                if eps.numel() != E * Cn * self.act:
+                    raise ValueError(f"eps has {eps.numel()} elements, expected (E={E}, C={Cn}, A={self.act})")
+            with torch.cuda.device(self.device):
+                nat.check(self.lib.m3pc_backward_plan_draws(self._h, {"id": 0, "piid": 1}[mode], E, int(horizon), Cn, ws.data_ptr(), wa.data_ptr(),
+                                                            wr.data_ptr(), wt.data_ptr(), _ptr(eps), int(seed) & (2 ** 64 - 1), ev.data_ptr(),
+                                                            sm.data_ptr(), _stream()), "m3pc_backward_plan_draws")
+            return ev, sm, {}
         ev = torch.empty(E, self.act, device=self.device)
         sm = torch.empty(E, self.act, device=self.device)
         filled = torch.empty(E, self.T, self.obs, device=self.device) if debug else None

@@ -35,7 +35,7 @@ class Learner(PlannerMixin):
     #: eps (E, A) consumed by ``action_dist.sample()`` instead of the device Philox stream (parity tests)
     injected_eps: Optional[torch.Tensor] = None
 
-    def _backward(self, mode: str, histories: Sequence[dict], percentage, rtg):
+    def _backward(self, mode: str, histories: Sequence[dict], percentage, rtg, n_draws: Optional[int] = None):
         eng = self._engine()
         horizons = {self._clamped_horizon(h) for h in histories}
         if len(horizons) != 1:
@@ -54,7 +54,7 @@ class Learner(PlannerMixin):
         T = self.cfg.traj_length
         ev, sm, dbg = eng.backward_plan(mode=mode, horizon=horizon, win_states=wb.d_states.view(E, T, -1), win_actions=wb.d_actions.view(E, T, -1),
                                         win_rewards=wb.d_rewards.view(E, T), win_returns_tok=wb.d_returns.view(E, T), eps=self.injected_eps,
-                                        debug=self.debug_plans)
+                                        debug=self.debug_plans, n_draws=n_draws, seed=self._next_seed())
         if self.debug_plans:
             self.last_plan_debug = dbg
         return ev, sm
@@ -85,6 +85,13 @@ class Learner(PlannerMixin):
     def action_id_sample_batch(self, histories: Sequence[dict], percentage=1.0, eval=False, rtg=None):
         ev, sm = self._backward("id", histories, percentage, rtg)
         return ev if eval else sm
+
+    @torch.no_grad()
+    def action_piid_draws_batch(self, histories: Sequence[dict], n_draws: int, percentage=1.0, rtg=None, mode: str = "piid"):
+        """BASELINE.json config 4 (E environments x C candidate actions): the piid (or id) passes run once per environment and
+        C actions are drawn from the resulting distribution -- what C calls of the reference's ``action_piid_sample`` on the same
+        history draw (zeroshot_omtm/learner.py:248-259).  Returns (mean action (E, A), draws (E, C, A))."""
+        return self._backward(mode, histories, percentage, rtg, n_draws=int(n_draws))
 
     @torch.no_grad()
     def action_piid_sample_batch(self, histories: Sequence[dict], percentage=1.0, eval=False, rtg=None):

@@ -557,3 +557,37 @@ def test_zeroshot_batch_rows_equal_single_env_calls(precision):
         np.testing.assert_allclose(single[0].cpu().numpy(), batch[e].cpu().numpy(), atol=1e-5 if precision == "fp32" else 1e-2)
     ids = L.action_id_sample_batch(hists, eval=True, rtg=2.0)
     assert ids.shape == (37, shape.act_dim) and torch.isfinite(ids).all()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_zeroshot_candidate_draws_per_environment(precision):
+    """BASELINE.json config 4 shape (E environments x C candidate actions): every draw is tanh(mu_e + std_e * eps[e, c]) of the
+    distribution the single-draw planner samples from; draw c of environment e with injected noise == the reference-shaped
+    single call with that noise; Philox draws differ across environments / draws and follow the distribution."""
+    from m3pc_b200.zeroshot_learner import Learner as ZLearner
+    E, C = 9, 64
+    shape, L = _learner("hopper", "rtg_guiding", 1, 0.01, precision, cls=ZLearner, max_envs=E)
+    A = shape.act_dim
+    hists = [syn.make_history(shape, seed=60 + e, path_length=45 + e) for e in range(E)]
+    g = torch.Generator(device="cuda").manual_seed(2)
+    eps = torch.randn(E, C, A, device="cuda", generator=g)
+    L.injected_eps = eps
+    ev, draws = L.action_piid_draws_batch(hists, C, rtg=2.0)
+    assert ev.shape == (E, A) and draws.shape == (E, C, A) and float(draws.abs().max()) <= 1.0
+    for e, c in ((0, 0), (4, 17), (8, 63)):
+        L.injected_eps = eps[:, c, :].contiguous()
+        one = L.action_piid_sample_batch(hists, eval=False, rtg=2.0)
+        assert torch.equal(one[e], draws[e, c])
+    L.injected_eps = eps[:, 0, :].contiguous()
+    assert torch.equal(L.action_piid_sample_batch(hists, eval=True, rtg=2.0), ev)
+    # on-device noise: atanh(draw) = mu + std * z with z ~ N(0, 1) per (environment, draw)
+    L.injected_eps = None
+    ev2, d2 = L.action_piid_draws_batch(hists, 4096, rtg=2.0)
+    assert torch.equal(ev2, ev)
+    z = torch.atanh(d2.double().clamp(-0.9999999, 0.9999999))
+    zs = (z - z.mean(1, keepdim=True)) / z.std(1, keepdim=True)
+    assert abs(float((zs ** 3).mean())) < 0.1 and abs(float((zs ** 4).mean()) - 3.0) < 0.3
+    np.testing.assert_allclose(torch.tanh(z.mean(1)).cpu().numpy(), ev.double().cpu().numpy(), atol=0.05)
+    assert not torch.equal(d2[0, 0], d2[0, 1]) and not torch.equal(d2[0, 0], d2[1, 0])
+    _, d3 = L.action_piid_draws_batch(hists, 4096, rtg=2.0)
+    assert not torch.equal(d3, d2)  # the plan counter advances the Philox key
