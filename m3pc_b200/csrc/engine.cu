@@ -126,6 +126,7 @@ struct m3pc_engine {
   DevBuf X, XS, Y, Y2, QKV, QSEL, ATT, HID, ENC;
   DevBuf fb_xd, fb_bar;  // fused B = 1 path: decoder-embedding scratch, grid-barrier state
   bool use_fused_b1 = true;
+  bool restrict_deep = true;  // decoders with > 1 layer: last layer on the consumed rows only (M3PC_DEC_FULL=1 disables)
   bool use_mega = false;  // encoder megakernel: measured slower than the per-op path at <= 1024 rows per chunk; M3PC_MEGA=1 enables
   // planner buffers
   DevBuf p1_mu, p1_std, cand, pred_states, pred_rewards, pred_returns, sa, qa, qb1, qb2, qvals, J, filled, e_mu, e_std;
@@ -675,41 +676,35 @@ int decode_full(m3pc_engine* e, const FwdIO& io, const void* enc_out, const int*
   return heads(e, io, need, e->Y.p, e->Y2.p, b0, Bc, st);
 }
 
-// Single-layer decoder restricted to the rows the caller consumes.  Identical results to decode_full for those rows:
-//   * keys / values still cover all 4T tokens, but the mask-token rows are batch-constant, so their K/V (and Q) come from the
-//     table built once at finalize (const_qkv) and only the kept tokens' K/V are projected per batch row;
-//   * queries, out-projection, MLP, norms and heads run on the needed tokens only.
-int decode_restricted(m3pc_engine* e, const FwdIO& io, const void* enc_out, const int* dec_src, int S, const NeedSet& need, int b0, int Bc,
-                      cudaStream_t st) {
+// Last decoder layer restricted to the rows the caller consumes.  Identical results to the full layer for those rows:
+//   * keys / values still cover all 4T tokens; queries, out-projection, MLP, norms and heads run on the needed tokens only;
+//   * `src[j]` names the row block of X / Y (layer input and its LayerNorm) that holds decoder token j, or -1 for a token
+//     whose layer input is batch-constant (single-layer decoder: mask-token rows) -- its Q / K / V come from the table built
+//     once at finalize (const_qkv) and only the other tokens' K / V are projected per batch row.
+// Expects X[0 : S*Bc) = layer input and Y = LN1(X) on entry.
+int restricted_last_layer(m3pc_engine* e, const FwdIO& io, const LayerW& w, const int* src, int S, const NeedSet& need, int b0, int Bc,
+                          cudaStream_t st) {
   const int D = e->D, T = e->T, F = e->F;
   const size_t ab = act_bytes(e);
-  const LayerW& w = e->dec.layers[0];
-  // (a) decoder embedding of the kept tokens, compact (encoder order) -> X[0 : S*Bc)
-  M3PC_TRY(decoder_embed(e, enc_out, dec_src, Bc, true, st));
-  // (b) LN1 -> Y
-  LnParams ln{};
-  ln.x = e->X.as<float>();
-  ln.rows = S * Bc;
-  ln.rows_per_group = Bc;
-  ln.g1 = w.n1_w;
-  ln.b1 = w.n1_b;
-  ln.y1 = e->Y.p;
-  M3PC_TRY(launch_layernorm(ln, D, e->bf16, st));
-  // (c) K, V of the kept tokens: rows D..3D of in_proj -> QKV as (S*Bc, 2D)
+  // (c) K, V of the per-batch tokens: rows D..3D of in_proj -> QKV as (S*Bc, 2D)
   GemmEpilogue ge;
   ge.bias = w.in_b + D;
   GemmJob kvq[MAX_TOK + 1];
   int nkvq = 0;
   kvq[nkvq++] = GemmJob{e->Y.p, w.in_w + static_cast<size_t>(D) * D, e->bf16 ? w.in_w16 + static_cast<size_t>(D) * D : nullptr, e->QKV.p, S * Bc, 2 * D, D, ge};
-  // (d) Q of needed tokens that are kept (per-batch) tokens -> QSEL row block qi (same launch as the K/V projection)
-  for (int qi = 0; qi < need.n; ++qi) {
-    const int src = dec_src[need.tok[qi]];
-    if (src < 0) continue;
+  // (d) Q of needed per-batch tokens -> QSEL row block qi (same launch as the K/V projection); runs of needed tokens whose
+  //     source row blocks are consecutive share one problem
+  for (int qi = 0; qi < need.n;) {
+    const int s0 = src[need.tok[qi]];
+    if (s0 < 0) { ++qi; continue; }
+    int len = 1;
+    while (qi + len < need.n && src[need.tok[qi + len]] == s0 + len) ++len;
     GemmEpilogue gq;
     gq.bias = w.in_b;
-    const char* a = reinterpret_cast<const char*>(e->Y.p) + static_cast<size_t>(src) * Bc * D * ab;
+    const char* a = reinterpret_cast<const char*>(e->Y.p) + static_cast<size_t>(s0) * Bc * D * ab;
     char* c = reinterpret_cast<char*>(e->QSEL.p) + static_cast<size_t>(qi) * Bc * D * ab;
-    kvq[nkvq++] = GemmJob{a, w.in_w, w.in_w16, c, Bc, D, D, gq};
+    kvq[nkvq++] = GemmJob{a, w.in_w, w.in_w16, c, len * Bc, D, D, gq};
+    qi += len;
   }
   M3PC_TRY(gemm_group(e, kvq, nkvq, st));
   // (e) attention: needed queries x all 4T keys
@@ -722,17 +717,17 @@ int decode_restricted(m3pc_engine* e, const FwdIO& io, const void* enc_out, cons
   const char* cq = reinterpret_cast<const char*>(e->const_qkv.p);
   for (int qi = 0; qi < need.n; ++qi) {
     const int j = need.tok[qi];
-    if (dec_src[j] < 0)
+    if (src[j] < 0)
       ap.q[qi] = AttnTok{cq + static_cast<size_t>(j) * 3 * D * ab, 0};
     else
       ap.q[qi] = AttnTok{reinterpret_cast<const char*>(e->QSEL.p) + static_cast<size_t>(qi) * Bc * D * ab, D};
   }
   for (int j = 0; j < 4 * T; ++j) {
-    if (dec_src[j] < 0) {
+    if (src[j] < 0) {
       ap.k[j] = AttnTok{cq + (static_cast<size_t>(j) * 3 * D + D) * ab, 0};
       ap.v[j] = AttnTok{cq + (static_cast<size_t>(j) * 3 * D + 2 * D) * ab, 0};
     } else {
-      const char* row = reinterpret_cast<const char*>(e->QKV.p) + static_cast<size_t>(dec_src[j]) * Bc * 2 * D * ab;
+      const char* row = reinterpret_cast<const char*>(e->QKV.p) + static_cast<size_t>(src[j]) * Bc * 2 * D * ab;
       ap.k[j] = AttnTok{row, 2 * D};
       ap.v[j] = AttnTok{row + D * ab, 2 * D};
     }
@@ -743,11 +738,11 @@ int decode_restricted(m3pc_engine* e, const FwdIO& io, const void* enc_out, cons
   fp.B = Bc;
   for (int qi = 0; qi < need.n; ++qi) {
     const int j = need.tok[qi];
-    if (dec_src[j] < 0) {
+    if (src[j] < 0) {
       fp.row[fp.n] = e->dec_maskrow + static_cast<size_t>(j) * D;
       fp.bstride[fp.n] = 0;
     } else {
-      fp.row[fp.n] = e->X.as<float>() + static_cast<size_t>(dec_src[j]) * Bc * D;
+      fp.row[fp.n] = e->X.as<float>() + static_cast<size_t>(src[j]) * Bc * D;
       fp.bstride[fp.n] = D;
     }
     fp.tok[fp.n++] = qi;
@@ -759,7 +754,7 @@ int decode_restricted(m3pc_engine* e, const FwdIO& io, const void* enc_out, cons
   ge.flags = EPI_RESIDUAL;
   M3PC_TRY(gemm(e, e->ATT.p, w.out_w, w.out_w16, e->XS.p, rows, D, D, ge, st));
   // (g) MLP
-  ln = LnParams{};
+  LnParams ln{};
   ln.x = e->XS.as<float>();
   ln.rows = rows;
   ln.rows_per_group = Bc;
@@ -778,6 +773,57 @@ int decode_restricted(m3pc_engine* e, const FwdIO& io, const void* enc_out, cons
   // (h) norms + heads
   M3PC_TRY(final_norms(e, e->XS.as<float>(), need.n, need.tok, Bc, st));
   return heads(e, io, need, e->Y.p, e->Y2.p, b0, Bc, st);
+}
+
+// Single-layer decoder: the masked tokens' layer input is batch-constant, so only the kept tokens are embedded (compact,
+// encoder order) and the rest comes from the constant table.
+int decode_restricted(m3pc_engine* e, const FwdIO& io, const void* enc_out, const int* dec_src, int S, const NeedSet& need, int b0, int Bc,
+                      cudaStream_t st) {
+  const LayerW& w = e->dec.layers[0];
+  // (a) decoder embedding of the kept tokens, compact (encoder order) -> X[0 : S*Bc)
+  M3PC_TRY(decoder_embed(e, enc_out, dec_src, Bc, true, st));
+  // (b) LN1 -> Y
+  LnParams ln{};
+  ln.x = e->X.as<float>();
+  ln.rows = S * Bc;
+  ln.rows_per_group = Bc;
+  ln.g1 = w.n1_w;
+  ln.b1 = w.n1_b;
+  ln.y1 = e->Y.p;
+  M3PC_TRY(launch_layernorm(ln, e->D, e->bf16, st));
+  return restricted_last_layer(e, io, w, dec_src, S, need, b0, Bc, st);
+}
+
+// Deeper decoders: layers 0 .. Ld-2 run on all 4T rows (after the first layer no row is batch-constant any more), the last
+// layer only on the rows the caller consumes (mtm_model.py:663-716 computes every row of every layer).
+int decode_deep_restricted(m3pc_engine* e, const FwdIO& io, const void* enc_out, const int* dec_src, const NeedSet& need, int b0, int Bc,
+                           cudaStream_t st) {
+  const int D = e->D, T = e->T, Sd = 4 * T;
+  FillParams fp{};
+  fp.B = Bc;
+  for (int j = 0; j < Sd; ++j)
+    if (dec_src[j] < 0) {
+      fp.row[fp.n] = e->dec_maskrow + static_cast<size_t>(j) * D;
+      fp.bstride[fp.n] = 0;
+      fp.tok[fp.n] = j;
+      ++fp.n;
+    }
+  M3PC_TRY(launch_fill_rows(fp, D, e->X.as<float>(), st));
+  M3PC_TRY(decoder_embed(e, enc_out, dec_src, Bc, false, st));
+  LnParams ln{};
+  ln.x = e->X.as<float>();
+  ln.rows = Sd * Bc;
+  ln.rows_per_group = Bc;
+  ln.y1 = e->Y.p;
+  for (int l = 0; l < e->Ld; ++l) {
+    ln.g1 = e->dec.layers[l].n1_w;
+    ln.b1 = e->dec.layers[l].n1_b;
+    M3PC_TRY(launch_layernorm(ln, D, e->bf16, st));
+    if (l + 1 < e->Ld) M3PC_TRY(block(e, e->dec.layers[l], Bc, Sd, st));
+  }
+  int ident[MAX_TOK];
+  for (int j = 0; j < Sd; ++j) ident[j] = j;
+  return restricted_last_layer(e, io, e->dec.layers[e->Ld - 1], ident, Sd, need, b0, Bc, st);
 }
 
 int forward_chunk(m3pc_engine* e, const FwdIO& io, int b0, int Bc, cudaStream_t st) {
@@ -950,6 +996,7 @@ int forward_chunk(m3pc_engine* e, const FwdIO& io, int b0, int Bc, cudaStream_t 
 
   if (need.n == 0) return M3PC_OK;
   if (e->Ld == 1 && need.n < 4 * T) return decode_restricted(e, io, enc_out, dec_src, S, need, b0, Bc, st);
+  if (e->Ld > 1 && need.n < 4 * T && e->restrict_deep) return decode_deep_restricted(e, io, enc_out, dec_src, need, b0, Bc, st);
   return decode_full(e, io, enc_out, dec_src, need, b0, Bc, st);
 }
 
@@ -1278,6 +1325,7 @@ int create(m3pc_handle_t* out, const m3pc_config_t* cfg) {
   M3PC_TRY(e->fb_bar.alloc(16));
   M3PC_CHECK_CUDA(cudaMemset(e->fb_bar.p, 0, 16));
   if (const char* g = getenv("M3PC_NO_FUSED_B1")) e->use_fused_b1 = !(g[0] == '1');
+  if (const char* g = getenv("M3PC_DEC_FULL")) e->restrict_deep = !(g[0] == '1');
   if (const char* g = getenv("M3PC_MEGA")) e->use_mega = g[0] == '1';
   if (const char* g = getenv("M3PC_NO_GRAPHS")) e->use_graphs = !(g[0] == '1');
   if (const char* g = getenv("M3PC_NO_PDL")) g_use_pdl = !(g[0] == '1');

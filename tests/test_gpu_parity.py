@@ -223,11 +223,11 @@ def test_forward_scaled_model_bf16():
 
 
 # ------------------------------------------------------------------------------------------------ planners
-def _learner(env, guidance, n_cand, temperature, precision, chunk=0, cls=None, **kw):
+def _learner(env, guidance, n_cand, temperature, precision, chunk=0, cls=None, scaled=False, **kw):
     from m3pc_b200.learner import Learner
     from m3pc_b200.mtm_model import omtmConfig
     from m3pc_b200.tokenizers import manager_from_stats
-    shape = syn.shipped_shape(env)
+    shape = syn.scaled_shape(env) if scaled else syn.shipped_shape(env)
     cfg = SimpleNamespace(traj_length=shape.traj_length, device="cuda", action_samples=n_cand, discount=0.99, temperature=temperature,
                           horizon=4, plan_guidance=guidance, lmbda=0.6)
     mcfg = omtmConfig(n_embd=shape.n_embd, n_head=shape.n_head, n_enc_layer=shape.n_enc_layer, n_dec_layer=shape.n_dec_layer, dropout=0.1,
@@ -408,6 +408,42 @@ def test_philox_noise_is_shard_invariant_and_seeded():
     z = torch.atanh(c.double().clamp(-0.999999, 0.999999))   # tanh^-1 recovers mu + std * eps: check eps ~ N(0,1) per (t, a)
     zs = (z - z.mean(0)) / z.std(0)
     assert abs(float(zs.mean())) < 0.05 and abs(float((zs ** 2).mean()) - 1.0) < 0.05 and abs(float((zs ** 3).mean())) < 0.3
+
+
+# ------------------------------------------------------------------------------------------------ deeper decoders
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_plan_scaled_model_last_decoder_layer_restricted(precision, monkeypatch):
+    """BASELINE.json config 5 (D=1024, 8 heads, 4+2 layers, T=16, h=8): with more than one decoder layer only the LAST layer
+    is restricted to the consumed rows.  Checked against the float64 oracle (which computes every row of every layer) and
+    against the same engine with the restriction switched off (M3PC_DEC_FULL=1)."""
+    from oracle import planner_oracle as po
+    N, temp = 24, 0.01
+    shape, L = _learner("hopper", "rtg_guiding", N, temp, precision, scaled=True)
+    L.cfg.horizon = 8
+    T, A, h = shape.traj_length, shape.act_dim, 8
+    hist = syn.make_history(shape, seed=9, path_length=50)
+    rs = np.random.RandomState(3)
+    eps, q = torch.from_numpy(rs.randn(N, 1, T, 1, A)), torch.from_numpy(rs.exponential(1.0, N))
+    noise = (eps[:, 0, T - h:, 0, :].float().contiguous().cuda(), q.float().cuda())
+    L.injected_noise, L.debug_plans = noise, True
+    ev = L.action_sample(hist, plan=True, eval=True, rtg=3.0).clone()
+    J = L.last_plan_debug["expect_return"].double().cpu()
+    assert L.mtm.sync_engine().last_launch_count() > 0
+    P = po.from_synthetic(shape, syn.make_state_dict(shape, 0), syn.make_tokenizer_stats(shape, 1), dtype=torch.float64, action_samples=N,
+                          temperature=temp, plan_guidance="rtg_guiding", horizon=8)
+    _, ref = P.action_sample(hist, plan=True, eval=True, rtg=3.0, eps=eps, q=q)
+    tol = 2 * TOL[precision]  # twice the layers of the shipped model
+    assert float((J - ref["expect_return"]).abs().max()) <= tol * max(1.0, float(ref["expect_return"].abs().max()))
+    assert rel(ev, ref["eval_action"]) < (2e-4 if precision == "fp32" else 4e-2)
+    n_restricted = L.mtm.sync_engine().last_launch_count()
+    monkeypatch.setenv("M3PC_DEC_FULL", "1")
+    _, Lf = _learner("hopper", "rtg_guiding", N, temp, precision, scaled=True)
+    Lf.cfg.horizon = 8
+    Lf.injected_noise, Lf.debug_plans = noise, True
+    Lf.action_sample(hist, plan=True, eval=True, rtg=3.0)
+    Jf = Lf.last_plan_debug["expect_return"].double().cpu()
+    assert Lf.mtm.sync_engine().last_launch_count() != n_restricted  # the switch really selects the other path
+    assert float((J - Jf).abs().max()) <= (1e-4 if precision == "fp32" else TOL["bf16"]) * max(1.0, float(Jf.abs().max()))
 
 
 # ------------------------------------------------------------------------------------------------ E lock-step environments per plan
