@@ -23,6 +23,11 @@ constexpr int HD = 128;       // head dim
 constexpr int QS = HD + 1;    // padded row stride (floats) for conflict-free row-parallel reads
 constexpr int ATT_THREADS = 128;
 
+// element offset of batch row b in a token's source (AttnTok)
+__device__ __forceinline__ size_t tok_off(const AttnTok& t, int b) {
+  return static_cast<size_t>(t.bdiv > 0 ? b / t.bdiv : b) * t.bstride;
+}
+
 // ------------------------------------------------------------------------------------------------ fp32 path
 __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __grid_constant__ AttnParams p) {
   PDL_PROLOGUE();
@@ -37,16 +42,16 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __grid_con
 
   for (int idx = tid; idx < n_q * (HD / 4); idx += ATT_THREADS) {
     const int i = idx / (HD / 4), c = (idx % (HD / 4)) * 4;
-    const float4 v = ld4(reinterpret_cast<const float*>(p.q[i].ptr) + static_cast<size_t>(b) * p.q[i].bstride + h * HD + c);
+    const float4 v = ld4(reinterpret_cast<const float*>(p.q[i].ptr) + tok_off(p.q[i], b) + h * HD + c);
     float* d = Qs + i * QS + c;
     d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
   }
   for (int idx = tid; idx < S * (HD / 4); idx += ATT_THREADS) {
     const int j = idx / (HD / 4), c = (idx % (HD / 4)) * 4;
-    const float4 kv = ld4(reinterpret_cast<const float*>(p.k[j].ptr) + static_cast<size_t>(b) * p.k[j].bstride + h * HD + c);
+    const float4 kv = ld4(reinterpret_cast<const float*>(p.k[j].ptr) + tok_off(p.k[j], b) + h * HD + c);
     float* d = Ks + j * QS + c;
     d[0] = kv.x; d[1] = kv.y; d[2] = kv.z; d[3] = kv.w;
-    *reinterpret_cast<float4*>(Vs + j * HD + c) = ld4(reinterpret_cast<const float*>(p.v[j].ptr) + static_cast<size_t>(b) * p.v[j].bstride + h * HD + c);
+    *reinterpret_cast<float4*>(Vs + j * HD + c) = ld4(reinterpret_cast<const float*>(p.v[j].ptr) + tok_off(p.v[j], b) + h * HD + c);
   }
   __syncthreads();
 
@@ -155,7 +160,7 @@ __global__ void __launch_bounds__(MMA_WARPS * 32) attention_mma_kernel(const __g
   for (int idx = lane; idx < QP * 16; idx += 32) {
     const int r = idx >> 4, c = idx & 15;
     if (r < n_q)
-      cp_async16(uQ + swz(r, c), reinterpret_cast<const __nv_bfloat16*>(p.q[r].ptr) + static_cast<size_t>(b) * p.q[r].bstride + h * HD + c * 8);
+      cp_async16(uQ + swz(r, c), reinterpret_cast<const __nv_bfloat16*>(p.q[r].ptr) + tok_off(p.q[r], b) + h * HD + c * 8);
     else
       *reinterpret_cast<uint4*>(sQ + swz(r, c)) = make_uint4(0, 0, 0, 0);
   }
@@ -163,8 +168,8 @@ __global__ void __launch_bounds__(MMA_WARPS * 32) attention_mma_kernel(const __g
     const int r = idx >> 4, c = idx & 15;
     const uint32_t off = swz(r, c);
     if (r < S) {
-      cp_async16(uK + off, reinterpret_cast<const __nv_bfloat16*>(p.k[r].ptr) + static_cast<size_t>(b) * p.k[r].bstride + h * HD + c * 8);
-      cp_async16(uV + off, reinterpret_cast<const __nv_bfloat16*>(p.v[r].ptr) + static_cast<size_t>(b) * p.v[r].bstride + h * HD + c * 8);
+      cp_async16(uK + off, reinterpret_cast<const __nv_bfloat16*>(p.k[r].ptr) + tok_off(p.k[r], b) + h * HD + c * 8);
+      cp_async16(uV + off, reinterpret_cast<const __nv_bfloat16*>(p.v[r].ptr) + tok_off(p.v[r], b) + h * HD + c * 8);
     } else {
       *reinterpret_cast<uint4*>(sK + off) = make_uint4(0, 0, 0, 0);
       *reinterpret_cast<uint4*>(sV + off) = make_uint4(0, 0, 0, 0);

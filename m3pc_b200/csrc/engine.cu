@@ -26,6 +26,8 @@ namespace {
 
 const char* kMod[4] = {"states", "actions", "rewards", "returns"};
 
+constexpr int TAB_ROWS = 4096;  // capacity (token x group rows) of the shared-history tables
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -124,6 +126,8 @@ struct m3pc_engine {
 
   // workspaces (per chunk)
   DevBuf X, XS, Y, Y2, QKV, QSEL, ATT, HID, ENC;
+  DevBuf XT, YT, QKVT;  // shared-history tables of the first encoder block (TAB_ROWS rows)
+  bool dedupe_history = true;  // M3PC_NO_DEDUPE=1 disables
   DevBuf fb_xd, fb_bar;  // fused B = 1 path: decoder-embedding scratch, grid-barrier state
   bool use_fused_b1 = true;
   bool restrict_deep = true;  // decoders with > 1 layer: last layer on the consumed rows only (M3PC_DEC_FULL=1 disables)
@@ -514,17 +518,9 @@ int gemm_group(m3pc_engine* e, const GemmJob* jobs, int n, cudaStream_t st) {
   return M3PC_OK;
 }
 
-// one pre-LN transformer block on `rows` = S * Bc token-major rows; expects Y = LN1(X) on entry
-int block(m3pc_engine* e, const LayerW& w, int Bc, int S, cudaStream_t st) {
-  const int D = e->D, F = e->F, rows = S * Bc;
-  GemmEpilogue ep;
-  ep.bias = w.in_b;
-  M3PC_TRY(gemm(e, e->Y.p, w.in_w, w.in_w16, e->QKV.p, rows, 3 * D, D, ep, st));
-  M3PC_TRY(launch_attention(e->QKV.p, e->ATT.p, Bc, S, e->H, e->bf16, st));
-  ep = GemmEpilogue{};
-  ep.bias = w.out_b;
-  ep.flags = EPI_RESIDUAL;
-  M3PC_TRY(gemm(e, e->ATT.p, w.out_w, w.out_w16, e->X.p, rows, D, D, ep, st));
+// second half of a pre-LN transformer block: X += MLP(LN2(X)) on `rows` token-major rows
+int mlp_half(m3pc_engine* e, const LayerW& w, int rows, cudaStream_t st) {
+  const int D = e->D, F = e->F;
   LnParams ln{};
   ln.x = e->X.as<float>();
   ln.rows = rows;
@@ -533,7 +529,7 @@ int block(m3pc_engine* e, const LayerW& w, int Bc, int S, cudaStream_t st) {
   ln.y1 = e->Y.p;
   ln.rows_per_group = 1;
   M3PC_TRY(launch_layernorm(ln, D, e->bf16, st));
-  ep = GemmEpilogue{};
+  GemmEpilogue ep;
   ep.bias = w.l1_b;
   ep.flags = EPI_GELU;
   M3PC_TRY(gemm(e, e->Y.p, w.l1_w, w.l1_w16, e->HID.p, rows, F, D, ep, st));
@@ -542,6 +538,66 @@ int block(m3pc_engine* e, const LayerW& w, int Bc, int S, cudaStream_t st) {
   ep.flags = EPI_RESIDUAL;
   M3PC_TRY(gemm(e, e->HID.p, w.l2_w, w.l2_w16, e->X.p, rows, D, F, ep, st));
   return M3PC_OK;
+}
+
+// one pre-LN transformer block on `rows` = S * Bc token-major rows; expects Y = LN1(X) on entry
+int block(m3pc_engine* e, const LayerW& w, int Bc, int S, cudaStream_t st) {
+  const int D = e->D, rows = S * Bc;
+  GemmEpilogue ep;
+  ep.bias = w.in_b;
+  M3PC_TRY(gemm(e, e->Y.p, w.in_w, w.in_w16, e->QKV.p, rows, 3 * D, D, ep, st));
+  M3PC_TRY(launch_attention(e->QKV.p, e->ATT.p, Bc, S, e->H, e->bf16, st));
+  ep = GemmEpilogue{};
+  ep.bias = w.out_b;
+  ep.flags = EPI_RESIDUAL;
+  M3PC_TRY(gemm(e, e->ATT.p, w.out_w, w.out_w16, e->X.p, rows, D, D, ep, st));
+  return mlp_half(e, w, rows, st);
+}
+
+// First encoder block when the first `n_sh` tokens are history tokens shared by groups of `grp` batch rows (the candidates of
+// one environment): their embedding, LayerNorm and Q / K / V are computed once per group (tables XT / YT / QKVT, row =
+// token * nG + group) instead of once per candidate.  The attention output differs per candidate, so from the
+// out-projection on every row exists; for the shared tokens the residual is the table row, added in the epilogue.
+// Expects: XT / YT = embedding / LN1 of the shared tokens, X / Y rows [n_sh*Bc, S*Bc) = the per-candidate tokens.
+int block_shared_history(m3pc_engine* e, const LayerW& w, int Bc, int S, int n_sh, int grp, cudaStream_t st) {
+  const int D = e->D, nG = Bc / grp;
+  const size_t ab = act_bytes(e);
+  const size_t off = static_cast<size_t>(n_sh) * Bc;  // first per-candidate row
+  GemmJob qkv[2];
+  GemmEpilogue ep;
+  ep.bias = w.in_b;
+  qkv[0] = GemmJob{e->YT.p, w.in_w, w.in_w16, e->QKVT.p, n_sh * nG, 3 * D, D, ep};
+  qkv[1] = GemmJob{reinterpret_cast<const char*>(e->Y.p) + off * D * ab, w.in_w, w.in_w16, reinterpret_cast<char*>(e->QKV.p) + off * 3 * D * ab,
+                   (S - n_sh) * Bc, 3 * D, D, ep};
+  M3PC_TRY(gemm_group(e, qkv, 2, st));
+  AttnParams ap{};
+  ap.n_q = ap.n_kv = S;
+  ap.B = Bc;
+  ap.n_head = e->H;
+  ap.out = e->ATT.p;
+  for (int s = 0; s < S; ++s) {
+    const bool sh = s < n_sh;
+    const char* row = sh ? reinterpret_cast<const char*>(e->QKVT.p) + static_cast<size_t>(s) * nG * 3 * D * ab
+                         : reinterpret_cast<const char*>(e->QKV.p) + static_cast<size_t>(s) * Bc * 3 * D * ab;
+    const int bdiv = sh ? grp : 0;
+    ap.q[s] = AttnTok{row, 3 * D, bdiv};
+    ap.k[s] = AttnTok{row + D * ab, 3 * D, bdiv};
+    ap.v[s] = AttnTok{row + 2 * D * ab, 3 * D, bdiv};
+  }
+  M3PC_TRY(launch_attention_gather(ap, e->bf16, st));
+  GemmJob op[2];
+  GemmEpilogue es;  // shared tokens: X = table[token, group] + att W^T + b (plain store; row / grp = token * nG + group)
+  es.bias = w.out_b;
+  es.table = e->XT.as<float>();
+  es.rows_per_group = grp;
+  es.flags = EPI_OUT_F32 | EPI_ROWTABLE;
+  op[0] = GemmJob{e->ATT.p, w.out_w, w.out_w16, e->X.p, static_cast<int>(off), D, D, es};
+  GemmEpilogue er;  // per-candidate tokens: X += att W^T + b
+  er.bias = w.out_b;
+  er.flags = EPI_RESIDUAL;
+  op[1] = GemmJob{reinterpret_cast<const char*>(e->ATT.p) + off * D * ab, w.out_w, w.out_w16, e->X.as<float>() + off * D, (S - n_sh) * Bc, D, D, er};
+  M3PC_TRY(gemm_group(e, op, 2, st));
+  return mlp_half(e, w, S * Bc, st);
 }
 
 struct NeedSet {
@@ -954,8 +1010,42 @@ int forward_chunk(m3pc_engine* e, const FwdIO& io, int b0, int Bc, cudaStream_t 
   const bool mega = e->bf16 && e->use_mega && D == 512 && cpt > 0 && e->Le >= 1 && e->Le <= 4 && Bc >= 32 &&
                     static_cast<size_t>(ceil_div(ceil_div(Bc, cpt), 2)) * 256 <= static_cast<size_t>(4) * T * e->chunk + 128;
   ep.cpt = mega ? cpt : 0;
-  M3PC_TRY(launch_embed(ep, D, e->X.as<float>(), e->Y.p, e->bf16, e->Le > 0 ? first.n1_w : e->enc.norm_w,
-                        e->Le > 0 ? first.n1_b : e->enc.norm_b, st));
+  // shared-history analysis: the leading encoder tokens whose source row is shared by whole groups of batch rows (one window
+  // for the whole batch: bstride 0; one window per environment: bdiv rows each) -- the chunk must hold whole groups
+  int n_sh = 0, grp = 0;
+  if (e->dedupe_history && !mega && e->Le >= 1 && Bc >= 64) {
+    for (int s = 0; s < S; ++s) {
+      const EmbedTok& tk = ep.tok[s];
+      const int g = tk.bdiv > 0 ? tk.bdiv : (tk.bstride == 0 ? Bc : 0);
+      if (g == 0 || (grp != 0 && g != grp)) break;
+      grp = g;
+      ++n_sh;
+    }
+    const bool aligned = grp > 0 && Bc % grp == 0 && (grp == Bc || b0 % grp == 0);
+    if (!aligned || n_sh == S || static_cast<long>(n_sh) * (Bc / std::max(grp, 1)) > TAB_ROWS) n_sh = 0;
+  }
+  if (n_sh > 0) {
+    const int nG = Bc / grp;
+    EmbedParams ea{};  // shared tokens, one row per group
+    ea.n_tok = n_sh;
+    ea.B = nG;
+    for (int s = 0; s < n_sh; ++s) {
+      ea.tok[s] = ep.tok[s];
+      if (ea.tok[s].bdiv > 0) ea.tok[s].src += static_cast<size_t>(b0 / grp) * ea.tok[s].bstride;  // first group of this chunk
+      ea.tok[s].bdiv = 0;
+    }
+    M3PC_TRY(launch_embed(ea, D, e->XT.as<float>(), e->YT.p, e->bf16, first.n1_w, first.n1_b, st));
+    EmbedParams eb{};  // per-candidate tokens, written at their usual rows
+    eb.n_tok = S - n_sh;
+    eb.B = Bc;
+    eb.b0 = b0;
+    for (int s = n_sh; s < S; ++s) eb.tok[s - n_sh] = ep.tok[s];
+    const size_t off = static_cast<size_t>(n_sh) * Bc * D;
+    M3PC_TRY(launch_embed(eb, D, e->X.as<float>() + off, reinterpret_cast<char*>(e->Y.p) + off * ab, e->bf16, first.n1_w, first.n1_b, st));
+  } else {
+    M3PC_TRY(launch_embed(ep, D, e->X.as<float>(), e->Y.p, e->bf16, e->Le > 0 ? first.n1_w : e->enc.norm_w,
+                          e->Le > 0 ? first.n1_b : e->enc.norm_b, st));
+  }
   void* enc_out = e->Le > 0 ? e->ENC.p : e->Y.p;
 
   if (mega) {
@@ -977,7 +1067,10 @@ int forward_chunk(m3pc_engine* e, const FwdIO& io, int b0, int Bc, cudaStream_t 
 
   // ---- encoder stack (mtm_model.py:379-391, 619-644) ----
   for (int l = 0; l < (mega ? 0 : e->Le); ++l) {
-    M3PC_TRY(block(e, e->enc.layers[l], Bc, S, st));
+    if (l == 0 && n_sh > 0)
+      M3PC_TRY(block_shared_history(e, e->enc.layers[0], Bc, S, n_sh, grp, st));
+    else
+      M3PC_TRY(block(e, e->enc.layers[l], Bc, S, st));
     LnParams ln{};
     ln.x = e->X.as<float>();
     ln.rows = S * Bc;
@@ -1300,6 +1393,9 @@ int create(m3pc_handle_t* out, const m3pc_config_t* cfg) {
   M3PC_TRY(e->ATT.alloc(rows * D * ab));
   M3PC_TRY(e->HID.alloc(rows * 4 * D * ab));
   M3PC_TRY(e->ENC.alloc(rows * D * ab));
+  M3PC_TRY(e->XT.alloc(static_cast<size_t>(TAB_ROWS + 128) * D * 4));
+  M3PC_TRY(e->YT.alloc(static_cast<size_t>(TAB_ROWS + 128) * D * ab));
+  M3PC_TRY(e->QKVT.alloc(static_cast<size_t>(TAB_ROWS + 128) * 3 * D * ab));
   for (DevBuf* b : {&e->X, &e->XS, &e->Y, &e->Y2, &e->QKV, &e->QSEL, &e->ATT, &e->HID, &e->ENC})
     M3PC_CHECK_CUDA(cudaMemset(b->p, 0, b->bytes));
   const size_t N = cfg->max_batch, T = e->T;
@@ -1326,6 +1422,7 @@ int create(m3pc_handle_t* out, const m3pc_config_t* cfg) {
   M3PC_CHECK_CUDA(cudaMemset(e->fb_bar.p, 0, 16));
   if (const char* g = getenv("M3PC_NO_FUSED_B1")) e->use_fused_b1 = !(g[0] == '1');
   if (const char* g = getenv("M3PC_DEC_FULL")) e->restrict_deep = !(g[0] == '1');
+  if (const char* g = getenv("M3PC_NO_DEDUPE")) e->dedupe_history = !(g[0] == '1');
   if (const char* g = getenv("M3PC_MEGA")) e->use_mega = g[0] == '1';
   if (const char* g = getenv("M3PC_NO_GRAPHS")) e->use_graphs = !(g[0] == '1');
   if (const char* g = getenv("M3PC_NO_PDL")) g_use_pdl = !(g[0] == '1');

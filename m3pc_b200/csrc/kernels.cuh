@@ -139,6 +139,8 @@ int launch_rowdot(const RowDotParams& p, int D, bool y_bf16, cudaStream_t st);
 struct AttnTok {
   const void* ptr;
   int bstride;
+  int bdiv;  // > 0: the row of batch row b is ptr + (b / bdiv) * bstride -- one row per group of bdiv batch rows (history tokens of
+             // an environment, shared by all of its candidates); 0: ptr + b * bstride
 };
 struct AttnParams {
   AttnTok q[MAX_TOK], k[MAX_TOK], v[MAX_TOK];
