@@ -148,49 +148,81 @@ __global__ void __launch_bounds__(256) fill_rows_kernel(const __grid_constant__ 
   }
 }
 
-template <int NJ, typename AT>
+// A warp owns R consecutive rows: every weight vector it loads is used for R dot products (at R = 1 the kernel re-read the
+// whole (d_out, D) weight matrix through L1 for every row, which bounded it at ~10 % of the HBM rate its inputs need).
+// Per row the arithmetic (per-lane FMA chain, then warp_sum) is the same for every R, so results do not depend on R.
+template <int NJ, typename AT, int R>
 __global__ void __launch_bounds__(256) rowdot_kernel(const __grid_constant__ RowDotParams p) {
   PDL_PROLOGUE();
   constexpr int D = NJ * 128;
   const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);  // r = t * B + b
-  if (r >= p.n_t * p.B) return;
-  const int t = r / p.B, b = r - t * p.B;
-  const AT* yrow = reinterpret_cast<const AT*>(p.y) + (static_cast<size_t>(p.tok0) * p.B + r) * D;
-  float4 v[NJ];
+  const int n_rows = p.n_t * p.B;
+  const int r0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * R;  // r = t * B + b
+  if (r0 >= n_rows) return;
+  float4 v[R][NJ];
 #pragma unroll
-  for (int j = 0; j < NJ; ++j) v[j] = ld4(yrow + j * 128 + lane * 4);
-  const size_t obase = (static_cast<size_t>(b) * p.T_out + (p.t_out0 + t)) * p.d_out;
+  for (int i = 0; i < R; ++i) {
+    const int r = min(r0 + i, n_rows - 1);  // tail rows repeat the last row; they are not stored
+    const AT* yrow = reinterpret_cast<const AT*>(p.y) + (static_cast<size_t>(p.tok0) * p.B + r) * D;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) v[i][j] = ld4(yrow + j * 128 + lane * 4);
+  }
   for (int o0 = 0; o0 < p.d_out; o0 += 32) {
-    float mine = 0.f, mine2 = 0.f;
+    float mine[R], mine2[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) mine[i] = mine2[i] = 0.f;
     const int o_end = min(p.d_out, o0 + 32);
-#pragma unroll 4
+#pragma unroll 2
     for (int o = o0; o < o_end; ++o) {
-      float s = 0.f;
+      float s[R];
+#pragma unroll
+      for (int i = 0; i < R; ++i) s[i] = 0.f;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const float4 w = __ldg(reinterpret_cast<const float4*>(p.w + static_cast<size_t>(o) * D + j * 128 + lane * 4));
-        s = fmaf(v[j].x, w.x, s); s = fmaf(v[j].y, w.y, s); s = fmaf(v[j].z, w.z, s); s = fmaf(v[j].w, w.w, s);
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          s[i] = fmaf(v[i][j].x, w.x, s[i]); s[i] = fmaf(v[i][j].y, w.y, s[i]); s[i] = fmaf(v[i][j].z, w.z, s[i]); s[i] = fmaf(v[i][j].w, w.w, s[i]);
+        }
       }
-      s = warp_sum(s);
-      if (lane == o - o0) mine = s + __ldg(p.b + o);
+      const float bo = __ldg(p.b + o);
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const float t = warp_sum(s[i]);
+        if (lane == o - o0) mine[i] = t + bo;
+      }
       if (p.w2 != nullptr) {
-        float s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < R; ++i) s[i] = 0.f;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
           const float4 w = __ldg(reinterpret_cast<const float4*>(p.w2 + static_cast<size_t>(o) * D + j * 128 + lane * 4));
-          s2 = fmaf(v[j].x, w.x, s2); s2 = fmaf(v[j].y, w.y, s2); s2 = fmaf(v[j].z, w.z, s2); s2 = fmaf(v[j].w, w.w, s2);
+#pragma unroll
+          for (int i = 0; i < R; ++i) {
+            s[i] = fmaf(v[i][j].x, w.x, s[i]); s[i] = fmaf(v[i][j].y, w.y, s[i]); s[i] = fmaf(v[i][j].z, w.z, s[i]); s[i] = fmaf(v[i][j].w, w.w, s[i]);
+          }
         }
-        s2 = warp_sum(s2);
-        if (lane == o - o0) mine2 = s2 + __ldg(p.b2 + o);
+        const float bo2 = __ldg(p.b2 + o);
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          const float t = warp_sum(s[i]);
+          if (lane == o - o0) mine2[i] = t + bo2;
+        }
       }
     }
     if (o0 + lane < p.d_out) {
-      p.out[obase + o0 + lane] = mine;
-      if (p.w2 != nullptr) {
-        // log_std = -5 + 0.5 * (2 - (-5)) * (tanh(.) + 1); std = exp(log_std)     (mtm_model.py:313-321)
-        const float ls = -5.0f + 3.5f * (tanhf(mine2) + 1.0f);
-        p.out2[obase + o0 + lane] = expf(ls);
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const int r = r0 + i;
+        if (r >= n_rows) break;
+        const int t = r / p.B, b = r - t * p.B;
+        const size_t obase = (static_cast<size_t>(b) * p.T_out + (p.t_out0 + t)) * p.d_out;
+        p.out[obase + o0 + lane] = mine[i];
+        if (p.w2 != nullptr) {
+          // log_std = -5 + 0.5 * (2 - (-5)) * (tanh(.) + 1); std = exp(log_std)     (mtm_model.py:313-321)
+          const float ls = -5.0f + 3.5f * (tanhf(mine2[i]) + 1.0f);
+          p.out2[obase + o0 + lane] = expf(ls);
+        }
       }
     }
   }
@@ -261,13 +293,25 @@ int launch_fill_rows(const FillParams& p, int D, float* x, cudaStream_t st) {
 
 int launch_rowdot(const RowDotParams& p, int D, bool y_bf16, cudaStream_t st) {
   if (p.n_t <= 0) return M3PC_OK;
-  dim3 grid(ceil_div(p.n_t * p.B, 8));
+  const int rows = p.n_t * p.B;
+  const bool wide = rows >= 4096 && D <= 512;  // 4 rows per warp once there are enough rows to fill the SMs (register budget: D <= 512)
+  dim3 grid(ceil_div(rows, 8 * (wide ? 4 : 1)));
   return dispatch_d(D, [&](auto nj) -> int {
     constexpr int NJ = decltype(nj)::value;
+    if constexpr (NJ <= 4) {
+      if (wide) {
+        if (y_bf16)
+          M3PC_CHECK_CUDA(launch_k(rowdot_kernel<NJ, __nv_bfloat16, 4>, dim3(grid), dim3(256), 0, st, p));
+        else
+          M3PC_CHECK_CUDA(launch_k(rowdot_kernel<NJ, float, 4>, dim3(grid), dim3(256), 0, st, p));
+        M3PC_CHECK_LAUNCH();
+        return M3PC_OK;
+      }
+    }
     if (y_bf16)
-      M3PC_CHECK_CUDA(launch_k(rowdot_kernel<NJ, __nv_bfloat16>, dim3(grid), dim3(256), 0, st, p));
+      M3PC_CHECK_CUDA(launch_k(rowdot_kernel<NJ, __nv_bfloat16, 1>, dim3(grid), dim3(256), 0, st, p));
     else
-      M3PC_CHECK_CUDA(launch_k(rowdot_kernel<NJ, float>, dim3(grid), dim3(256), 0, st, p));
+      M3PC_CHECK_CUDA(launch_k(rowdot_kernel<NJ, float, 1>, dim3(grid), dim3(256), 0, st, p));
     M3PC_CHECK_LAUNCH();
     return M3PC_OK;
   });
