@@ -139,6 +139,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ uint32_t swz(int r, int c) { return static_cast<uint32_t>(r * 256 + ((c ^ (r & 7)) << 4)); }
 
 constexpr int MMA_WARPS = 4;  // (b, head) pairs per CTA
+const bool g_attn_shared = getenv("M3PC_ATTN_SHARED") == nullptr || getenv("M3PC_ATTN_SHARED")[0] != '0';  // M3PC_ATTN_SHARED=0: legacy staging
 
 // NTQ = ceil(n_q / 16) query tiles, NTK = ceil(n_kv / 16) key tiles
 template <int NTQ, int NTK>
@@ -268,6 +269,161 @@ __global__ void __launch_bounds__(MMA_WARPS * 32) attention_mma_kernel(const __g
   }
 }
 
+// Variant for the planner's restricted decoder layer: most keys / values are batch-constant mask-token rows (19 of 32 at the
+// shipped sizes).  One CTA works on ONE head for SH_WARPS batch rows: the constant K / V tiles are staged once per CTA and
+// shared by its warps; every warp stages only its own batch row's keys (one query tile).  Key order is [per-batch keys, constant
+// keys] (softmax and P V are invariant to a common permutation of keys and values); each key tile is homogeneous.
+constexpr int SH_WARPS = 8;
+template <int NTB, int NTC>
+__global__ void __launch_bounds__(SH_WARPS * 32) attention_mma_shared_kernel(const __grid_constant__ AttnParams p) {
+  PDL_PROLOGUE();
+  constexpr int NTK = NTB + NTC, BP = NTB * 16, CP = NTC * 16;
+  extern __shared__ __align__(128) uint8_t smem_att[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y;
+  const int b_raw = blockIdx.x * SH_WARPS + warp;
+  const bool live = b_raw < p.B;
+  const int b = live ? b_raw : p.B - 1;  // idle warps shadow the last row (they must reach the barrier) and store nothing
+  const int n_q = p.n_q, n_b = p.n_kv_batch, n_c = p.n_kv - p.n_kv_batch;
+  uint8_t* sKc = smem_att;             // CP x 256 B, shared by the CTA
+  uint8_t* sVc = sKc + CP * 256;
+  uint8_t* sQ = sVc + CP * 256 + static_cast<size_t>(warp) * (16 + 2 * BP) * 256;
+  uint8_t* sKb = sQ + 16 * 256;
+  uint8_t* sVb = sKb + BP * 256;
+  const uint32_t uKc = smem_u32(sKc), uVc = smem_u32(sVc), uQ = smem_u32(sQ), uKb = smem_u32(sKb), uVb = smem_u32(sVb);
+
+  for (int idx = threadIdx.x; idx < CP * 16; idx += SH_WARPS * 32) {  // constant keys / values: whole CTA
+    const int r = idx >> 4, c = idx & 15;
+    const uint32_t off = swz(r, c);
+    if (r < n_c) {
+      cp_async16(uKc + off, reinterpret_cast<const __nv_bfloat16*>(p.k[n_b + r].ptr) + h * HD + c * 8);
+      cp_async16(uVc + off, reinterpret_cast<const __nv_bfloat16*>(p.v[n_b + r].ptr) + h * HD + c * 8);
+    } else {
+      *reinterpret_cast<uint4*>(sKc + off) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(sVc + off) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  for (int idx = lane; idx < 16 * 16; idx += 32) {  // queries of this warp's batch row
+    const int r = idx >> 4, c = idx & 15;
+    if (r < n_q)
+      cp_async16(uQ + swz(r, c), reinterpret_cast<const __nv_bfloat16*>(p.q[r].ptr) + tok_off(p.q[r], b) + h * HD + c * 8);
+    else
+      *reinterpret_cast<uint4*>(sQ + swz(r, c)) = make_uint4(0, 0, 0, 0);
+  }
+  for (int idx = lane; idx < BP * 16; idx += 32) {  // per-batch keys / values
+    const int r = idx >> 4, c = idx & 15;
+    const uint32_t off = swz(r, c);
+    if (r < n_b) {
+      cp_async16(uKb + off, reinterpret_cast<const __nv_bfloat16*>(p.k[r].ptr) + tok_off(p.k[r], b) + h * HD + c * 8);
+      cp_async16(uVb + off, reinterpret_cast<const __nv_bfloat16*>(p.v[r].ptr) + tok_off(p.v[r], b) + h * HD + c * 8);
+    } else {
+      *reinterpret_cast<uint4*>(sKb + off) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(sVb + off) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  const int g = lane >> 2, t = lane & 3;
+  const float sl2 = 0.08838834764831845f * 1.4426950408889634f;  // 1/sqrt(128) * log2(e)
+  // ---- scores = Q K^T : 16 x (BP + CP), fp32 accumulators ----
+  float sc[2 * NTK][4];
+#pragma unroll
+  for (int j = 0; j < 2 * NTK; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < HD / 16; ++kk) {
+    uint32_t a[4];
+    {
+      const int r = (lane & 7) + 8 * ((lane >> 3) & 1), c = 2 * kk + (lane >> 4);
+      ldsm_x4(uQ + swz(r, c), a[0], a[1], a[2], a[3]);
+    }
+#pragma unroll
+    for (int jp = 0; jp < NTK; ++jp) {
+      uint32_t b0, b1, b2, b3;
+      const uint32_t base = jp < NTB ? uKb : uKc;
+      const int r = (jp < NTB ? jp : jp - NTB) * 16 + (lane & 7) + 8 * (lane >> 4), c = 2 * kk + ((lane >> 3) & 1);
+      ldsm_x4(base + swz(r, c), b0, b1, b2, b3);
+      mma_bf16_16816(sc[2 * jp], a, b0, b1);
+      mma_bf16_16816(sc[2 * jp + 1], a, b2, b3);
+    }
+  }
+  // ---- softmax over keys; pad keys of each tile masked ----
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 2 * NTK; ++j) {
+    const int tile = j >> 1;
+    const int cnt = tile < NTB ? n_b - 16 * tile : n_c - 16 * (tile - NTB);  // valid keys in this tile
+    const int key = 8 * (j & 1) + 2 * t;
+    if (key >= cnt) sc[j][0] = sc[j][2] = -INFINITY;
+    if (key + 1 >= cnt) sc[j][1] = sc[j][3] = -INFINITY;
+    m0 = fmaxf(m0, fmaxf(sc[j][0], sc[j][1]));
+    m1 = fmaxf(m1, fmaxf(sc[j][2], sc[j][3]));
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 2 * NTK; ++j) {
+    sc[j][0] = exp2f((sc[j][0] - m0) * sl2); sc[j][1] = exp2f((sc[j][1] - m0) * sl2);
+    sc[j][2] = exp2f((sc[j][2] - m1) * sl2); sc[j][3] = exp2f((sc[j][3] - m1) * sl2);
+    l0 += sc[j][0] + sc[j][1];
+    l1 += sc[j][2] + sc[j][3];
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+
+  // ---- O = P V : 16 x 128 ----
+  float o[HD / 8][4];
+#pragma unroll
+  for (int n = 0; n < HD / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < NTK; ++kk) {
+    uint32_t a[4];
+    a[0] = pack_bf16(sc[2 * kk][0] * inv0, sc[2 * kk][1] * inv0);
+    a[1] = pack_bf16(sc[2 * kk][2] * inv1, sc[2 * kk][3] * inv1);
+    a[2] = pack_bf16(sc[2 * kk + 1][0] * inv0, sc[2 * kk + 1][1] * inv0);
+    a[3] = pack_bf16(sc[2 * kk + 1][2] * inv1, sc[2 * kk + 1][3] * inv1);
+    const uint32_t base = kk < NTB ? uVb : uVc;
+#pragma unroll
+    for (int np = 0; np < HD / 16; ++np) {
+      uint32_t b0, b1, b2, b3;
+      const int r = (kk < NTB ? kk : kk - NTB) * 16 + (lane & 7) + 8 * ((lane >> 3) & 1), c = 2 * np + (lane >> 4);
+      ldsm_x4_t(base + swz(r, c), b0, b1, b2, b3);
+      mma_bf16_16816(o[2 * np], a, b0, b1);
+      mma_bf16_16816(o[2 * np + 1], a, b2, b3);
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int n = 0; n < HD / 8; ++n) {  // stage O into the (now dead) Q rows, same swizzle
+    *reinterpret_cast<uint32_t*>(sQ + swz(g, n) + 4 * t) = pack_bf16(o[n][0], o[n][1]);
+    *reinterpret_cast<uint32_t*>(sQ + swz(g + 8, n) + 4 * t) = pack_bf16(o[n][2], o[n][3]);
+  }
+  __syncwarp();
+  if (!live) return;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+  const int D = p.n_head * HD;
+  for (int idx = lane; idx < n_q * 16; idx += 32) {
+    const int r = idx >> 4, c = idx & 15;
+    *reinterpret_cast<uint4*>(out + (static_cast<size_t>(r) * p.B + b) * D + h * HD + c * 8) = *reinterpret_cast<const uint4*>(sQ + swz(r, c));
+  }
+}
+
+template <int NTB, int NTC>
+int launch_mma_shared(const AttnParams& p, cudaStream_t st) {
+  constexpr int smem = 2 * NTC * 16 * 256 + SH_WARPS * (16 + 2 * NTB * 16) * 256;
+  static bool configured = false;
+  if (!configured) {
+    M3PC_CHECK_CUDA(cudaFuncSetAttribute(attention_mma_shared_kernel<NTB, NTC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  M3PC_CHECK_CUDA(launch_k(attention_mma_shared_kernel<NTB, NTC>, dim3(ceil_div(p.B, SH_WARPS), p.n_head), dim3(SH_WARPS * 32), smem, st, p));
+  M3PC_CHECK_LAUNCH();
+  return M3PC_OK;
+}
+
 template <int NTQ, int NTK>
 int launch_mma(const AttnParams& p, cudaStream_t st) {
   constexpr int smem = MMA_WARPS * (NTQ + 2 * NTK) * 16 * 256;
@@ -296,6 +452,22 @@ int dispatch_q(const AttnParams& p, cudaStream_t st) {
 int launch_attention_gather(const AttnParams& p, bool bf16, cudaStream_t st) {
   M3PC_REQUIRE(p.B > 0 && p.n_q > 0 && p.n_kv > 0 && p.n_q <= MAX_TOK && p.n_kv <= MAX_TOK && p.n_head > 0, "attention: bad shape (<= 64 tokens)");
   if (!bf16) return launch_simple(p, st);
+  if (g_attn_shared && p.n_kv_batch > 0 && p.n_q <= 16 && p.B >= 64) {  // batch keys first, constant keys after (see AttnParams)
+    const int n_c = p.n_kv - p.n_kv_batch, ntb = (p.n_kv_batch + 15) / 16, ntc = (n_c + 15) / 16;
+    bool ok = n_c >= 8 && ntb <= 2 && ntc <= 3;
+    for (int j = 0; j < p.n_kv && ok; ++j)
+      ok = j < p.n_kv_batch ? true : (p.k[j].bstride == 0 && p.v[j].bstride == 0 && p.k[j].bdiv == 0 && p.v[j].bdiv == 0);
+    if (ok) {
+      switch (ntb * 10 + ntc) {
+        case 11: return launch_mma_shared<1, 1>(p, st);
+        case 12: return launch_mma_shared<1, 2>(p, st);
+        case 13: return launch_mma_shared<1, 3>(p, st);
+        case 21: return launch_mma_shared<2, 1>(p, st);
+        case 22: return launch_mma_shared<2, 2>(p, st);
+        default: return launch_mma_shared<2, 3>(p, st);
+      }
+    }
+  }
   switch ((p.n_kv + 15) / 16) {
     case 1: return dispatch_q<1>(p, st);
     case 2: return dispatch_q<2>(p, st);

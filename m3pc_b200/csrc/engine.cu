@@ -679,13 +679,13 @@ int heads(m3pc_engine* e, const FwdIO& io, const NeedSet& need, const void* y1, 
 }
 
 // final decoder norm (-> Y) chained with each head's own LayerNorm (-> Y2), mtm_model.py:428-433
-int final_norms(m3pc_engine* e, const float* x, int n_tok, const int* tok, int Bc, cudaStream_t st) {
+int final_norms(m3pc_engine* e, const float* x, int n_tok, const int* tok, int Bc, cudaStream_t st, bool want_y1 = true) {
   LnParams ln{};
   ln.x = x;
   ln.rows = n_tok * Bc;
   ln.g1 = e->dec.norm_w;
   ln.b1 = e->dec.norm_b;
-  ln.y1 = e->Y.p;
+  ln.y1 = want_y1 ? e->Y.p : nullptr;  // only the actor head reads the final norm itself; the MLP heads read their own LayerNorm of it
   ln.y2 = e->Y2.p;
   ln.rows_per_group = Bc;
   for (int i = 0; i < n_tok; ++i) ln.tok_group[i] = static_cast<unsigned char>(tok[i] / e->T);
@@ -778,16 +778,24 @@ int restricted_last_layer(m3pc_engine* e, const FwdIO& io, const LayerW& w, cons
     else
       ap.q[qi] = AttnTok{reinterpret_cast<const char*>(e->QSEL.p) + static_cast<size_t>(qi) * Bc * D * ab, D};
   }
-  for (int j = 0; j < 4 * T; ++j) {
-    if (src[j] < 0) {
-      ap.k[j] = AttnTok{cq + (static_cast<size_t>(j) * 3 * D + D) * ab, 0};
-      ap.v[j] = AttnTok{cq + (static_cast<size_t>(j) * 3 * D + 2 * D) * ab, 0};
-    } else {
-      const char* row = reinterpret_cast<const char*>(e->QKV.p) + static_cast<size_t>(src[j]) * Bc * 2 * D * ab;
-      ap.k[j] = AttnTok{row, 2 * D};
-      ap.v[j] = AttnTok{row + D * ab, 2 * D};
+  // keys / values: per-batch tokens first, batch-constant tokens after (attention is invariant to the key order; the bf16
+  // kernel stages the constant ones once per CTA)
+  int nk = 0;
+  for (int pass = 0; pass < 2; ++pass)
+    for (int j = 0; j < 4 * T; ++j) {
+      if ((src[j] < 0) != (pass == 1)) continue;
+      if (src[j] < 0) {
+        ap.k[nk] = AttnTok{cq + (static_cast<size_t>(j) * 3 * D + D) * ab, 0};
+        ap.v[nk] = AttnTok{cq + (static_cast<size_t>(j) * 3 * D + 2 * D) * ab, 0};
+      } else {
+        const char* row = reinterpret_cast<const char*>(e->QKV.p) + static_cast<size_t>(src[j]) * Bc * 2 * D * ab;
+        ap.k[nk] = AttnTok{row, 2 * D};
+        ap.v[nk] = AttnTok{row + D * ab, 2 * D};
+      }
+      ++nk;
+      if (pass == 0) ap.n_kv_batch = nk;
     }
-  }
+  if (ap.n_kv_batch == 4 * T) ap.n_kv_batch = 0;  // no constant keys (deeper decoders): plain kernel
   M3PC_TRY(launch_attention_gather(ap, e->bf16, st));
   // (f) residual rows of the needed tokens -> XS, then out-projection accumulates into them
   FillParams fp{};
@@ -827,7 +835,7 @@ int restricted_last_layer(m3pc_engine* e, const FwdIO& io, const LayerW& w, cons
   ge.flags = EPI_RESIDUAL;
   M3PC_TRY(gemm(e, e->HID.p, w.l2_w, w.l2_w16, e->XS.p, rows, D, F, ge, st));
   // (h) norms + heads
-  M3PC_TRY(final_norms(e, e->XS.as<float>(), need.n, need.tok, Bc, st));
+  M3PC_TRY(final_norms(e, e->XS.as<float>(), need.n, need.tok, Bc, st, io.out_mu != nullptr && need.nt[M3PC_ACTIONS] > 0));
   return heads(e, io, need, e->Y.p, e->Y2.p, b0, Bc, st);
 }
 

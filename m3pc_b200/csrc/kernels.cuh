@@ -145,6 +145,8 @@ struct AttnTok {
 struct AttnParams {
   AttnTok q[MAX_TOK], k[MAX_TOK], v[MAX_TOK];
   int n_q, n_kv, B, n_head;
+  int n_kv_batch;  // > 0: keys [0, n_kv_batch) are per-batch rows and keys [n_kv_batch, n_kv) are batch-constant (bstride 0);
+                   // the bf16 kernel then stages the constant keys / values once per CTA instead of once per batch row
   void* out;  // (n_q * B, n_head * 128), row = query token * B + b
 };
 int launch_attention_gather(const AttnParams& p, bool bf16, cudaStream_t st);
