@@ -170,6 +170,22 @@ int m3pc_backward_plan_draws(m3pc_handle_t h, int32_t mode, int32_t n_env, int32
                              const float* win_actions, const float* win_rewards, const float* win_returns_tok, const float* eps,
                              uint64_t seed, float* out_eval_action, float* out_sample_actions, void* stream);
 
+/* Device-resident episode histories of E lock-step environments: what the reference keeps as
+ * `current_trajectory` numpy arrays (replay_buffer.py:192-205, learner.py:663-675) and re-slices on the host every step
+ * (learner.py:346-366).  ring: device fp32 (E, ring_len, obs+act+1), row = [observation | action | reward] of one time step,
+ * zero-initialised by the caller at episode start.
+ *   m3pc_ring_append   writes the observation of step t and (when non-NULL) the action / reward of step t-1 -- the per-step
+ *                      host->device traffic is E*(obs+act+1) floats instead of E windows.
+ *   m3pc_ring_windows  builds the (E,T,.) planner windows of step `path_length` exactly as learner.py:346-366 does (the last
+ *                      T-horizon+1 steps, zero padded; zeroshot_omtm/learner.py:97-106 when future_obs: the states window
+ *                      also holds the stored future waypoints) and fills the tokenised return-to-go (one scalar per
+ *                      environment, rtg_tok (E), computed by the host as in m3pc_plan_args_t.win_returns_tok). */
+int m3pc_ring_append(float* ring, int32_t n_env, int32_t ring_len, int32_t obs_dim, int32_t act_dim, int32_t t, const float* obs,
+                     const float* prev_action, const float* prev_reward, void* stream);
+int m3pc_ring_windows(const float* ring, int32_t n_env, int32_t ring_len, int32_t obs_dim, int32_t act_dim, int32_t path_length,
+                      int32_t horizon, int32_t traj_length, int32_t future_obs, const float* rtg_tok, float* win_states,
+                      float* win_actions, float* win_rewards, float* win_returns_tok, void* stream);
+
 /* ---- kernel-level entry points (unit parity tests and profiling; same kernels the calls above launch) ---- */
 
 /* C[M,N] = epilogue(A[M,K] * W[N,K]^T): flags bit0 = GELU(erf), bit1 = C += residual (fp32 in place, C is fp32),

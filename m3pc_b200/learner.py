@@ -160,23 +160,32 @@ class PlannerMixin:
         end_idx = sequence_history["path_length"]
         hl = T - horizon + 1
         lo, hi = end_idx - hl + 1, end_idx + 1
-        states[:] = 0
-        actions[:] = 0
-        rewards[:] = 0
-        states[:hl] = sequence_history["observations"][lo:hi]
+        obs = sequence_history["observations"]
+        states[:hl] = obs[lo:hi]
+        states[hl:] = 0
         actions[:hl] = sequence_history["actions"][lo:hi]
-        rewards[:hl] = np.asarray(sequence_history["rewards"][lo:hi]).reshape(-1)
+        actions[hl:] = 0
+        rewards[:hl] = sequence_history["rewards"][lo:hi, 0] if getattr(sequence_history["rewards"], "ndim", 0) == 2 else \
+            np.asarray(sequence_history["rewards"][lo:hi]).reshape(-1)
+        rewards[hl:] = 0
         if future_obs:
             smart_T = T
             if end_idx + horizon > 1000:
                 smart_T = smart_T - (end_idx + horizon - 1000)
-            states[:smart_T] = sequence_history["observations"][lo:lo + T]
+            states[:smart_T] = obs[lo:lo + T]
         if rtg is not None:
             return_to_go = float(rtg)
         else:
             stats = self.tokenizer_manager.tokenizers["returns"].stats
             return_to_go = float(np.asarray(stats.min + (stats.max - stats.min) * percentage).reshape(-1)[0])
-        returns[:] = self._returns_tok(return_to_go * np.ones(T))
+        # the token of a constant return-to-go is one scalar: (rtg * 1.0 - mean) / std in float64, rounded once to fp32
+        cache = self.__dict__.setdefault("_rtg_tok", {})
+        tok = cache.get(return_to_go)
+        if tok is None:
+            if len(cache) > 4096:
+                cache.clear()
+            tok = cache[return_to_go] = self._returns_tok(return_to_go * np.ones(1)).reshape(-1)[0]
+        returns[:] = tok
 
     def _clamped_horizon(self, sequence_history) -> int:
         """learner.py:342-345: early in an episode the planning horizon grows so the window stays full."""

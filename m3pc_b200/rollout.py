@@ -13,6 +13,7 @@ reference's loop.  Environments use the reference's (old gym) protocol: ``reset(
 """
 from __future__ import annotations
 
+from types import SimpleNamespace
 from typing import Any, Callable, Dict, List, Optional, Sequence
 
 import numpy as np
@@ -108,6 +109,133 @@ def evaluate_plan(learner, make_env: Callable[[], Any], num_episodes: int, episo
         rets += out["returns"].tolist()
         lens += out["lengths"].tolist()
     return {"return_mean": float(np.mean(rets)), "return_std": float(np.std(rets)), "length_mean": float(np.mean(lens)), "episodes": len(rets)}
+
+
+class DeviceEpisodes:
+    """Device-resident histories of E lock-step episodes (``m3pc_ring_*`` in include/m3pc.h).
+
+    The reference keeps each episode as zero-filled (1000, d) numpy arrays and re-slices a window out of them on the host at
+    every step (learner.py:346-366).  Here the arrays live in HBM: a step uploads only the new observation and the action /
+    reward just taken (E * (obs + act + 1) floats), and the planner's (E, T, .) windows are cut on the device.
+
+        ep = DeviceEpisodes(learner, n_env=E); ep.start(obs0)                     # obs0: (E, obs)
+        a = ep.plan_async(rtg=3.0, plan=True, eval=True).result()                 # (E, act)
+        ep.step(a, rewards, next_obs)                                             # then plan again
+    """
+
+    def __init__(self, learner, n_env: int, max_path_length: int = 1000):
+        import ctypes as C
+
+        import torch
+
+        from . import _native as nat
+        self.learner, self.E, self.L = learner, int(n_env), int(max_path_length)
+        if self.E < 1 or self.E > int(getattr(learner, "max_envs", 1)):
+            raise ValueError(f"{n_env} environments but the Learner was built with max_envs={getattr(learner, 'max_envs', 1)}")
+        learner._engine()
+        self._nat, self._C, self._torch = nat, C, torch
+        self.obs = int(learner.mtm.data_shapes["states"][1])
+        self.act = int(learner.mtm.data_shapes["actions"][1])
+        self.T = int(learner.cfg.traj_length)
+        dev = learner.mtm.pos_embed.device
+        w = self.obs + self.act + 1
+        self.ring = torch.zeros(self.E, self.L, w, device=dev)
+        self.t = -1  # path_length of the current step; -1 before start()
+        self._stage = [SimpleNamespace(host=torch.zeros(self.E * (w + 1)).pin_memory(), event=torch.cuda.Event(), used=False) for _ in range(2)]
+        self._turn = 0
+        self._dev_stage = torch.zeros(self.E * (w + 1), device=dev)
+        E, T = self.E, self.T
+        self.win_states = torch.zeros(E, T, self.obs, device=dev)
+        self.win_actions = torch.zeros(E, T, self.act, device=dev)
+        self.win_rewards = torch.zeros(E, T, device=dev)
+        self.win_returns = torch.zeros(E, T, device=dev)
+
+    def _slot(self):
+        s = self._stage[self._turn]
+        self._turn ^= 1
+        if s.used:
+            s.event.synchronize()
+        return s
+
+    def _upload(self, slot, n: int):
+        self._dev_stage[:n].copy_(slot.host[:n], non_blocking=True)
+        slot.event.record()
+        slot.used = True
+
+    def _stream(self):
+        return self._torch.cuda.current_stream().cuda_stream
+
+    def start(self, obs0) -> None:
+        """Begin E episodes: clears the histories and stores the first observations (E, obs)."""
+        self.ring.zero_()
+        self.t = 0
+        self._append(np.asarray(obs0, dtype=np.float32), None, None)
+
+    def step(self, actions, rewards, next_obs) -> None:
+        """Record the actions taken at the current step and their rewards, and the observations of the next step."""
+        if self.t < 0:
+            raise RuntimeError("DeviceEpisodes.step() before start()")
+        if self.t + 1 >= self.L:
+            raise RuntimeError("episode longer than max_path_length")
+        self.t += 1
+        self._append(np.asarray(next_obs, dtype=np.float32), np.asarray(actions, dtype=np.float32), np.asarray(rewards, dtype=np.float32))
+
+    def _append(self, obs, act, rew) -> None:
+        E, o, a = self.E, self.obs, self.act
+        if obs.shape != (E, o):
+            raise ValueError(f"observations have shape {obs.shape}, expected {(E, o)}")
+        slot = self._slot()
+        h = slot.host.numpy()
+        h[:E * o] = obs.reshape(-1)
+        n = E * o
+        pa = pr = None
+        if act is not None:
+            h[n:n + E * a] = act.reshape(E * a)
+            h[n + E * a:n + E * a + E] = rew.reshape(E)
+            pa = self._dev_stage.data_ptr() + 4 * n
+            pr = pa + 4 * E * a
+            n += E * a + E
+        self._upload(slot, n)
+        nat = self._nat
+        nat.check(nat.lib().m3pc_ring_append(self.ring.data_ptr(), E, self.L, o, a, self.t, self._dev_stage.data_ptr(), pa, pr, self._stream()),
+                  "m3pc_ring_append")
+
+    def plan_async(self, percentage: float = 1.0, plan: bool = True, eval: bool = False, rtg=None):
+        """``Learner.action_sample_async`` on the device-resident histories: returns a ticket for the (E, act) actions."""
+        L = self.learner
+        if eval == True:  # noqa: E712
+            assert rtg is not None
+        if self.t < 0:
+            raise RuntimeError("DeviceEpisodes.plan_async() before start()")
+        E, T = self.E, self.T
+        horizon = L._clamped_horizon({"path_length": self.t})
+        if rtg is not None:
+            r = np.broadcast_to(np.asarray(rtg, dtype=np.float64).reshape(-1), (E,)) if np.ndim(rtg) else np.full(E, float(rtg))
+        else:
+            stats = L.tokenizer_manager.tokenizers["returns"].stats
+            r = np.full(E, float(np.asarray(stats.min + (stats.max - stats.min) * percentage).reshape(-1)[0]))
+        slot = self._slot()
+        slot.host.numpy()[:E] = L._returns_tok(r * np.ones(E)).reshape(E)
+        self._upload(slot, E)
+        nat = self._nat
+        nat.check(nat.lib().m3pc_ring_windows(self.ring.data_ptr(), E, self.L, self.obs, self.act, self.t, horizon, T,
+                                              1 if getattr(L, "_future_obs_windows", False) else 0, self._dev_stage.data_ptr(),
+                                              self.win_states.data_ptr(), self.win_actions.data_ptr(), self.win_rewards.data_ptr(),
+                                              self.win_returns.data_ptr(), self._stream()), "m3pc_ring_windows")
+        if plan:
+            assert L.cfg.plan_guidance in ("critic_lambda_guiding", "rtg_guiding", "noise_adding_lambda")
+            lmbda = 0.6 if L.cfg.plan_guidance == "rtg_guiding" else L.cfg.lmbda
+            guidance = L.cfg.plan_guidance
+        else:
+            lmbda, guidance = 0.0, "mtm_sampling"
+        lead = (E,) if E > 1 else ()
+        ev, sm = L._plan_device(guidance, horizon, lmbda, self.win_states.view(*lead, T, self.obs), self.win_actions.view(*lead, T, self.act),
+                                self.win_rewards.view(*lead, T), self.win_returns.view(*lead, T), n_env=E)
+        from .learner import PlanTicket
+        pool = L.__dict__.setdefault("_tickets", {}).setdefault(E, [])
+        ticket = pool.pop() if pool else PlanTicket(E, self.act, pool)
+        ticket._submit(ev if eval else sm)
+        return ticket
 
 
 class LinearEnv:

@@ -136,3 +136,43 @@ def test_evaluate_plan_with_the_planner_and_tickets():
     np.testing.assert_array_equal(a, b)
     with pytest.raises(RuntimeError):
         t.result()
+
+
+@pytest.mark.gpu
+def test_device_resident_episodes_build_the_same_windows_and_actions():
+    """m3pc_ring_append / m3pc_ring_windows: windows cut on the device from HBM-resident histories
+    are bit-identical to the host window builder (learner.py:346-366 semantics) at every step, across the horizon-clamp regime
+    change, and the plans on them return the same actions."""
+    E, H = 5, 13
+    shape, L = _gpu_learner("bf16", 32, E)
+    envs = [ro.LinearEnv(shape.obs_dim, shape.act_dim, seed=70 + e, horizon=H) for e in range(E)]
+    trajs = [ro.new_trajectory(shape.obs_dim, shape.act_dim, 1000) for _ in range(E)]
+    ep = ro.DeviceEpisodes(L, n_env=E, max_path_length=1000)
+    obs = np.stack([env.reset() for env in envs])
+    ep.start(obs)
+    for e in range(E):
+        trajs[e]["observations"][0] = obs[e]
+    T = shape.traj_length
+    for t in range(H):
+        rtg = [3.0 - 0.1 * t + 0.01 * e for e in range(E)]
+        L.__dict__["_plan_counter"] = 500 + t
+        host = L.action_sample_batch(trajs, plan=True, eval=True, rtg=rtg).cpu().numpy()
+        ring = L.__dict__["_win"][(shape.obs_dim, shape.act_dim, T, E)]
+        hs, ha, hr, ht = ring.d_states.clone(), ring.d_actions.clone(), ring.d_rewards.clone(), ring.d_returns.clone()
+        L.__dict__["_plan_counter"] = 500 + t
+        dev = ep.plan_async(plan=True, eval=True, rtg=rtg).result()
+        assert torch.equal(ep.win_states, hs) and torch.equal(ep.win_actions, ha), f"step {t}"
+        assert torch.equal(ep.win_rewards, hr) and torch.equal(ep.win_returns, ht), f"step {t}"
+        np.testing.assert_array_equal(dev, host)
+        actions = np.clip(dev, -1, 1)
+        nxt, rew = np.zeros_like(obs), np.zeros(E, np.float32)
+        for e in range(E):
+            o, r, _, _ = envs[e].step(actions[e])
+            nxt[e], rew[e] = o, r
+            trajs[e]["actions"][t], trajs[e]["rewards"][t] = actions[e], r
+            trajs[e]["path_length"] += 1
+            if t + 1 < 1000:
+                trajs[e]["observations"][t + 1] = o
+        ep.step(actions, rew, nxt)
+    with pytest.raises(ValueError):
+        ro.DeviceEpisodes(L, n_env=E + 1)
