@@ -269,8 +269,9 @@ __global__ void __launch_bounds__(MMA_WARPS * 32) attention_mma_kernel(const __g
   }
 }
 
-// Variant for the planner's restricted decoder layer: most keys / values are batch-constant mask-token rows (19 of 32 at the
-// shipped sizes).  One CTA works on ONE head for SH_WARPS batch rows: the constant K / V tiles are staged once per CTA and
+// Variant for attention whose keys / values are mostly shared between batch rows: the planner's restricted decoder layer (19 of
+// 32 keys are batch-constant mask-token rows at the shipped sizes) and the first encoder block of pass 2 (9 of 13 keys are the
+// history tokens of the row's environment).  One CTA works on ONE head for SH_WARPS batch rows: the constant K / V tiles are staged once per CTA and
 // shared by its warps; every warp stages only its own batch row's keys (one query tile).  Key order is [per-batch keys, constant
 // keys] (softmax and P V are invariant to a common permutation of keys and values); each key tile is homogeneous.
 constexpr int SH_WARPS = 8;
@@ -292,12 +293,17 @@ __global__ void __launch_bounds__(SH_WARPS * 32) attention_mma_shared_kernel(con
   uint8_t* sVb = sKb + BP * 256;
   const uint32_t uKc = smem_u32(sKc), uVc = smem_u32(sVc), uQ = smem_u32(sQ), uKb = smem_u32(sKb), uVb = smem_u32(sVb);
 
-  for (int idx = threadIdx.x; idx < CP * 16; idx += SH_WARPS * 32) {  // constant keys / values: whole CTA
+  // keys / values shared by the CTA's batch rows: batch-constant rows (bstride 0) or one row per group of bdiv batch rows
+  // (bdiv is a multiple of SH_WARPS, so the 8 rows of a CTA belong to one group)
+  const int b_cta = min(static_cast<int>(blockIdx.x) * SH_WARPS, p.B - 1);
+  for (int idx = threadIdx.x; idx < CP * 16; idx += SH_WARPS * 32) {
     const int r = idx >> 4, c = idx & 15;
     const uint32_t off = swz(r, c);
     if (r < n_c) {
-      cp_async16(uKc + off, reinterpret_cast<const __nv_bfloat16*>(p.k[n_b + r].ptr) + h * HD + c * 8);
-      cp_async16(uVc + off, reinterpret_cast<const __nv_bfloat16*>(p.v[n_b + r].ptr) + h * HD + c * 8);
+      const AttnTok& tk = p.k[n_b + r];
+      const AttnTok& tv = p.v[n_b + r];
+      cp_async16(uKc + off, reinterpret_cast<const __nv_bfloat16*>(tk.ptr) + (tk.bdiv > 0 ? tok_off(tk, b_cta) : 0) + h * HD + c * 8);
+      cp_async16(uVc + off, reinterpret_cast<const __nv_bfloat16*>(tv.ptr) + (tv.bdiv > 0 ? tok_off(tv, b_cta) : 0) + h * HD + c * 8);
     } else {
       *reinterpret_cast<uint4*>(sKc + off) = make_uint4(0, 0, 0, 0);
       *reinterpret_cast<uint4*>(sVc + off) = make_uint4(0, 0, 0, 0);
@@ -456,7 +462,8 @@ int launch_attention_gather(const AttnParams& p, bool bf16, cudaStream_t st) {
     const int n_c = p.n_kv - p.n_kv_batch, ntb = (p.n_kv_batch + 15) / 16, ntc = (n_c + 15) / 16;
     bool ok = n_c >= 8 && ntb <= 2 && ntc <= 3;
     for (int j = 0; j < p.n_kv && ok; ++j)
-      ok = j < p.n_kv_batch ? true : (p.k[j].bstride == 0 && p.v[j].bstride == 0 && p.k[j].bdiv == 0 && p.v[j].bdiv == 0);
+      ok = j < p.n_kv_batch ? true : ((p.k[j].bstride == 0 && p.v[j].bstride == 0 && p.k[j].bdiv == 0 && p.v[j].bdiv == 0) ||
+                                      (p.k[j].bdiv > 0 && p.k[j].bdiv % SH_WARPS == 0 && p.v[j].bdiv == p.k[j].bdiv));
     if (ok) {
       switch (ntb * 10 + ntc) {
         case 11: return launch_mma_shared<1, 1>(p, st);

@@ -575,15 +575,19 @@ int block_shared_history(m3pc_engine* e, const LayerW& w, int Bc, int S, int n_s
   ap.B = Bc;
   ap.n_head = e->H;
   ap.out = e->ATT.p;
-  for (int s = 0; s < S; ++s) {
+  // queries in token order (the output row block is the query's token); keys / values with the per-candidate tokens first and the
+  // shared history tokens after them, which lets the bf16 kernel stage the shared ones once per CTA
+  auto tok = [&](int s, int part) {
     const bool sh = s < n_sh;
     const char* row = sh ? reinterpret_cast<const char*>(e->QKVT.p) + static_cast<size_t>(s) * nG * 3 * D * ab
                          : reinterpret_cast<const char*>(e->QKV.p) + static_cast<size_t>(s) * Bc * 3 * D * ab;
-    const int bdiv = sh ? grp : 0;
-    ap.q[s] = AttnTok{row, 3 * D, bdiv};
-    ap.k[s] = AttnTok{row + D * ab, 3 * D, bdiv};
-    ap.v[s] = AttnTok{row + 2 * D * ab, 3 * D, bdiv};
-  }
+    return AttnTok{row + static_cast<size_t>(part) * D * ab, 3 * D, sh ? grp : 0};
+  };
+  for (int s = 0; s < S; ++s) ap.q[s] = tok(s, 0);
+  int nk = 0;
+  for (int s = n_sh; s < S; ++s, ++nk) { ap.k[nk] = tok(s, 1); ap.v[nk] = tok(s, 2); }
+  ap.n_kv_batch = nk;
+  for (int s = 0; s < n_sh; ++s, ++nk) { ap.k[nk] = tok(s, 1); ap.v[nk] = tok(s, 2); }
   M3PC_TRY(launch_attention_gather(ap, e->bf16, st));
   GemmJob op[2];
   GemmEpilogue es;  // shared tokens: X = table[token, group] + att W^T + b (plain store; row / grp = token * nG + group)

@@ -22,7 +22,11 @@ lead = (E,) if E > 1 else ()
 ws, wa = torch.randn(*lead, T, shape.obs_dim, device="cuda", generator=g), torch.rand(*lead, T, shape.act_dim, device="cuda", generator=g) * 2 - 1
 wr, wt = torch.randn(*lead, T, device="cuda", generator=g), torch.full((*lead, T), 0.7, device="cuda")
 for i in range(n):
+    if i == n - 1:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()  # ncu --profile-from-start off: only the last plan is captured
     eng.plan(guidance=w["guidance"], horizon=4, n_cand=w["n_cand"], win_states=ws, win_actions=wa, win_rewards=wr, win_returns_tok=wt,
              discount=0.99, temperature=w["temperature"], lmbda=0.6, seed=i, n_env=E)
     torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("launches per plan", eng.last_launch_count(), "last ms", eng.last_device_ms())
