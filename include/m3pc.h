@@ -201,6 +201,10 @@ int m3pc_gemm_fp32(const float* A, const float* W, const float* bias, float* C, 
 int m3pc_gemm_bf16_grouped(int32_t n, const void* const* A, const void* const* W, const float* const* bias,
                            void* const* C, const int32_t* M, const int32_t* N, const int32_t* K, const int32_t* flags,
                            void* stream);
+/* Fused residual GEMM + LayerNorm (N = 512): X[M,512] (fp32, in place) += A[M,K] W[512,K]^T + bias, or, with `table`,
+ * X = table[row / rows_per_group] + A W^T + bias; Y[M,512] (bf16) = LayerNorm(X; gamma, beta), eps 1e-5.  A, W bf16. */
+int m3pc_gemm_ln_bf16(const void* A, const void* W, const float* bias, float* X, void* Y, const float* gamma, const float* beta,
+                      const float* table, int32_t rows_per_group, int32_t M, int32_t K, void* stream);
 /* y = LayerNorm(x) over the last dim (eps 1e-5); x fp32 (M,D); y bf16 (out_bf16=1) or fp32. */
 int m3pc_layernorm(const float* x, const float* gamma, const float* beta, void* y, int32_t M, int32_t D,
                    int32_t out_bf16, void* stream);

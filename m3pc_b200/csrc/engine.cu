@@ -130,6 +130,7 @@ struct m3pc_engine {
   bool dedupe_history = true;  // M3PC_NO_DEDUPE=1 disables
   DevBuf fb_xd, fb_bar;  // fused B = 1 path: decoder-embedding scratch, grid-barrier state
   bool use_fused_b1 = true;
+  bool fuse_ln = true;        // residual GEMM + LayerNorm in one kernel (gemm_ln.cu); M3PC_NO_FUSED_LN=1 disables
   bool restrict_deep = true;  // decoders with > 1 layer: last layer on the consumed rows only (M3PC_DEC_FULL=1 disables)
   bool use_mega = false;  // encoder megakernel: measured slower than the per-op path at <= 1024 rows per chunk; M3PC_MEGA=1 enables
   // planner buffers
@@ -518,40 +519,79 @@ int gemm_group(m3pc_engine* e, const GemmJob* jobs, int n, cudaStream_t st) {
   return M3PC_OK;
 }
 
-// second half of a pre-LN transformer block: X += MLP(LN2(X)) on `rows` token-major rows
-int mlp_half(m3pc_engine* e, const LayerW& w, int rows, cudaStream_t st) {
-  const int D = e->D, F = e->F;
+// X += A W^T + bias (or, with `table`, X = table[row / rpg] + A W^T + bias) followed by Y = LayerNorm(X; g, b): ONE tensor-core
+// kernel whose epilogue owns whole rows (gemm_ln.cu) where it applies (bf16 mode, n_embd 512), else GEMM + LayerNorm kernel.
+int gemm_res_ln(m3pc_engine* e, const void* A, const float* w32, const __nv_bfloat16* w16, const float* bias, float* X, void* Y,
+                const float* g, const float* b, const float* table, int rpg, int M, int K, cudaStream_t st) {
+  const int D = e->D;
+  if (e->bf16 && e->fuse_ln && D == 512 && M > 128) {
+    size_t slot = 0;
+    if (e->profile) {
+      slot = e->prof_used++;
+      if (slot >= e->prof_events.size()) {
+        cudaEvent_t a, c;
+        M3PC_CHECK_CUDA(cudaEventCreate(&a));
+        M3PC_CHECK_CUDA(cudaEventCreate(&c));
+        e->prof_events.push_back({a, c});
+        e->prof_flops.push_back(0.0);
+      }
+      e->prof_flops[slot] = 2.0 * M * static_cast<double>(D) * K;
+      M3PC_CHECK_CUDA(cudaEventRecord(e->prof_events[slot].first, st));
+    }
+    M3PC_TRY(gemm_ln_bf16(reinterpret_cast<const __nv_bfloat16*>(A), w16, bias, X, reinterpret_cast<__nv_bfloat16*>(Y), g, b, table, rpg, M, K, st));
+    if (e->profile) M3PC_CHECK_CUDA(cudaEventRecord(e->prof_events[slot].second, st));
+    return M3PC_OK;
+  }
+  GemmEpilogue ep;
+  ep.bias = bias;
+  if (table != nullptr) {
+    ep.table = table;
+    ep.rows_per_group = rpg;
+    ep.flags = EPI_OUT_F32 | EPI_ROWTABLE;
+  } else {
+    ep.flags = EPI_RESIDUAL;
+  }
+  M3PC_TRY(gemm(e, A, w32, w16, X, M, D, K, ep, st));
   LnParams ln{};
-  ln.x = e->X.as<float>();
-  ln.rows = rows;
-  ln.g1 = w.n2_w;
-  ln.b1 = w.n2_b;
-  ln.y1 = e->Y.p;
+  ln.x = X;
+  ln.rows = M;
+  ln.g1 = g;
+  ln.b1 = b;
+  ln.y1 = Y;
   ln.rows_per_group = 1;
-  M3PC_TRY(launch_layernorm(ln, D, e->bf16, st));
+  return launch_layernorm(ln, D, e->bf16, st);
+}
+
+// LayerNorm applied to the residual stream right after a block: the next block's norm1 or a stack's final norm
+struct PostLn {
+  const float* g = nullptr;
+  const float* b = nullptr;
+  void* y = nullptr;
+};
+
+// second half of a pre-LN transformer block on `rows` token-major rows: expects Y = LN2(X); X += MLP(Y); then `post` (optional)
+int mlp_half(m3pc_engine* e, const LayerW& w, int rows, cudaStream_t st, const PostLn& post) {
+  const int D = e->D, F = e->F;
   GemmEpilogue ep;
   ep.bias = w.l1_b;
   ep.flags = EPI_GELU;
   M3PC_TRY(gemm(e, e->Y.p, w.l1_w, w.l1_w16, e->HID.p, rows, F, D, ep, st));
+  if (post.y != nullptr) return gemm_res_ln(e, e->HID.p, w.l2_w, w.l2_w16, w.l2_b, e->X.as<float>(), post.y, post.g, post.b, nullptr, 1, rows, F, st);
   ep = GemmEpilogue{};
   ep.bias = w.l2_b;
   ep.flags = EPI_RESIDUAL;
-  M3PC_TRY(gemm(e, e->HID.p, w.l2_w, w.l2_w16, e->X.p, rows, D, F, ep, st));
-  return M3PC_OK;
+  return gemm(e, e->HID.p, w.l2_w, w.l2_w16, e->X.p, rows, D, F, ep, st);
 }
 
 // one pre-LN transformer block on `rows` = S * Bc token-major rows; expects Y = LN1(X) on entry
-int block(m3pc_engine* e, const LayerW& w, int Bc, int S, cudaStream_t st) {
+int block(m3pc_engine* e, const LayerW& w, int Bc, int S, cudaStream_t st, const PostLn& post = PostLn{}) {
   const int D = e->D, rows = S * Bc;
   GemmEpilogue ep;
   ep.bias = w.in_b;
   M3PC_TRY(gemm(e, e->Y.p, w.in_w, w.in_w16, e->QKV.p, rows, 3 * D, D, ep, st));
   M3PC_TRY(launch_attention(e->QKV.p, e->ATT.p, Bc, S, e->H, e->bf16, st));
-  ep = GemmEpilogue{};
-  ep.bias = w.out_b;
-  ep.flags = EPI_RESIDUAL;
-  M3PC_TRY(gemm(e, e->ATT.p, w.out_w, w.out_w16, e->X.p, rows, D, D, ep, st));
-  return mlp_half(e, w, rows, st);
+  M3PC_TRY(gemm_res_ln(e, e->ATT.p, w.out_w, w.out_w16, w.out_b, e->X.as<float>(), e->Y.p, w.n2_w, w.n2_b, nullptr, 1, rows, D, st));
+  return mlp_half(e, w, rows, st, post);
 }
 
 // First encoder block when the first `n_sh` tokens are history tokens shared by groups of `grp` batch rows (the candidates of
@@ -559,7 +599,7 @@ int block(m3pc_engine* e, const LayerW& w, int Bc, int S, cudaStream_t st) {
 // token * nG + group) instead of once per candidate.  The attention output differs per candidate, so from the
 // out-projection on every row exists; for the shared tokens the residual is the table row, added in the epilogue.
 // Expects: XT / YT = embedding / LN1 of the shared tokens, X / Y rows [n_sh*Bc, S*Bc) = the per-candidate tokens.
-int block_shared_history(m3pc_engine* e, const LayerW& w, int Bc, int S, int n_sh, int grp, cudaStream_t st) {
+int block_shared_history(m3pc_engine* e, const LayerW& w, int Bc, int S, int n_sh, int grp, cudaStream_t st, const PostLn& post) {
   const int D = e->D, nG = Bc / grp;
   const size_t ab = act_bytes(e);
   const size_t off = static_cast<size_t>(n_sh) * Bc;  // first per-candidate row
@@ -589,19 +629,13 @@ int block_shared_history(m3pc_engine* e, const LayerW& w, int Bc, int S, int n_s
   ap.n_kv_batch = nk;
   for (int s = 0; s < n_sh; ++s, ++nk) { ap.k[nk] = tok(s, 1); ap.v[nk] = tok(s, 2); }
   M3PC_TRY(launch_attention_gather(ap, e->bf16, st));
-  GemmJob op[2];
-  GemmEpilogue es;  // shared tokens: X = table[token, group] + att W^T + b (plain store; row / grp = token * nG + group)
-  es.bias = w.out_b;
-  es.table = e->XT.as<float>();
-  es.rows_per_group = grp;
-  es.flags = EPI_OUT_F32 | EPI_ROWTABLE;
-  op[0] = GemmJob{e->ATT.p, w.out_w, w.out_w16, e->X.p, static_cast<int>(off), D, D, es};
-  GemmEpilogue er;  // per-candidate tokens: X += att W^T + b
-  er.bias = w.out_b;
-  er.flags = EPI_RESIDUAL;
-  op[1] = GemmJob{reinterpret_cast<const char*>(e->ATT.p) + off * D * ab, w.out_w, w.out_w16, e->X.as<float>() + off * D, (S - n_sh) * Bc, D, D, er};
-  M3PC_TRY(gemm_group(e, op, 2, st));
-  return mlp_half(e, w, S * Bc, st);
+  // out-projection + norm2.  Shared tokens: X = table[token, group] + att W^T + b (row / grp = token * nG + group);
+  // per-candidate tokens: X += att W^T + b.
+  M3PC_TRY(gemm_res_ln(e, e->ATT.p, w.out_w, w.out_w16, w.out_b, e->X.as<float>(), e->Y.p, w.n2_w, w.n2_b, e->XT.as<float>(), grp,
+                       static_cast<int>(off), D, st));
+  M3PC_TRY(gemm_res_ln(e, reinterpret_cast<const char*>(e->ATT.p) + off * D * ab, w.out_w, w.out_w16, w.out_b, e->X.as<float>() + off * D,
+                       reinterpret_cast<char*>(e->Y.p) + off * D * ab, w.n2_w, w.n2_b, nullptr, 1, (S - n_sh) * Bc, D, st));
+  return mlp_half(e, w, S * Bc, st, post);
 }
 
 struct NeedSet {
@@ -720,12 +754,14 @@ int decode_full(m3pc_engine* e, const FwdIO& io, const void* enc_out, const int*
   ln.x = e->X.as<float>();
   ln.rows = Sd * Bc;
   ln.rows_per_group = Bc;
+  ln.g1 = e->dec.layers[0].n1_w;
+  ln.b1 = e->dec.layers[0].n1_b;
+  ln.y1 = e->Y.p;
+  M3PC_TRY(launch_layernorm(ln, D, e->bf16, st));
   for (int l = 0; l < e->Ld; ++l) {
-    ln.g1 = e->dec.layers[l].n1_w;
-    ln.b1 = e->dec.layers[l].n1_b;
-    ln.y1 = e->Y.p;
-    M3PC_TRY(launch_layernorm(ln, D, e->bf16, st));
-    M3PC_TRY(block(e, e->dec.layers[l], Bc, Sd, st));
+    PostLn post;  // the next layer's norm1 rides on this layer's linear2
+    if (l + 1 < e->Ld) post = PostLn{e->dec.layers[l + 1].n1_w, e->dec.layers[l + 1].n1_b, e->Y.p};
+    M3PC_TRY(block(e, e->dec.layers[l], Bc, Sd, st, post));
   }
   // heads over all rows: token blocks in decoder order
   int all_tok[MAX_TOK];
@@ -817,19 +853,8 @@ int restricted_last_layer(m3pc_engine* e, const FwdIO& io, const LayerW& w, cons
   }
   M3PC_TRY(launch_fill_rows(fp, D, e->XS.as<float>(), st));
   const int rows = need.n * Bc;
-  ge = GemmEpilogue{};
-  ge.bias = w.out_b;
-  ge.flags = EPI_RESIDUAL;
-  M3PC_TRY(gemm(e, e->ATT.p, w.out_w, w.out_w16, e->XS.p, rows, D, D, ge, st));
-  // (g) MLP
-  LnParams ln{};
-  ln.x = e->XS.as<float>();
-  ln.rows = rows;
-  ln.rows_per_group = Bc;
-  ln.g1 = w.n2_w;
-  ln.b1 = w.n2_b;
-  ln.y1 = e->Y.p;
-  M3PC_TRY(launch_layernorm(ln, D, e->bf16, st));
+  // out-projection + norm2 (g) MLP
+  M3PC_TRY(gemm_res_ln(e, e->ATT.p, w.out_w, w.out_w16, w.out_b, e->XS.as<float>(), e->Y.p, w.n2_w, w.n2_b, nullptr, 1, rows, D, st));
   ge = GemmEpilogue{};
   ge.bias = w.l1_b;
   ge.flags = EPI_GELU;
@@ -883,12 +908,11 @@ int decode_deep_restricted(m3pc_engine* e, const FwdIO& io, const void* enc_out,
   ln.rows = Sd * Bc;
   ln.rows_per_group = Bc;
   ln.y1 = e->Y.p;
-  for (int l = 0; l < e->Ld; ++l) {
-    ln.g1 = e->dec.layers[l].n1_w;
-    ln.b1 = e->dec.layers[l].n1_b;
-    M3PC_TRY(launch_layernorm(ln, D, e->bf16, st));
-    if (l + 1 < e->Ld) M3PC_TRY(block(e, e->dec.layers[l], Bc, Sd, st));
-  }
+  ln.g1 = e->dec.layers[0].n1_w;
+  ln.b1 = e->dec.layers[0].n1_b;
+  M3PC_TRY(launch_layernorm(ln, D, e->bf16, st));
+  for (int l = 0; l + 1 < e->Ld; ++l)  // the next layer's norm1 rides on this layer's linear2
+    M3PC_TRY(block(e, e->dec.layers[l], Bc, Sd, st, PostLn{e->dec.layers[l + 1].n1_w, e->dec.layers[l + 1].n1_b, e->Y.p}));
   int ident[MAX_TOK];
   for (int j = 0; j < Sd; ++j) ident[j] = j;
   return restricted_last_layer(e, io, e->dec.layers[e->Ld - 1], ident, Sd, need, b0, Bc, st);
@@ -1079,24 +1103,16 @@ int forward_chunk(m3pc_engine* e, const FwdIO& io, int b0, int Bc, cudaStream_t 
 
   // ---- encoder stack (mtm_model.py:379-391, 619-644) ----
   for (int l = 0; l < (mega ? 0 : e->Le); ++l) {
-    if (l == 0 && n_sh > 0)
-      M3PC_TRY(block_shared_history(e, e->enc.layers[0], Bc, S, n_sh, grp, st));
+    // the LayerNorm that follows the block (next block's norm1, or the final encoder norm -> ENC) rides on its linear2
+    PostLn post;
+    if (l + 1 < e->Le)
+      post = PostLn{e->enc.layers[l + 1].n1_w, e->enc.layers[l + 1].n1_b, e->Y.p};
     else
-      M3PC_TRY(block(e, e->enc.layers[l], Bc, S, st));
-    LnParams ln{};
-    ln.x = e->X.as<float>();
-    ln.rows = S * Bc;
-    ln.rows_per_group = 1;
-    if (l + 1 < e->Le) {
-      ln.g1 = e->enc.layers[l + 1].n1_w;
-      ln.b1 = e->enc.layers[l + 1].n1_b;
-      ln.y1 = e->Y.p;
-    } else {
-      ln.g1 = e->enc.norm_w;
-      ln.b1 = e->enc.norm_b;
-      ln.y1 = e->ENC.p;
-    }
-    M3PC_TRY(launch_layernorm(ln, D, e->bf16, st));
+      post = PostLn{e->enc.norm_w, e->enc.norm_b, e->ENC.p};
+    if (l == 0 && n_sh > 0)
+      M3PC_TRY(block_shared_history(e, e->enc.layers[0], Bc, S, n_sh, grp, st, post));
+    else
+      M3PC_TRY(block(e, e->enc.layers[l], Bc, S, st, post));
   }
 
   if (need.n == 0) return M3PC_OK;
@@ -1433,6 +1449,7 @@ int create(m3pc_handle_t* out, const m3pc_config_t* cfg) {
   M3PC_TRY(e->fb_bar.alloc(16));
   M3PC_CHECK_CUDA(cudaMemset(e->fb_bar.p, 0, 16));
   if (const char* g = getenv("M3PC_NO_FUSED_B1")) e->use_fused_b1 = !(g[0] == '1');
+  if (const char* g = getenv("M3PC_NO_FUSED_LN")) e->fuse_ln = !(g[0] == '1');
   if (const char* g = getenv("M3PC_DEC_FULL")) e->restrict_deep = !(g[0] == '1');
   if (const char* g = getenv("M3PC_NO_DEDUPE")) e->dedupe_history = !(g[0] == '1');
   if (const char* g = getenv("M3PC_MEGA")) e->use_mega = g[0] == '1';
@@ -1585,6 +1602,12 @@ int m3pc_gemm_bf16_grouped(int32_t n, const void* const* A, const void* const* W
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   for (int i0 = 0; i0 < n; i0 += 4) M3PC_TRY(m3pc::gemm_bf16_grouped(pr + i0, std::min(4, n - i0), st));
   return M3PC_OK;
+}
+
+int m3pc_gemm_ln_bf16(const void* A, const void* W, const float* bias, float* X, void* Y, const float* gamma, const float* beta,
+                      const float* table, int32_t rows_per_group, int32_t M, int32_t K, void* stream) {
+  return m3pc::gemm_ln_bf16(reinterpret_cast<const __nv_bfloat16*>(A), reinterpret_cast<const __nv_bfloat16*>(W), bias, X,
+                            reinterpret_cast<__nv_bfloat16*>(Y), gamma, beta, table, rows_per_group, M, K, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int m3pc_gemm_fp32(const float* A, const float* W, const float* bias, float* C, int32_t M, int32_t N, int32_t K, int32_t flags, void* stream) {

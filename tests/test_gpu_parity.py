@@ -114,6 +114,36 @@ def test_gemm_bf16_grouped(nat, probs):
         assert rel(Cm, ref) < (2e-5 if flags & 2 else 4e-3), (M, N, K, flags)
 
 
+@pytest.mark.parametrize("M,K,table_rows", [(256, 512, 0), (300, 512, 0), (13312, 512, 0), (13312, 2048, 0), (4000, 512, 1000), (53248 + 77, 2048, 0)])
+def test_gemm_residual_layernorm_fused(nat, M, K, table_rows):
+    """m3pc_gemm_ln_bf16: X += A W^T + b (or X = table[row / g] + A W^T + b) and Y = LayerNorm(X) in one tensor-core kernel whose
+    CTA pair owns whole 512-wide rows -- against plain PyTorch fp32 on the same bf16-rounded operands."""
+    L = nat.lib()
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(512, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(512, device="cuda", generator=g)
+    gamma = 1 + 0.2 * torch.randn(512, device="cuda", generator=g)
+    beta = 0.2 * torch.randn(512, device="cuda", generator=g)
+    X = 2.0 * torch.randn(M, 512, device="cuda", generator=g) + 0.5
+    Y = torch.full((M, 512), float("nan"), device="cuda", dtype=torch.bfloat16)
+    table, grp = None, 1
+    if table_rows:
+        grp = table_rows
+        table = torch.randn((M + grp - 1) // grp, 512, device="cuda", generator=g)
+        resid = table.repeat_interleave(grp, dim=0)[:M]
+    else:
+        resid = X.clone()
+    ref_x = resid + A.float() @ W.float().t() + bias
+    ref_y = torch.nn.functional.layer_norm(ref_x, (512,), gamma, beta, 1e-5)
+    nat.check(L.m3pc_gemm_ln_bf16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), X.data_ptr(), Y.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                  table.data_ptr() if table is not None else None, grp, M, K, None), "m3pc_gemm_ln_bf16")
+    torch.cuda.synchronize()
+    assert rel(X, ref_x) < 2e-3
+    assert torch.isfinite(Y.float()).all()
+    assert rel(Y.float(), ref_y) < 1e-2
+
+
 def test_gemm_rejects_bad_shapes(nat):
     A = torch.zeros(128, 100, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(ValueError):
