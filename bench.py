@@ -361,7 +361,7 @@ def run_ours(args, w, shape, rank, local_rank, world):
                        "launches_per_plan": single.launches, "api": "Learner.action_sample(host numpy history) -> .cpu()"},
         "gpu_launches": launches * K,
         "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None,
-                     "traffic": traffic, "kernel": "gemm_bf16_2sm_kernel (tcgen05 cta_group::2)", "launches_per_step": g_n // 3, "gemm_ms_per_step": g_ms / 3,
+                     "traffic": traffic, "kernel": "gemm_bf16_2sm_kernel + gemm_ln_2sm_kernel (tcgen05 cta_group::2; the latter carries the residual add and the LayerNorm)", "launches_per_step": g_n // 3, "gemm_ms_per_step": g_ms / 3,
                      "gemm_flops_per_step": g_fl / 3, "gemm_flops_per_plan": g_fl / 3 / E_head, "peak_source": peak_src,
                      "whole_plan_dense_frac": fl_plan * value / (world * peak_tf * 1e12)},
         "flops_per_plan_dense": fl_plan, "flops_per_candidate_row": fl_row,

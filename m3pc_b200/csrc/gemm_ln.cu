@@ -187,9 +187,11 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
       const int row = row0 + lane;
       const bool live = row0 < P.M;
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(cgrp * 128);
-      // the residual tile is pulled into L2 while the MMAs of this row block are still running (each box load then waits for an
-      // L2 hit instead of an HBM round trip), and the box of the first chunk travels all the way to shared memory
-      if (from_x && live && lane < 8) tma_prefetch_l2_2d(&P.tx, cgrp * 128 + lane * 16, row0);
+      // short K: the residual tile is pulled into L2 while the MMAs of this row block are still running (each box load then waits
+      // for an L2 hit instead of an HBM round trip).  Not for long K: the A stream evicts the prefetched lines before they are
+      // used and the tile is read from HBM twice (measured: 838 MB instead of 654 MB per launch at K = 2048).
+      if (from_x && live && lane < 8 && P.num_kb <= 8) tma_prefetch_l2_2d(&P.tx, cgrp * 128 + lane * 16, row0);
+      // the box of the first chunk travels all the way to shared memory before the accumulator is ready
       if (from_x && live && lane == 0) {
         bulk_wait_read<0>();  // the buffer's last store has been read
         mbar_arrive_expect_tx(&rbar[nbox & 1], L::kBoxBytes);
