@@ -48,6 +48,15 @@ WORKLOADS = {
     "scaled_rtg_4096": dict(env="hopper", guidance="rtg_guiding", n_cand=4096, temperature=0.01, model="scaled"),
 }
 METRIC = "plans_per_sec"
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's real stdout (everything else -- NCCL's version banner, library
+    chatter -- was redirected to stderr in main())."""
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 UNIT = "plans/s"
 
 
@@ -170,7 +179,7 @@ def run_reference(args, w, shape, rank):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "p50_ms": 1e3 * statistics.median(times),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ ours
@@ -370,7 +379,7 @@ def run_ours(args, w, shape, rank, local_rank, world):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -386,6 +395,10 @@ def main():
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")  # keep the real stdout for the JSON line ...
+    os.dup2(2, 1)                              # ... and send every other write to fd 1 (NCCL prints its version there) to stderr
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = WORKLOADS[args.workload]
     shape = model_shape(w)
