@@ -282,9 +282,6 @@ __global__ void __launch_bounds__(SH_WARPS * 32) attention_mma_shared_kernel(con
   extern __shared__ __align__(128) uint8_t smem_att[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y;
-  const int b_raw = blockIdx.x * SH_WARPS + warp;
-  const bool live = b_raw < p.B;
-  const int b = live ? b_raw : p.B - 1;  // idle warps shadow the last row (they must reach the barrier) and store nothing
   const int n_q = p.n_q, n_b = p.n_kv_batch, n_c = p.n_kv - p.n_kv_batch;
   uint8_t* sKc = smem_att;             // CP x 256 B, shared by the CTA
   uint8_t* sVc = sKc + CP * 256;
@@ -292,10 +289,28 @@ __global__ void __launch_bounds__(SH_WARPS * 32) attention_mma_shared_kernel(con
   uint8_t* sKb = sQ + 16 * 256;
   uint8_t* sVb = sKb + BP * 256;
   const uint32_t uKc = smem_u32(sKc), uVc = smem_u32(sVc), uQ = smem_u32(sQ), uKb = smem_u32(sKb), uVb = smem_u32(sVb);
+  const int g = lane >> 2, t = lane & 3;
+  const float sl2 = 0.08838834764831845f * 1.4426950408889634f;  // 1/sqrt(128) * log2(e)
 
+  // persistent over a contiguous range of 8-row blocks: the shared tiles are staged only when their source changes (never for
+  // batch-constant rows, once per environment for per-group rows) and the CTA launch cost is paid once
+  const int nblk = (p.B + SH_WARPS - 1) / SH_WARPS;
+  const int bx_lo = static_cast<int>(static_cast<long long>(blockIdx.x) * nblk / gridDim.x);
+  const int bx_hi = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * nblk / gridDim.x);
+  int cur_grp = -1;
+#pragma unroll 1
+  for (int bx = bx_lo; bx < bx_hi; ++bx) {
+  const int b_raw = bx * SH_WARPS + warp;
+  const bool live = b_raw < p.B;
+  const int b = live ? b_raw : p.B - 1;  // idle warps shadow the last row (they must reach the barriers) and store nothing
   // keys / values shared by the CTA's batch rows: batch-constant rows (bstride 0) or one row per group of bdiv batch rows
-  // (bdiv is a multiple of SH_WARPS, so the 8 rows of a CTA belong to one group)
-  const int b_cta = min(static_cast<int>(blockIdx.x) * SH_WARPS, p.B - 1);
+  // (bdiv is a multiple of SH_WARPS, so the 8 rows of a block belong to one group)
+  const int b_cta = min(bx * SH_WARPS, p.B - 1);
+  const int grp_id = p.k[n_b].bdiv > 0 ? b_cta / p.k[n_b].bdiv : 0;
+  const bool restage = grp_id != cur_grp;
+  if (restage) {
+    if (cur_grp != -1) __syncthreads();  // every warp has finished reading the previous tiles
+    cur_grp = grp_id;
   for (int idx = threadIdx.x; idx < CP * 16; idx += SH_WARPS * 32) {
     const int r = idx >> 4, c = idx & 15;
     const uint32_t off = swz(r, c);
@@ -308,6 +323,7 @@ __global__ void __launch_bounds__(SH_WARPS * 32) attention_mma_shared_kernel(con
       *reinterpret_cast<uint4*>(sKc + off) = make_uint4(0, 0, 0, 0);
       *reinterpret_cast<uint4*>(sVc + off) = make_uint4(0, 0, 0, 0);
     }
+  }
   }
   for (int idx = lane; idx < 16 * 16; idx += 32) {  // queries of this warp's batch row
     const int r = idx >> 4, c = idx & 15;
@@ -329,10 +345,8 @@ __global__ void __launch_bounds__(SH_WARPS * 32) attention_mma_shared_kernel(con
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
+  if (restage) __syncthreads(); else __syncwarp();
 
-  const int g = lane >> 2, t = lane & 3;
-  const float sl2 = 0.08838834764831845f * 1.4426950408889634f;  // 1/sqrt(128) * log2(e)
   // ---- scores = Q K^T : 16 x (BP + CP), fp32 accumulators ----
   float sc[2 * NTK][4];
 #pragma unroll
@@ -408,13 +422,16 @@ __global__ void __launch_bounds__(SH_WARPS * 32) attention_mma_shared_kernel(con
     *reinterpret_cast<uint32_t*>(sQ + swz(g + 8, n) + 4 * t) = pack_bf16(o[n][2], o[n][3]);
   }
   __syncwarp();
-  if (!live) return;
-  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-  const int D = p.n_head * HD;
-  for (int idx = lane; idx < n_q * 16; idx += 32) {
-    const int r = idx >> 4, c = idx & 15;
-    *reinterpret_cast<uint4*>(out + (static_cast<size_t>(r) * p.B + b) * D + h * HD + c * 8) = *reinterpret_cast<const uint4*>(sQ + swz(r, c));
+  if (live) {
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+    const int D = p.n_head * HD;
+    for (int idx = lane; idx < n_q * 16; idx += 32) {
+      const int r = idx >> 4, c = idx & 15;
+      *reinterpret_cast<uint4*>(out + (static_cast<size_t>(r) * p.B + b) * D + h * HD + c * 8) = *reinterpret_cast<const uint4*>(sQ + swz(r, c));
+    }
   }
+  __syncwarp();  // the copy-out has read this warp's tiles before the next block's loads overwrite them
+  }  // bx
 }
 
 template <int NTB, int NTC>
@@ -425,7 +442,13 @@ int launch_mma_shared(const AttnParams& p, cudaStream_t st) {
     M3PC_CHECK_CUDA(cudaFuncSetAttribute(attention_mma_shared_kernel<NTB, NTC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  M3PC_CHECK_CUDA(launch_k(attention_mma_shared_kernel<NTB, NTC>, dim3(ceil_div(p.B, SH_WARPS), p.n_head), dim3(SH_WARPS * 32), smem, st, p));
+  const int nblk = ceil_div(p.B, SH_WARPS);
+  const int per_sm = std::max(1, (227 * 1024) / (smem + 1024));
+  // one wave of resident CTAs, each walking a range of row blocks -- once there are enough blocks for the ranges to balance
+  // (>= 4 per CTA); smaller problems keep one block per CTA
+  const int wave = std::max(1, ceil_div(per_sm * 148, p.n_head));
+  const int gx = nblk >= 4 * wave ? wave : nblk;
+  M3PC_CHECK_CUDA(launch_k(attention_mma_shared_kernel<NTB, NTC>, dim3(gx, p.n_head), dim3(SH_WARPS * 32), smem, st, p));
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
 }
