@@ -300,137 +300,137 @@ __global__ void __launch_bounds__(SH_WARPS * 32) attention_mma_shared_kernel(con
   int cur_grp = -1;
 #pragma unroll 1
   for (int bx = bx_lo; bx < bx_hi; ++bx) {
-  const int b_raw = bx * SH_WARPS + warp;
-  const bool live = b_raw < p.B;
-  const int b = live ? b_raw : p.B - 1;  // idle warps shadow the last row (they must reach the barriers) and store nothing
-  // keys / values shared by the CTA's batch rows: batch-constant rows (bstride 0) or one row per group of bdiv batch rows
-  // (bdiv is a multiple of SH_WARPS, so the 8 rows of a block belong to one group)
-  const int b_cta = min(bx * SH_WARPS, p.B - 1);
-  const int grp_id = p.k[n_b].bdiv > 0 ? b_cta / p.k[n_b].bdiv : 0;
-  const bool restage = grp_id != cur_grp;
-  if (restage) {
-    if (cur_grp != -1) __syncthreads();  // every warp has finished reading the previous tiles
-    cur_grp = grp_id;
-  for (int idx = threadIdx.x; idx < CP * 16; idx += SH_WARPS * 32) {
-    const int r = idx >> 4, c = idx & 15;
-    const uint32_t off = swz(r, c);
-    if (r < n_c) {
-      const AttnTok& tk = p.k[n_b + r];
-      const AttnTok& tv = p.v[n_b + r];
-      cp_async16(uKc + off, reinterpret_cast<const __nv_bfloat16*>(tk.ptr) + (tk.bdiv > 0 ? tok_off(tk, b_cta) : 0) + h * HD + c * 8);
-      cp_async16(uVc + off, reinterpret_cast<const __nv_bfloat16*>(tv.ptr) + (tv.bdiv > 0 ? tok_off(tv, b_cta) : 0) + h * HD + c * 8);
-    } else {
-      *reinterpret_cast<uint4*>(sKc + off) = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(sVc + off) = make_uint4(0, 0, 0, 0);
-    }
-  }
-  }
-  for (int idx = lane; idx < 16 * 16; idx += 32) {  // queries of this warp's batch row
-    const int r = idx >> 4, c = idx & 15;
-    if (r < n_q)
-      cp_async16(uQ + swz(r, c), reinterpret_cast<const __nv_bfloat16*>(p.q[r].ptr) + tok_off(p.q[r], b) + h * HD + c * 8);
-    else
-      *reinterpret_cast<uint4*>(sQ + swz(r, c)) = make_uint4(0, 0, 0, 0);
-  }
-  for (int idx = lane; idx < BP * 16; idx += 32) {  // per-batch keys / values
-    const int r = idx >> 4, c = idx & 15;
-    const uint32_t off = swz(r, c);
-    if (r < n_b) {
-      cp_async16(uKb + off, reinterpret_cast<const __nv_bfloat16*>(p.k[r].ptr) + tok_off(p.k[r], b) + h * HD + c * 8);
-      cp_async16(uVb + off, reinterpret_cast<const __nv_bfloat16*>(p.v[r].ptr) + tok_off(p.v[r], b) + h * HD + c * 8);
-    } else {
-      *reinterpret_cast<uint4*>(sKb + off) = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(sVb + off) = make_uint4(0, 0, 0, 0);
-    }
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  if (restage) __syncthreads(); else __syncwarp();
-
-  // ---- scores = Q K^T : 16 x (BP + CP), fp32 accumulators ----
-  float sc[2 * NTK][4];
-#pragma unroll
-  for (int j = 0; j < 2 * NTK; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
-#pragma unroll
-  for (int kk = 0; kk < HD / 16; ++kk) {
-    uint32_t a[4];
-    {
-      const int r = (lane & 7) + 8 * ((lane >> 3) & 1), c = 2 * kk + (lane >> 4);
-      ldsm_x4(uQ + swz(r, c), a[0], a[1], a[2], a[3]);
-    }
-#pragma unroll
-    for (int jp = 0; jp < NTK; ++jp) {
-      uint32_t b0, b1, b2, b3;
-      const uint32_t base = jp < NTB ? uKb : uKc;
-      const int r = (jp < NTB ? jp : jp - NTB) * 16 + (lane & 7) + 8 * (lane >> 4), c = 2 * kk + ((lane >> 3) & 1);
-      ldsm_x4(base + swz(r, c), b0, b1, b2, b3);
-      mma_bf16_16816(sc[2 * jp], a, b0, b1);
-      mma_bf16_16816(sc[2 * jp + 1], a, b2, b3);
-    }
-  }
-  // ---- softmax over keys; pad keys of each tile masked ----
-  float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < 2 * NTK; ++j) {
-    const int tile = j >> 1;
-    const int cnt = tile < NTB ? n_b - 16 * tile : n_c - 16 * (tile - NTB);  // valid keys in this tile
-    const int key = 8 * (j & 1) + 2 * t;
-    if (key >= cnt) sc[j][0] = sc[j][2] = -INFINITY;
-    if (key + 1 >= cnt) sc[j][1] = sc[j][3] = -INFINITY;
-    m0 = fmaxf(m0, fmaxf(sc[j][0], sc[j][1]));
-    m1 = fmaxf(m1, fmaxf(sc[j][2], sc[j][3]));
-  }
-  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-  float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-  for (int j = 0; j < 2 * NTK; ++j) {
-    sc[j][0] = exp2f((sc[j][0] - m0) * sl2); sc[j][1] = exp2f((sc[j][1] - m0) * sl2);
-    sc[j][2] = exp2f((sc[j][2] - m1) * sl2); sc[j][3] = exp2f((sc[j][3] - m1) * sl2);
-    l0 += sc[j][0] + sc[j][1];
-    l1 += sc[j][2] + sc[j][3];
-  }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
-
-  // ---- O = P V : 16 x 128 ----
-  float o[HD / 8][4];
-#pragma unroll
-  for (int n = 0; n < HD / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
-#pragma unroll
-  for (int kk = 0; kk < NTK; ++kk) {
-    uint32_t a[4];
-    a[0] = pack_bf16(sc[2 * kk][0] * inv0, sc[2 * kk][1] * inv0);
-    a[1] = pack_bf16(sc[2 * kk][2] * inv1, sc[2 * kk][3] * inv1);
-    a[2] = pack_bf16(sc[2 * kk + 1][0] * inv0, sc[2 * kk + 1][1] * inv0);
-    a[3] = pack_bf16(sc[2 * kk + 1][2] * inv1, sc[2 * kk + 1][3] * inv1);
-    const uint32_t base = kk < NTB ? uVb : uVc;
-#pragma unroll
-    for (int np = 0; np < HD / 16; ++np) {
-      uint32_t b0, b1, b2, b3;
-      const int r = (kk < NTB ? kk : kk - NTB) * 16 + (lane & 7) + 8 * ((lane >> 3) & 1), c = 2 * np + (lane >> 4);
-      ldsm_x4_t(base + swz(r, c), b0, b1, b2, b3);
-      mma_bf16_16816(o[2 * np], a, b0, b1);
-      mma_bf16_16816(o[2 * np + 1], a, b2, b3);
-    }
-  }
-  __syncwarp();
-#pragma unroll
-  for (int n = 0; n < HD / 8; ++n) {  // stage O into the (now dead) Q rows, same swizzle
-    *reinterpret_cast<uint32_t*>(sQ + swz(g, n) + 4 * t) = pack_bf16(o[n][0], o[n][1]);
-    *reinterpret_cast<uint32_t*>(sQ + swz(g + 8, n) + 4 * t) = pack_bf16(o[n][2], o[n][3]);
-  }
-  __syncwarp();
-  if (live) {
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-    const int D = p.n_head * HD;
-    for (int idx = lane; idx < n_q * 16; idx += 32) {
+    const int b_raw = bx * SH_WARPS + warp;
+    const bool live = b_raw < p.B;
+    const int b = live ? b_raw : p.B - 1;  // idle warps shadow the last row (they must reach the barriers) and store nothing
+    // keys / values shared by the CTA's batch rows: batch-constant rows (bstride 0) or one row per group of bdiv batch rows
+    // (bdiv is a multiple of SH_WARPS, so the 8 rows of a block belong to one group)
+    const int b_cta = min(bx * SH_WARPS, p.B - 1);
+    const int grp_id = p.k[n_b].bdiv > 0 ? b_cta / p.k[n_b].bdiv : 0;
+    const bool restage = grp_id != cur_grp;
+    if (restage) {
+      if (cur_grp != -1) __syncthreads();  // every warp has finished reading the previous tiles
+      cur_grp = grp_id;
+      for (int idx = threadIdx.x; idx < CP * 16; idx += SH_WARPS * 32) {
+        const int r = idx >> 4, c = idx & 15;
+        const uint32_t off = swz(r, c);
+        if (r < n_c) {
+          const AttnTok& tk = p.k[n_b + r];
+          const AttnTok& tv = p.v[n_b + r];
+          cp_async16(uKc + off, reinterpret_cast<const __nv_bfloat16*>(tk.ptr) + (tk.bdiv > 0 ? tok_off(tk, b_cta) : 0) + h * HD + c * 8);
+          cp_async16(uVc + off, reinterpret_cast<const __nv_bfloat16*>(tv.ptr) + (tv.bdiv > 0 ? tok_off(tv, b_cta) : 0) + h * HD + c * 8);
+        } else {
+          *reinterpret_cast<uint4*>(sKc + off) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(sVc + off) = make_uint4(0, 0, 0, 0);
+        }
+      }
+      }
+    for (int idx = lane; idx < 16 * 16; idx += 32) {  // queries of this warp's batch row
       const int r = idx >> 4, c = idx & 15;
-      *reinterpret_cast<uint4*>(out + (static_cast<size_t>(r) * p.B + b) * D + h * HD + c * 8) = *reinterpret_cast<const uint4*>(sQ + swz(r, c));
+      if (r < n_q)
+        cp_async16(uQ + swz(r, c), reinterpret_cast<const __nv_bfloat16*>(p.q[r].ptr) + tok_off(p.q[r], b) + h * HD + c * 8);
+      else
+        *reinterpret_cast<uint4*>(sQ + swz(r, c)) = make_uint4(0, 0, 0, 0);
     }
-  }
-  __syncwarp();  // the copy-out has read this warp's tiles before the next block's loads overwrite them
+    for (int idx = lane; idx < BP * 16; idx += 32) {  // per-batch keys / values
+      const int r = idx >> 4, c = idx & 15;
+      const uint32_t off = swz(r, c);
+      if (r < n_b) {
+        cp_async16(uKb + off, reinterpret_cast<const __nv_bfloat16*>(p.k[r].ptr) + tok_off(p.k[r], b) + h * HD + c * 8);
+        cp_async16(uVb + off, reinterpret_cast<const __nv_bfloat16*>(p.v[r].ptr) + tok_off(p.v[r], b) + h * HD + c * 8);
+      } else {
+        *reinterpret_cast<uint4*>(sKb + off) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(sVb + off) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (restage) __syncthreads(); else __syncwarp();
+
+    // ---- scores = Q K^T : 16 x (BP + CP), fp32 accumulators ----
+    float sc[2 * NTK][4];
+#pragma unroll
+    for (int j = 0; j < 2 * NTK; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; ++kk) {
+      uint32_t a[4];
+      {
+        const int r = (lane & 7) + 8 * ((lane >> 3) & 1), c = 2 * kk + (lane >> 4);
+        ldsm_x4(uQ + swz(r, c), a[0], a[1], a[2], a[3]);
+      }
+#pragma unroll
+      for (int jp = 0; jp < NTK; ++jp) {
+        uint32_t b0, b1, b2, b3;
+        const uint32_t base = jp < NTB ? uKb : uKc;
+        const int r = (jp < NTB ? jp : jp - NTB) * 16 + (lane & 7) + 8 * (lane >> 4), c = 2 * kk + ((lane >> 3) & 1);
+        ldsm_x4(base + swz(r, c), b0, b1, b2, b3);
+        mma_bf16_16816(sc[2 * jp], a, b0, b1);
+        mma_bf16_16816(sc[2 * jp + 1], a, b2, b3);
+      }
+    }
+    // ---- softmax over keys; pad keys of each tile masked ----
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 2 * NTK; ++j) {
+      const int tile = j >> 1;
+      const int cnt = tile < NTB ? n_b - 16 * tile : n_c - 16 * (tile - NTB);  // valid keys in this tile
+      const int key = 8 * (j & 1) + 2 * t;
+      if (key >= cnt) sc[j][0] = sc[j][2] = -INFINITY;
+      if (key + 1 >= cnt) sc[j][1] = sc[j][3] = -INFINITY;
+      m0 = fmaxf(m0, fmaxf(sc[j][0], sc[j][1]));
+      m1 = fmaxf(m1, fmaxf(sc[j][2], sc[j][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2 * NTK; ++j) {
+      sc[j][0] = exp2f((sc[j][0] - m0) * sl2); sc[j][1] = exp2f((sc[j][1] - m0) * sl2);
+      sc[j][2] = exp2f((sc[j][2] - m1) * sl2); sc[j][3] = exp2f((sc[j][3] - m1) * sl2);
+      l0 += sc[j][0] + sc[j][1];
+      l1 += sc[j][2] + sc[j][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+
+    // ---- O = P V : 16 x 128 ----
+    float o[HD / 8][4];
+#pragma unroll
+    for (int n = 0; n < HD / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < NTK; ++kk) {
+      uint32_t a[4];
+      a[0] = pack_bf16(sc[2 * kk][0] * inv0, sc[2 * kk][1] * inv0);
+      a[1] = pack_bf16(sc[2 * kk][2] * inv1, sc[2 * kk][3] * inv1);
+      a[2] = pack_bf16(sc[2 * kk + 1][0] * inv0, sc[2 * kk + 1][1] * inv0);
+      a[3] = pack_bf16(sc[2 * kk + 1][2] * inv1, sc[2 * kk + 1][3] * inv1);
+      const uint32_t base = kk < NTB ? uVb : uVc;
+#pragma unroll
+      for (int np = 0; np < HD / 16; ++np) {
+        uint32_t b0, b1, b2, b3;
+        const int r = (kk < NTB ? kk : kk - NTB) * 16 + (lane & 7) + 8 * ((lane >> 3) & 1), c = 2 * np + (lane >> 4);
+        ldsm_x4_t(base + swz(r, c), b0, b1, b2, b3);
+        mma_bf16_16816(o[2 * np], a, b0, b1);
+        mma_bf16_16816(o[2 * np + 1], a, b2, b3);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int n = 0; n < HD / 8; ++n) {  // stage O into the (now dead) Q rows, same swizzle
+      *reinterpret_cast<uint32_t*>(sQ + swz(g, n) + 4 * t) = pack_bf16(o[n][0], o[n][1]);
+      *reinterpret_cast<uint32_t*>(sQ + swz(g + 8, n) + 4 * t) = pack_bf16(o[n][2], o[n][3]);
+    }
+    __syncwarp();
+    if (live) {
+      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+      const int D = p.n_head * HD;
+      for (int idx = lane; idx < n_q * 16; idx += 32) {
+        const int r = idx >> 4, c = idx & 15;
+        *reinterpret_cast<uint4*>(out + (static_cast<size_t>(r) * p.B + b) * D + h * HD + c * 8) = *reinterpret_cast<const uint4*>(sQ + swz(r, c));
+      }
+    }
+    __syncwarp();  // the copy-out has read this warp's tiles before the next block's loads overwrite them
   }  // bx
 }
 
