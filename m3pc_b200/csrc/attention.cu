@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(SH_WARPS * 32) attention_mma_shared_kernel(con
           *reinterpret_cast<uint4*>(sVc + off) = make_uint4(0, 0, 0, 0);
         }
       }
-      }
+    }
     for (int idx = lane; idx < 16 * 16; idx += 32) {  // queries of this warp's batch row
       const int r = idx >> 4, c = idx & 15;
       if (r < n_q)
