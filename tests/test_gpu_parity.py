@@ -657,3 +657,13 @@ def test_zeroshot_candidate_draws_per_environment(precision):
     assert not torch.equal(d2[0, 0], d2[0, 1]) and not torch.equal(d2[0, 0], d2[1, 0])
     _, d3 = L.action_piid_draws_batch(hists, 4096, rtg=2.0)
     assert not torch.equal(d3, d2)  # the plan counter advances the Philox key
+
+
+def test_plan_with_fused_residual_layernorm_forced_at_small_shapes(monkeypatch):
+    """The engine uses the fused residual GEMM + LayerNorm kernel from 1024 rows up; M3PC_FUSED_LN_MIN_ROWS=129 forces it at
+    test sizes so the oracle comparison covers its wiring (out-projection + norm2, linear2 + next norm1 / final encoder norm,
+    the table-residual form of the shared-history block, the restricted decoder layer)."""
+    monkeypatch.setenv("M3PC_FUSED_LN_MIN_ROWS", "129")
+    test_plan_internals_vs_fp64_oracle("bf16", "walker2d", "critic_lambda_guiding", 1.0, 130, 50)
+    test_plan_internals_vs_fp64_oracle("bf16", "hopper", "rtg_guiding", 0.01, 200, 50)
+    test_env_batched_plan_rows_equal_single_env_plans("bf16", "walker2d", "critic_lambda_guiding", 1.0, 96, 5, 0)
