@@ -65,17 +65,27 @@ __global__ void __launch_bounds__(256) embed_kernel(const __grid_constant__ Embe
       const float* src = tk.src + static_cast<size_t>(srow) * tk.bstride;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) acc[j] = __ldg(reinterpret_cast<const float4*>(tk.cvec + j * 128 + lane * 4));
+      // the d input features of the row: one coalesced (and, where the tokenizer applies, normalised) load per 32 features,
+      // broadcast with shuffles -- not d dependent scalar loads in the FMA chain
+      for (int i0 = 0; i0 < tk.d; i0 += 32) {
+        float xv = 0.f;
+        if (i0 + lane < tk.d) {
+          xv = __ldg(src + i0 + lane);
+          if (tk.nmean != nullptr) xv = (xv - __ldg(tk.nmean + i0 + lane)) / __ldg(tk.nstd + i0 + lane);
+        }
+        const int n_i = min(32, tk.d - i0);
 #pragma unroll 4
-      for (int i = 0; i < tk.d; ++i) {
-        float xi = __ldg(src + i);
-        if (tk.nmean != nullptr) xi = (xi - __ldg(tk.nmean + i)) / __ldg(tk.nstd + i);
+        for (int ii = 0; ii < n_i; ++ii) {
+          const float xi = __shfl_sync(0xffffffffu, xv, ii);
+          const int i = i0 + ii;
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-          const float4 w = __ldg(reinterpret_cast<const float4*>(tk.wt + static_cast<size_t>(i) * D + j * 128 + lane * 4));
-          acc[j].x = fmaf(xi, w.x, acc[j].x);
-          acc[j].y = fmaf(xi, w.y, acc[j].y);
-          acc[j].z = fmaf(xi, w.z, acc[j].z);
-          acc[j].w = fmaf(xi, w.w, acc[j].w);
+          for (int j = 0; j < NJ; ++j) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(tk.wt + static_cast<size_t>(i) * D + j * 128 + lane * 4));
+            acc[j].x = fmaf(xi, w.x, acc[j].x);
+            acc[j].y = fmaf(xi, w.y, acc[j].y);
+            acc[j].z = fmaf(xi, w.z, acc[j].z);
+            acc[j].w = fmaf(xi, w.w, acc[j].w);
+          }
         }
       }
       warp_layernorm<NJ>(acc, gamma, beta, lane, o);
