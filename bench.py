@@ -126,56 +126,113 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
+# ------------------------------------------------------------------------------------------------ reference arms
 def cpu_planner(w, shape):
+    """(planner, kind): the UNMODIFIED reference ``Learner`` (oracle/_ref staged by oracle/stage_ref.py, or /root/reference in
+    the dev container) -> kind "reference"; only if neither exists, the oracle port -> kind "port"."""
     import torch
     from m3pc_b200 import synthetic as syn
+    from oracle import ref_harness as rh
+    if rh.available():
+        return rh.build_learner(shape, guidance=w["guidance"], n_cand=w["n_cand"], temperature=w["temperature"], device="cpu"), "reference"
     from oracle import planner_oracle as po
     crit = w["guidance"] != "rtg_guiding"
-    return po.from_synthetic(shape, syn.make_state_dict(shape, 0), syn.make_tokenizer_stats(shape, 1), dtype=torch.float32,
-                             critic_np=syn.make_critic_state_dict(shape) if crit else None, obs_norm=syn.make_obs_norm(shape) if crit else None,
-                             action_samples=w["n_cand"], temperature=w["temperature"], plan_guidance=w["guidance"])
+    P = po.from_synthetic(shape, syn.make_state_dict(shape, 0), syn.make_tokenizer_stats(shape, 1), dtype=torch.float32,
+                          critic_np=syn.make_critic_state_dict(shape) if crit else None, obs_norm=syn.make_obs_norm(shape) if crit else None,
+                          action_samples=w["n_cand"], temperature=w["temperature"], plan_guidance=w["guidance"])
+    return P, "port"
 
 
 def time_cpu(w, shape, steps, warmup, budget_s=None):
-    """Oracle port of Learner.action_sample on the host cores; returns (plans/s, per-plan seconds list, threads)."""
+    """``Learner.action_sample(history, plan=True, eval=True, rtg=3.0)`` (research/finetune_omtm/learner.py:329-417) on the host
+    cores, all threads; returns (plans/s, per-plan seconds, threads, kind)."""
     import numpy as np
     import torch
     from m3pc_b200 import synthetic as syn
     torch.set_num_threads(os.cpu_count() or 1)
-    P = cpu_planner(w, shape)
+    P, kind = cpu_planner(w, shape)
     T, A, N = shape.traj_length, shape.act_dim, w["n_cand"]
     rs = np.random.RandomState(7)
     times = []
     t_start = time.perf_counter()
     for i in range(warmup + steps):
         hist = syn.make_history(shape, seed=100 + i, path_length=50)
-        eps = torch.from_numpy(rs.randn(N, 1, T, 1, A).astype(np.float32))
-        q = torch.from_numpy(rs.exponential(1.0, N).astype(np.float32))
+        if kind == "port":
+            kw = dict(eps=torch.from_numpy(rs.randn(N, 1, T, 1, A).astype(np.float32)), q=torch.from_numpy(rs.exponential(1.0, N).astype(np.float32)))
+        else:
+            kw = {}  # the reference draws its own noise from torch's generator
         t0 = time.perf_counter()
         with torch.no_grad():
-            P.action_sample(hist, plan=True, eval=True, rtg=3.0, eps=eps, q=q)
+            P.action_sample(hist, plan=True, eval=True, rtg=3.0, **kw)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
         if budget_s is not None and i >= warmup and time.perf_counter() - t_start > budget_s:
             break
-    return len(times) / sum(times), times, torch.get_num_threads()
+    return len(times) / sum(times), times, torch.get_num_threads(), kind
+
+
+def _kind_text(kind):
+    return ("UNMODIFIED reference Learner.action_sample from oracle/_ref" if kind == "reference" else
+            "oracle port of Learner.action_sample (the reference is not staged on this box)")
+
+
+def time_gpu_library(w, shape, dev, steps=12, warmup=3):
+    """The "stock PyTorch on the same B200" bar (SURVEY.md section 8d "Also time"): the UNMODIFIED reference objects moved to
+    the GPU (``cfg.device = "cuda"``, finetune.py:154) -- cuBLAS / ATen library kernels, one plan per call as the reference
+    runs it -- in fp32, with TF32 matmuls allowed, and under bf16 autocast.  CUDA events around each plan (the call ends in
+    the device-side selection; the host sync the caller's ``.cpu()`` adds is not counted).  Returns None when the reference
+    is not staged."""
+    import torch
+    from m3pc_b200 import synthetic as syn
+    from oracle import ref_harness as rh
+    if not rh.available():
+        return None
+    L = rh.build_learner(shape, guidance=w["guidance"], n_cand=w["n_cand"], temperature=w["temperature"], device=str(dev))
+    hists = [syn.make_history(shape, seed=100 + i, path_length=50) for i in range(steps + warmup)]
+    out = {"api": "research.finetune_omtm.learner.Learner.action_sample(device='cuda'), one plan per call (the reference has no "
+                  "multi-environment call)", "unit": UNIT, "plans_timed": steps}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+
+    def run(mode):
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = mode == "tf32"
+        ms = []
+        for i, hist in enumerate(hists):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "bf16_autocast"):
+                L.action_sample(hist, plan=True, eval=True, rtg=3.0)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= warmup:
+                ms.append(e0.elapsed_time(e1))
+        return {"value": 1e3 * len(ms) / sum(ms), "p50_ms": statistics.median(ms)}
+
+    try:
+        for mode in ("fp32", "tf32", "bf16_autocast"):
+            try:
+                out[mode] = run(mode)
+            except Exception as exc:  # a library path that does not run under this mode is reported, not hidden
+                out[mode] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    return out
 
 
 def run_reference(args, w, shape, rank):
     if rank != 0:
         return
     steps, warmup = args.steps, args.warmup
-    val, times, threads = time_cpu(w, shape, steps, warmup)
+    val, times, threads, kind = time_cpu(w, shape, steps, warmup, budget_s=240.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times), "warmup": warmup,
         "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": args.workload, "candidates": w["n_cand"], "horizon": 4, "guidance": w["guidance"], "env_shapes": w["env"],
-                   "model": f"D={shape.n_embd},heads={shape.n_head},enc={shape.n_enc_layer},dec={shape.n_dec_layer},T={shape.traj_length}"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{len(times)} full plans (oracle port of Learner.action_sample, torch CPU fp32, {threads} threads of {os.cpu_count()} host cpus)"},
+                   "model": f"D={shape.n_embd},heads={shape.n_head},enc={shape.n_enc_layer},dec={shape.n_dec_layer},T={shape.traj_length}",
+                   "plans_per_step": 1, "step": "one window per plan (Learner.action_sample), the reference's only call shape"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"{len(times)} full plans ({_kind_text(kind)}, torch CPU fp32, {threads} threads of {os.cpu_count()} host cpus)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "p50_ms": 1e3 * statistics.median(times),
     }
@@ -346,9 +403,9 @@ def run_ours(args, w, shape, rank, local_rank, world):
         pass
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cval, ctimes, threads = time_cpu(w, shape, steps=8, warmup=1, budget_s=25.0)
-        cpu = {"value": cval, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{len(ctimes)} full plans of the same workload (oracle port of Learner.action_sample, torch CPU fp32, {threads} threads of {os.cpu_count()} host cpus)"}
+        cval, ctimes, threads, kind = time_cpu(w, shape, steps=8, warmup=1, budget_s=25.0)
+        cpu = {"value": cval, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": f"{len(ctimes)} full plans of the same workload ({_kind_text(kind)}, torch CPU fp32, {threads} threads of {os.cpu_count()} host cpus)"}
     win_bytes = 4 * T * (shape.obs_dim + A + 2) * E_head
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * dev_s / K,

@@ -88,8 +88,24 @@ int m3pc_destroy(m3pc_handle_t h);
  * `data` is a HOST pointer to `count` fp32 values in the tensor's row-major order.
  */
 int m3pc_set_param(m3pc_handle_t h, const char* name, const float* data, size_t count);
-/* Packs weights for the device (bf16 K-major copies, fused constants). Must follow the last m3pc_set_param. */
+/* Packs weights for the device (bf16 K-major copies, fused constants). Must follow the last m3pc_set_param.
+ * The handle keeps the host copies, so a later m3pc_set_param of ANY subset of the names followed by another
+ * m3pc_finalize_params re-packs with the new values (the reference mutates parameters in place on every optimiser step,
+ * finetune_omtm/learner.py:506-538).  Both calls drop every CUDA graph the handle has captured: a graph freezes the
+ * parameter addresses and the scalar statistics it was captured with. */
 int m3pc_finalize_params(m3pc_handle_t h);
+
+/* Selects between RESULT-EQUIVALENT launch sequences of the handle (parity tests compare them; none changes what is
+ * computed).  Unknown names fail with M3PC_ERR_INVALID.  Names and defaults:
+ *   "graphs" 1                 capture m3pc_plan into a CUDA graph and replay it (0: launch every kernel eagerly)
+ *   "pdl" 1                    programmatic dependent launch between consecutive kernels (process-wide)
+ *   "fused_b1" 1               one cooperative kernel for a B = 1 forward (0: one launch per op)
+ *   "fused_ln" 1               residual GEMM + LayerNorm in one kernel (0: GEMM, then LayerNorm kernel)
+ *   "fused_ln_min_rows" 1024   smallest GEMM (rows) the fused kernel is used for (>= 129)
+ *   "restrict_deep_decoder" 1  decoders with > 1 layer: last layer on the consumed rows only (0: every row)
+ *   "dedupe_history" 1         first encoder block: history tokens once per environment (0: once per candidate)
+ * The release library reads no environment variable. */
+int m3pc_set_option(m3pc_handle_t h, const char* name, int32_t value);
 
 /*
  * omtm.forward(trajectories, masks)  (mtm_model.py:593-607), P = 1 token per time step.

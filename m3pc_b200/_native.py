@@ -11,7 +11,9 @@ import subprocess
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libm3pc.so")
+#: M3PC_LIB=tuning selects the -DM3PC_TUNING build (``make -C m3pc_b200/csrc tuning``) that tools/ use for A/B experiments;
+#: it is the only place environment switches exist.  Everything else -- tests, bench.py, smoke() -- loads the release library.
+LIB_PATH = os.path.join(HERE, "libm3pc_tuning.so" if os.environ.get("M3PC_LIB") == "tuning" else "libm3pc.so")
 CSRC = os.path.join(HERE, "csrc")
 
 OK = 0
@@ -29,7 +31,7 @@ GUIDANCE = {
 
 #: every symbol include/m3pc.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = (
-    "m3pc_last_error", "m3pc_version", "m3pc_create", "m3pc_destroy", "m3pc_set_param", "m3pc_finalize_params",
+    "m3pc_last_error", "m3pc_version", "m3pc_create", "m3pc_destroy", "m3pc_set_param", "m3pc_finalize_params", "m3pc_set_option",
     "m3pc_forward", "m3pc_plan", "m3pc_merge_partials", "m3pc_backward_plan", "m3pc_backward_plan_draws", "m3pc_ring_append", "m3pc_ring_windows", "m3pc_gemm_bf16", "m3pc_gemm_bf16_grouped", "m3pc_gemm_ln_bf16", "m3pc_gemm_fp32",
     "m3pc_layernorm", "m3pc_attention", "m3pc_last_device_ms", "m3pc_last_launch_count", "m3pc_set_profile", "m3pc_get_profile",
 )
@@ -64,7 +66,8 @@ _lib: Optional[C.CDLL] = None
 
 def build(verbose: bool = False) -> str:
     """Compile the library in-tree with nvcc for sm_100a (``make -C m3pc_b200/csrc``)."""
-    res = subprocess.run(["make", "-C", CSRC, "-j8"], capture_output=True, text=True)
+    target = ["tuning"] if os.environ.get("M3PC_LIB") == "tuning" else []
+    res = subprocess.run(["make", "-C", CSRC, "-j8"] + target, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         print(res.stdout[-4000:])
         print(res.stderr[-4000:])
@@ -92,6 +95,7 @@ def lib() -> C.CDLL:
     L.m3pc_destroy.argtypes = [vp]
     L.m3pc_set_param.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
     L.m3pc_finalize_params.argtypes = [vp]
+    L.m3pc_set_option.argtypes = [vp, C.c_char_p, i32]
     L.m3pc_forward.argtypes = [vp, i32, f32p, f32p, f32p, f32p, vp, f32p, f32p, f32p, f32p, f32p, vp]
     L.m3pc_plan.argtypes = [vp, C.POINTER(PlanArgs), vp]
     L.m3pc_merge_partials.argtypes = [vp, f32p, i32, C.c_float, f32p, f32p, vp, vp]

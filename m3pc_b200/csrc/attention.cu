@@ -104,10 +104,10 @@ int launch_simple(const AttnParams& p, cudaStream_t st) {
   const size_t smem = (static_cast<size_t>(p.n_q) * QS + static_cast<size_t>(p.n_kv) * QS + static_cast<size_t>(p.n_kv) * HD +
                        static_cast<size_t>(p.n_q) * (p.n_kv + 1)) * sizeof(float);
   M3PC_REQUIRE(smem <= 200 * 1024, "attention: sequence too long for the shared-memory resident kernel");
-  static size_t configured = 0;
-  if (smem > configured) {
+  static PerDevice<size_t> configured;
+  if (smem > configured.here()) {
     M3PC_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = smem;
+    configured.here() = smem;
   }
   M3PC_CHECK_CUDA(launch_k(attention_kernel, dim3(p.B * p.n_head), dim3(ATT_THREADS), smem, st, p));
   M3PC_CHECK_LAUNCH();
@@ -139,7 +139,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ uint32_t swz(int r, int c) { return static_cast<uint32_t>(r * 256 + ((c ^ (r & 7)) << 4)); }
 
 constexpr int MMA_WARPS = 4;  // (b, head) pairs per CTA
-const bool g_attn_shared = getenv("M3PC_ATTN_SHARED") == nullptr || getenv("M3PC_ATTN_SHARED")[0] != '0';  // M3PC_ATTN_SHARED=0: legacy staging
+const bool g_attn_shared = tune_env("M3PC_ATTN_SHARED") == nullptr || tune_env("M3PC_ATTN_SHARED")[0] != '0';  // tuning build, M3PC_ATTN_SHARED=0: legacy staging
 
 // NTQ = ceil(n_q / 16) query tiles, NTK = ceil(n_kv / 16) key tiles
 template <int NTQ, int NTK>
@@ -437,16 +437,16 @@ __global__ void __launch_bounds__(SH_WARPS * 32) attention_mma_shared_kernel(con
 template <int NTB, int NTC>
 int launch_mma_shared(const AttnParams& p, cudaStream_t st) {
   constexpr int smem = 2 * NTC * 16 * 256 + SH_WARPS * (16 + 2 * NTB * 16) * 256;
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice<bool> configured;
+  if (!configured.here()) {
     M3PC_CHECK_CUDA(cudaFuncSetAttribute(attention_mma_shared_kernel<NTB, NTC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured.here() = true;
   }
   const int nblk = ceil_div(p.B, SH_WARPS);
   const int per_sm = std::max(1, (227 * 1024) / (smem + 1024));
   // one wave of resident CTAs, each walking a range of row blocks -- once there are enough blocks for the ranges to balance
   // (>= 4 per CTA); smaller problems keep one block per CTA
-  const int wave = std::max(1, ceil_div(per_sm * 148, p.n_head));
+  const int wave = std::max(1, ceil_div(per_sm * device_num_sms(), p.n_head));
   const int gx = nblk >= 4 * wave ? wave : nblk;
   M3PC_CHECK_CUDA(launch_k(attention_mma_shared_kernel<NTB, NTC>, dim3(gx, p.n_head), dim3(SH_WARPS * 32), smem, st, p));
   M3PC_CHECK_LAUNCH();
@@ -456,10 +456,10 @@ int launch_mma_shared(const AttnParams& p, cudaStream_t st) {
 template <int NTQ, int NTK>
 int launch_mma(const AttnParams& p, cudaStream_t st) {
   constexpr int smem = MMA_WARPS * (NTQ + 2 * NTK) * 16 * 256;
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice<bool> configured;
+  if (!configured.here()) {
     M3PC_CHECK_CUDA(cudaFuncSetAttribute(attention_mma_kernel<NTQ, NTK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured.here() = true;
   }
   M3PC_CHECK_CUDA(launch_k(attention_mma_kernel<NTQ, NTK>, dim3(ceil_div(p.B * p.n_head, MMA_WARPS)), dim3(MMA_WARPS * 32), smem, st, p));
   M3PC_CHECK_LAUNCH();

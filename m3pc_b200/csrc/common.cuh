@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/m3pc.h"
@@ -127,6 +128,32 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
 }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- per-device launch bookkeeping ---------------------------------------------------------------------------------------
+// cudaFuncSetAttribute and the SM count belong to a DEVICE, not to the process: a second handle on another GPU of the same
+// process must configure its own copy of every kernel.  Launchers keep `static PerDevice<...> configured;` and index it with
+// current_device().
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d < 0 || d >= kMaxDevices) ? 0 : d;
+}
+template <typename T>
+struct PerDevice {
+  T v[kMaxDevices] = {};
+  T& here() { return v[current_device()]; }
+};
+int device_num_sms();  // multiprocessors of the current device (cached per device; engine.cu)
+
+// Tuning switches (environment variables that pick between result-equivalent kernels, or that time a kernel with parts
+// skipped) exist only in the -DM3PC_TUNING build used by tools/; the release library reads no environment variable at all.
+// What tests and callers may legitimately choose between goes through m3pc_set_option (include/m3pc.h).
+#ifdef M3PC_TUNING
+inline const char* tune_env(const char* name) { return getenv(name); }
+#else
+inline const char* tune_env(const char*) { return nullptr; }
+#endif
 
 // ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------------
 // Every kernel of a plan is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it may be scheduled while

@@ -90,8 +90,7 @@ __global__ void __launch_bounds__(256) embed_kernel(const __grid_constant__ Embe
       }
       warp_layernorm<NJ>(acc, gamma, beta, lane, o);
     }
-    const size_t row = p.cpt > 0 ? static_cast<size_t>(b / p.cpt) * 128 + static_cast<size_t>(b % p.cpt) * p.n_tok + s
-                                 : static_cast<size_t>(s) * p.B + b;
+    const size_t row = static_cast<size_t>(s) * p.B + b;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       st4(x + row * D + j * 128 + lane * 4, acc[j]);

@@ -22,6 +22,16 @@ bool g_use_pdl = true;
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 
+int device_num_sms() {
+  static PerDevice<int> sms;
+  int& n = sms.here();
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 0;
+  }
+  return n;
+}
+
 namespace {
 
 const char* kMod[4] = {"states", "actions", "rewards", "returns"};
@@ -133,7 +143,6 @@ struct m3pc_engine {
   bool fuse_ln = true;        // residual GEMM + LayerNorm in one kernel (gemm_ln.cu); M3PC_NO_FUSED_LN=1 disables
   int fuse_ln_min_rows = 1024;  // M3PC_FUSED_LN_MIN_ROWS overrides (the kernel-level parity tests call it at any size)
   bool restrict_deep = true;  // decoders with > 1 layer: last layer on the consumed rows only (M3PC_DEC_FULL=1 disables)
-  bool use_mega = false;  // encoder megakernel: measured slower than the per-op path at <= 1024 rows per chunk; M3PC_MEGA=1 enables
   // planner buffers
   DevBuf p1_mu, p1_std, cand, pred_states, pred_rewards, pred_returns, sa, qa, qb1, qb2, qvals, J, filled, e_mu, e_std;
 
@@ -163,9 +172,17 @@ struct m3pc_engine {
   std::vector<double> prof_flops;
   size_t prof_used = 0;
 
-  ~m3pc_engine() {
+  // Every captured plan has the weight / tokenizer / critic arena addresses and the scalar statistics baked into its kernel
+  // nodes: whenever any of those may change (m3pc_set_param, m3pc_finalize_params, m3pc_set_option) the graphs are dropped
+  // and the next plan re-captures.
+  void drop_graphs() {
     for (auto& kv : plan_graphs)
       if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    plan_graphs.clear();
+  }
+
+  ~m3pc_engine() {
+    drop_graphs();
     if (cap_stream) cudaStreamDestroy(cap_stream);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -268,6 +285,10 @@ int build_const_rows(m3pc_engine* e);
 
 int finalize(m3pc_engine* e) {
   const size_t D = e->D, T = e->T;
+  // the arenas are about to be freed and re-allocated: no graph captured against the old addresses may survive, and no
+  // kernel still reading them may be in flight
+  M3PC_CHECK_CUDA(cudaDeviceSynchronize());
+  e->drop_graphs();
   Packer pk;
   pk.off = &e->off_f32;
   pk.off16 = &e->off_bf16;
@@ -425,8 +446,7 @@ int finalize(m3pc_engine* e) {
     e->obs_mean = f("critic.obs_mean");
     e->obs_std = f("critic.obs_std");
   }
-  e->staged.clear();
-  e->finalized = true;
+  e->finalized = true;  // `staged` is kept: a later m3pc_set_param of a subset + finalize re-packs (include/m3pc.h)
   if (e->Ld == 1) M3PC_TRY(build_const_rows(e));
   return M3PC_OK;
 }
@@ -1005,7 +1025,7 @@ int forward_chunk(m3pc_engine* e, const FwdIO& io, int b0, int Bc, cudaStream_t 
     fp.QKV = e->QKV.as<__nv_bfloat16>(); fp.ATT = e->ATT.as<__nv_bfloat16>(); fp.HID = e->HID.as<__nv_bfloat16>();
     fp.Y = e->Y.as<__nv_bfloat16>(); fp.Y2 = e->Y2.as<__nv_bfloat16>();
     fp.bar = e->fb_bar.as<unsigned>();
-    { static const bool tr = getenv("M3PC_FB_TRACE") != nullptr; fp.trace = tr ? 1 : 0; }
+    { static const bool tr = tune_env("M3PC_FB_TRACE") != nullptr; fp.trace = tr ? 1 : 0; }
     // the actor head is folded into the kernel's last phase; the MLP heads of the other modalities keep their own launches
     FwdIO io_rest = io;
     if (io.out_mu != nullptr && need.nt[M3PC_ACTIONS] > 0) {
@@ -1046,15 +1066,10 @@ int forward_chunk(m3pc_engine* e, const FwdIO& io, int b0, int Bc, cudaStream_t 
     tk.d = d;
   }
   const LayerW& first = e->Le > 0 ? e->enc.layers[0] : e->dec.layers[0];
-  // big batches: candidate-major tiles + the encoder megakernel (encoder_mega.cu); otherwise one launch per op
-  const int cpt = encoder_mega_cpt(S);
-  const bool mega = e->bf16 && e->use_mega && D == 512 && cpt > 0 && e->Le >= 1 && e->Le <= 4 && Bc >= 32 &&
-                    static_cast<size_t>(ceil_div(ceil_div(Bc, cpt), 2)) * 256 <= static_cast<size_t>(4) * T * e->chunk + 128;
-  ep.cpt = mega ? cpt : 0;
   // shared-history analysis: the leading encoder tokens whose source row is shared by whole groups of batch rows (one window
   // for the whole batch: bstride 0; one window per environment: bdiv rows each) -- the chunk must hold whole groups
   int n_sh = 0, grp = 0;
-  if (e->dedupe_history && !mega && e->Le >= 1 && Bc >= 64) {
+  if (e->dedupe_history && e->Le >= 1 && Bc >= 64) {
     for (int s = 0; s < S; ++s) {
       const EmbedTok& tk = ep.tok[s];
       const int g = tk.bdiv > 0 ? tk.bdiv : (tk.bstride == 0 ? Bc : 0);
@@ -1089,25 +1104,8 @@ int forward_chunk(m3pc_engine* e, const FwdIO& io, int b0, int Bc, cudaStream_t 
   }
   void* enc_out = e->Le > 0 ? e->ENC.p : e->Y.p;
 
-  if (mega) {
-    EncoderMegaArgs ma{};
-    ma.D = D; ma.S = S; ma.B = Bc; ma.n_layers = e->Le;
-    for (int l = 0; l < e->Le; ++l) {
-      const LayerW& w = e->enc.layers[l];
-      EncoderMegaLayer& m = ma.layer[l];
-      m.in_w = w.in_w16; m.out_w = w.out_w16; m.l1_w = w.l1_w16; m.l2_w = w.l2_w16;
-      m.in_b = w.in_b; m.out_b = w.out_b; m.l1_b = w.l1_b; m.l2_b = w.l2_b;
-      m.n2_w = w.n2_w; m.n2_b = w.n2_b;
-      m.post_w = l + 1 < e->Le ? e->enc.layers[l + 1].n1_w : e->enc.norm_w;
-      m.post_b = l + 1 < e->Le ? e->enc.layers[l + 1].n1_b : e->enc.norm_b;
-    }
-    ma.X = e->X.as<float>(); ma.Y = e->Y.as<__nv_bfloat16>(); ma.QKV = e->QKV.as<__nv_bfloat16>();
-    ma.ATT = e->ATT.as<__nv_bfloat16>(); ma.HID = e->HID.as<__nv_bfloat16>(); ma.ENC = e->ENC.as<__nv_bfloat16>();
-    M3PC_TRY(launch_encoder_mega(ma, st));
-  }
-
   // ---- encoder stack (mtm_model.py:379-391, 619-644) ----
-  for (int l = 0; l < (mega ? 0 : e->Le); ++l) {
+  for (int l = 0; l < e->Le; ++l) {
     // the LayerNorm that follows the block (next block's norm1, or the final encoder norm -> ENC) rides on its linear2
     PostLn post;
     if (l + 1 < e->Le)
@@ -1306,11 +1304,7 @@ int plan(m3pc_engine* e, const m3pc_plan_args_t* a, cudaStream_t st) {
   key.discount = a->discount; key.temperature = a->temperature; key.lmbda = a->lmbda;
   key.ws = a->win_states; key.wa = a->win_actions; key.wr = a->win_rewards; key.wt = a->win_returns_tok;
   key.ev = a->out_eval_action; key.sm = a->out_sample_action; key.pt = a->out_partials;
-  if (e->plan_graphs.size() > 64) {  // callers that keep changing buffers would otherwise grow the cache without bound
-    for (auto& kv : e->plan_graphs)
-      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-    e->plan_graphs.clear();
-  }
+  if (e->plan_graphs.size() > 64) e->drop_graphs();  // callers that keep changing buffers would otherwise grow the cache without bound
   m3pc_engine::PlanGraph& pg = e->plan_graphs[key];
   if (pg.exec == nullptr) {
     if (pg.seen++ < 1) {  // first sighting: run eagerly (also performs every lazy cudaFuncSetAttribute)
@@ -1453,14 +1447,13 @@ int create(m3pc_handle_t* out, const m3pc_config_t* cfg) {
   M3PC_TRY(e->fb_xd.alloc(static_cast<size_t>(FB_MAX_ROWS) * D * 4));
   M3PC_TRY(e->fb_bar.alloc(16));
   M3PC_CHECK_CUDA(cudaMemset(e->fb_bar.p, 0, 16));
-  if (const char* g = getenv("M3PC_NO_FUSED_B1")) e->use_fused_b1 = !(g[0] == '1');
-  if (const char* g = getenv("M3PC_NO_FUSED_LN")) e->fuse_ln = !(g[0] == '1');
-  if (const char* g = getenv("M3PC_FUSED_LN_MIN_ROWS")) e->fuse_ln_min_rows = std::max(129, atoi(g));
-  if (const char* g = getenv("M3PC_DEC_FULL")) e->restrict_deep = !(g[0] == '1');
-  if (const char* g = getenv("M3PC_NO_DEDUPE")) e->dedupe_history = !(g[0] == '1');
-  if (const char* g = getenv("M3PC_MEGA")) e->use_mega = g[0] == '1';
-  if (const char* g = getenv("M3PC_NO_GRAPHS")) e->use_graphs = !(g[0] == '1');
-  if (const char* g = getenv("M3PC_NO_PDL")) g_use_pdl = !(g[0] == '1');
+  if (const char* g = tune_env("M3PC_NO_FUSED_B1")) e->use_fused_b1 = !(g[0] == '1');
+  if (const char* g = tune_env("M3PC_NO_FUSED_LN")) e->fuse_ln = !(g[0] == '1');
+  if (const char* g = tune_env("M3PC_FUSED_LN_MIN_ROWS")) e->fuse_ln_min_rows = std::max(129, atoi(g));
+  if (const char* g = tune_env("M3PC_DEC_FULL")) e->restrict_deep = !(g[0] == '1');
+  if (const char* g = tune_env("M3PC_NO_DEDUPE")) e->dedupe_history = !(g[0] == '1');
+  if (const char* g = tune_env("M3PC_NO_GRAPHS")) e->use_graphs = !(g[0] == '1');
+  if (const char* g = tune_env("M3PC_NO_PDL")) g_use_pdl = !(g[0] == '1');
   M3PC_CHECK_CUDA(cudaEventCreate(&e->ev0));
   M3PC_CHECK_CUDA(cudaEventCreate(&e->ev1));
   M3PC_CHECK_CUDA(cudaDeviceSynchronize());
@@ -1501,7 +1494,26 @@ int m3pc_destroy(m3pc_handle_t h) {
 int m3pc_set_param(m3pc_handle_t h, const char* name, const float* data, size_t count) {
   M3PC_REQUIRE(h != nullptr && name != nullptr && data != nullptr, "null argument");
   h->finalized = false;
+  h->drop_graphs();
   h->staged[name].assign(data, data + count);
+  return M3PC_OK;
+}
+
+int m3pc_set_option(m3pc_handle_t h, const char* name, int32_t value) {
+  M3PC_REQUIRE(h != nullptr && name != nullptr, "null argument");
+  const std::string n(name);
+  h->drop_graphs();  // the launch sequence a graph froze may no longer be the selected one
+  if (n == "graphs") h->use_graphs = value != 0;
+  else if (n == "pdl") m3pc::g_use_pdl = value != 0;
+  else if (n == "fused_b1") h->use_fused_b1 = value != 0;
+  else if (n == "fused_ln") h->fuse_ln = value != 0;
+  else if (n == "fused_ln_min_rows") h->fuse_ln_min_rows = std::max(129, static_cast<int>(value));
+  else if (n == "restrict_deep_decoder") h->restrict_deep = value != 0;
+  else if (n == "dedupe_history") h->dedupe_history = value != 0;
+  else {
+    m3pc::set_error("m3pc_set_option: unknown option '" + n + "'");
+    return M3PC_ERR_INVALID;
+  }
   return M3PC_OK;
 }
 

@@ -515,18 +515,13 @@ int launch_fused_b1(const FusedB1Params& p, int D, cudaStream_t st) {
                "fused_b1: shape out of range");
   const size_t smem = fused_b1_smem_bytes(D, p.S, p.n_need);
   M3PC_REQUIRE(smem <= 200 * 1024, "fused_b1: activation panel does not fit shared memory");
-  static int num_sms = 0;
-  static size_t configured[2] = {0, 0};
+  static PerDevice<size_t> configured;  // the attribute and the SM count are per device, not per process
   auto kern = fused_b1_kernel<4>;
-  const int ki = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    M3PC_CHECK_CUDA(cudaGetDevice(&dev));
-    M3PC_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  if (smem > configured[ki]) {
+  const int num_sms = device_num_sms();
+  M3PC_REQUIRE(num_sms > 0, "fused_b1: no device");
+  if (smem > configured.here()) {
     M3PC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured[ki] = smem;
+    configured.here() = smem;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(num_sms);  // one CTA per SM: all CTAs are co-resident (cooperative launch), the grid barrier cannot deadlock

@@ -22,7 +22,6 @@ namespace m3pc {
 
 int make_tmap(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
 int make_tmap_out(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t cols, bool f32);
-int gemm_num_sms();
 
 namespace {
 
@@ -51,6 +50,8 @@ struct LnGemmParams {
   const float* table;  // null: residual = X
   int rows_per_group;
   int M, num_kb, n_units;
+  int tune;  // tuning build only (timing experiments, results are garbage): bit 0 = no residual loads, bit 1 = no X store,
+             // bit 2 = no Y store (pass 2 only drains TMEM), bit 3 = epilogue only hands the accumulator back
 };
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
@@ -176,7 +177,12 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
     uint32_t rph[2] = {0u, 0u};
     const uint32_t acc_empty_leader = mapa_u32(smem_u32(acc_empty), 0);
     const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);  // SWIZZLE_64B: 16-byte chunk j of row r lives at j ^ ((r >> 1) & 3)
-    const bool from_x = P.table == nullptr;
+#ifdef M3PC_TUNING
+    const int tune = P.tune;
+#else
+    constexpr int tune = 0;
+#endif
+    const bool from_x = P.table == nullptr && !(tune & 1);
     const float* sbias = sconst;
     const float* sgamma = sconst + LN_N;
     const float* sbeta = sconst + 2 * LN_N;
@@ -185,7 +191,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
     for (int u = pair; u < P.n_units; u += n_pairs, ++it) {
       const int row0 = (u * 2 + static_cast<int>(crank)) * BM + quarter * 32;
       const int row = row0 + lane;
-      const bool live = row0 < P.M;
+      const bool live = row0 < P.M && !(tune & 8);
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(cgrp * 128);
       // short K: the residual tile is pulled into L2 while the MMAs of this row block are still running (each box load then waits
       // for an L2 hit instead of an HBM round trip).  Not for long K: the A stream evicts the prefetched lines before they are
@@ -224,11 +230,11 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
           }
           tmem_ld_wait();
           float v[16];
-          const float* trow = from_x ? nullptr : P.table + static_cast<size_t>(min(row, P.M - 1) / P.rows_per_group) * LN_N + col0;
+          const float* trow = (from_x || P.table == nullptr) ? nullptr : P.table + static_cast<size_t>(min(row, P.M - 1) / P.rows_per_group) * LN_N + col0;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float4* slot = reinterpret_cast<float4*>(buf + lane * 64 + ((static_cast<uint32_t>(j) ^ sw) << 4));
-            const float4 res = from_x ? *slot : __ldg(reinterpret_cast<const float4*>(trow + 4 * j));
+            const float4 res = from_x ? *slot : (trow != nullptr ? __ldg(reinterpret_cast<const float4*>(trow + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f));
             const float4 b4 = *reinterpret_cast<const float4*>(sbias + col0 + 4 * j);
             v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b4.x + res.x;
             v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y + res.y;
@@ -245,7 +251,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&P.tx, buf, col0, row0);
+            if (!(tune & 2)) tma_store_2d(&P.tx, buf, col0, row0);
             bulk_commit();
           }
           ++nbox;
@@ -304,7 +310,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&P.ty, buf, col0, row0);
+            if (!(tune & 4)) tma_store_2d(&P.ty, buf, col0, row0);
             bulk_commit();
           }
           ++nbox;
@@ -335,11 +341,11 @@ int gemm_ln_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bi
   M3PC_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) & 15) == 0,
                "gemm_ln: operands must be 16-byte aligned");
   M3PC_TRY(gemm_init_driver_api());
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice<bool> configured;
+  if (!configured.here()) {
     static_assert(SmemLn::kTotal <= 227 * 1024, "shared memory budget exceeded");
     M3PC_CHECK_CUDA(cudaFuncSetAttribute(gemm_ln_2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLn::kTotal));
-    configured = true;
+    configured.here() = true;
   }
   LnGemmParams P{};
   M3PC_TRY(make_tmap(&P.ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), BM));
@@ -351,7 +357,8 @@ int gemm_ln_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bi
   P.M = M;
   P.num_kb = K / BK;
   P.n_units = ceil_div(M, 2 * BM);
-  const int pairs = std::min(P.n_units, gemm_num_sms() / 2);
+  if (const char* t = tune_env("M3PC_TUNE_LN")) P.tune = atoi(t);
+  const int pairs = std::min(P.n_units, device_num_sms() / 2);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(LN_THREADS);

@@ -117,10 +117,10 @@ int gemm_bf16_skinny(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, in
   M3PC_REQUIRE(M >= 1 && M <= SK_MAX_M && K % 8 == 0, "gemm_skinny: needs M <= 32 and K % 8 == 0");
   const size_t smem = static_cast<size_t>(M) * K * sizeof(__nv_bfloat16);
   M3PC_REQUIRE(smem <= 160 * 1024, "gemm_skinny: A panel does not fit shared memory");
-  static size_t configured = 0;
-  if (smem > configured) {
+  static PerDevice<size_t> configured;
+  if (smem > configured.here()) {
     M3PC_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = smem;
+    configured.here() = smem;
   }
   M3PC_CHECK_CUDA(launch_k(gemm_skinny_kernel, dim3(ceil_div(N, SK_THREADS / 32)), dim3(SK_THREADS), smem, st, A, W, C, M, N, K, epi.bias, epi.table,
                                                                           epi.rows_per_group > 0 ? epi.rows_per_group : 1, epi.flags));

@@ -42,10 +42,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode_tiled = nullptr;
-int g_num_sms = 0;
 int g_force_bn = 0, g_force_cl = 0;  // M3PC_GEMM_CONFIG="<bn>x<cl>" pins one single-CTA configuration (tuning / tests)
-int g_debug_skip_epi = 0;             // M3PC_GEMM_DEBUG_SKIP_EPI=1: tuning experiment, epilogue warps only hand the accumulator back
+#ifdef M3PC_TUNING
+int g_debug_skip_epi = 0;             // tuning build only, M3PC_GEMM_DEBUG_SKIP_EPI=1: the epilogue warps only hand the accumulator back (results are garbage)
 constexpr int EPI_DEBUG_SKIP = 1 << 30;
+#else
+constexpr int g_debug_skip_epi = 0;
+constexpr int EPI_DEBUG_SKIP = 0;     // the release library has no result-corrupting switch
+#endif
 int g_use_2sm = 1;                   // M3PC_GEMM_2SM=0 disables the CTA-pair kernel
 
 struct EpiParams {
@@ -343,6 +347,8 @@ struct GroupParams {
   GroupProblem p[MAX_GROUP];
   int n, total_units;
   int strided;  // 1: pair p works on units p, p + n_pairs, ... (see launch_2sm) instead of one contiguous range
+  int tune;     // tuning build only (timing experiments, results are garbage): bit 0 = load A for a pair's first unit only,
+                // bit 1 = load W for a pair's first unit only
 };
 struct UnitCoord { int g, mp, nt, ks; };
 __device__ __forceinline__ UnitCoord decode_unit(const GroupParams& gp, int u) {
@@ -424,13 +430,18 @@ __global__ void __launch_bounds__(GEMM_THREADS_2SM, 1) gemm_bf16_2sm_kernel(cons
         const GroupProblem& P = gp.p[uc.g];
         const int m0 = (uc.mp * 2 + static_cast<int>(crank)) * BM, n0 = uc.nt * BN + static_cast<int>(crank) * 128;
         const int num_kb = P.num_kb, k0 = uc.ks * num_kb;
+#ifdef M3PC_TUNING
+        const bool load_a = !(gp.tune & 1) || u == u_lo, load_w = !(gp.tune & 2) || u == u_lo;
+#else
+        constexpr bool load_a = true, load_w = true;
+#endif
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
-          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2u * L::kStageBytes);
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2u * ((load_a ? L::kABlk : 0) + (load_w ? L::kBBlk : 0)));
           uint8_t* dst = smem + s * L::kStageBytes;
           const uint32_t bar = full_leader + 8u * static_cast<uint32_t>(s);
-          tma_load_2d_2sm(dst, &P.ta, bar, (k0 + kb) * BK, m0);
-          tma_load_2d_2sm(dst + L::kABlk, &P.tw, bar, (k0 + kb) * BK, n0);
+          if (load_a) tma_load_2d_2sm(dst, &P.ta, bar, (k0 + kb) * BK, m0);
+          if (load_w) tma_load_2d_2sm(dst + L::kABlk, &P.tw, bar, (k0 + kb) * BK, n0);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -628,17 +639,17 @@ template <int BN, int STAGES, int CL>
 int launch(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, int M, int N, int K, const GemmEpilogue& epi, cudaStream_t st) {
   using L = SmemLayout<BN, STAGES>;
   static_assert(L::kTotal <= 227 * 1024, "shared memory budget exceeded");
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice<bool> configured;
+  if (!configured.here()) {
     M3PC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    configured = true;
+    configured.here() = true;
   }
   CUtensorMap ta, tw;
   M3PC_TRY(make_tmap(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), BM));
   M3PC_TRY(make_tmap(&tw, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), BN / CL));
   EpiParams ep{epi.bias, epi.table, epi.rows_per_group > 0 ? epi.rows_per_group : 1, epi.flags};
   const int units = (N / BN) * ceil_div(ceil_div(M, BM), CL);
-  const int clusters = std::min(units, g_num_sms / CL);
+  const int clusters = std::min(units, device_num_sms() / CL);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * CL);
   cfg.blockDim = dim3(GEMM_THREADS);
@@ -686,12 +697,12 @@ int launch_2sm(const GemmProblem* probs, int n, cudaStream_t st) {
   using L = Smem2<STAGES>;
   static_assert(L::kTotal <= 227 * 1024, "shared memory budget exceeded");
   static_assert(sizeof(GroupParams) <= 4000, "kernel parameter space");
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice<bool> configured;
+  if (!configured.here()) {
     M3PC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_2sm_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    configured = true;
+    configured.here() = true;
   }
-  const int n_pairs_max = g_num_sms / 2;
+  const int n_pairs_max = device_num_sms() / 2;
   GroupParams gp{};
   gp.n = n;
   int units = 0;
@@ -723,6 +734,7 @@ int launch_2sm(const GemmProblem* probs, int n, cudaStream_t st) {
     units += tiles * P.ksplit;
   }
   gp.total_units = units;
+  if (const char* t = tune_env("M3PC_TUNE_GEMM")) gp.tune = atoi(t);
   const int pairs = std::min(units, n_pairs_max);
   gp.strided = g_use_strided && n == 1 && gp.p[0].n_tiles == 2 && gp.p[0].ksplit == 1 && probs[0].K >= 1024 && pairs % 2 == 0 && units >= 2 * pairs;
   cudaLaunchConfig_t cfg{};
@@ -749,7 +761,7 @@ int launch_2sm(const GemmProblem* probs, int n, cudaStream_t st) {
 double model_time(int M, int N, int K, int bn, int cl) {
   const int m_tiles = ceil_div(M, BM);
   const int units = (N / bn) * ceil_div(m_tiles, cl);
-  const int clusters = std::min(units, g_num_sms / cl);
+  const int clusters = std::min(units, device_num_sms() / cl);
   const double rounds = std::ceil(static_cast<double>(units) / clusters);
   const double kb = K / BK;
   const double t_mma = rounds * kb * 4.0 * (bn / 2.0) / 1.7e9 + 2.0e-6;                          // 64 / 128 cycles per K=16 step
@@ -758,8 +770,6 @@ double model_time(int M, int N, int K, int bn, int cl) {
 }
 
 }  // namespace
-
-int gemm_num_sms() { return g_num_sms; }
 
 int gemm_init_driver_api() {
   if (g_encode_tiled != nullptr) return M3PC_OK;
@@ -770,15 +780,14 @@ int gemm_init_driver_api() {
     set_error("cuTensorMapEncodeTiled not available from the CUDA driver");
     return M3PC_ERR_CUDA;
   }
-  int dev = 0;
-  M3PC_CHECK_CUDA(cudaGetDevice(&dev));
-  M3PC_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
-  if (const char* f = getenv("M3PC_GEMM_2SM")) g_use_2sm = atoi(f);
-  if (const char* f = getenv("M3PC_GEMM_SPLITK")) g_use_splitk = atoi(f);
-  if (const char* f = getenv("M3PC_GEMM_STRIDED")) g_use_strided = atoi(f);
-  if (const char* f = getenv("M3PC_GEMM_DEBUG_SKIP_EPI")) g_debug_skip_epi = atoi(f);
-  if (const char* f = getenv("M3PC_GEMM_CONFIG")) {
+  if (const char* f = tune_env("M3PC_GEMM_2SM")) g_use_2sm = atoi(f);
+  if (const char* f = tune_env("M3PC_GEMM_SPLITK")) g_use_splitk = atoi(f);
+  if (const char* f = tune_env("M3PC_GEMM_STRIDED")) g_use_strided = atoi(f);
+#ifdef M3PC_TUNING
+  if (const char* f = tune_env("M3PC_GEMM_DEBUG_SKIP_EPI")) g_debug_skip_epi = atoi(f);
+#endif
+  if (const char* f = tune_env("M3PC_GEMM_CONFIG")) {
     if (sscanf(f, "%dx%d", &g_force_bn, &g_force_cl) != 2 || (g_force_bn != 128 && g_force_bn != 256) || (g_force_cl != 1 && g_force_cl != 2))
       g_force_bn = g_force_cl = 0;
   }

@@ -24,8 +24,6 @@ struct EmbedParams {
   int n_tok;
   int B;
   int b0;   // global batch row of this chunk's row 0 (only read for tokens with bdiv > 0)
-  int cpt;  // 0: token-major output rows (row = token * B + b); > 0: candidate-major 128-row tiles holding cpt batch rows each
-            // (row = (b / cpt) * 128 + (b % cpt) * n_tok + token) -- the layout of the encoder megakernel
 };
 // x (n_tok*B, D) fp32 residual stream, y (n_tok*B, D) = LayerNorm(x; gamma, beta) in AT.
 int launch_embed(const EmbedParams& p, int D, float* x, void* y, bool y_bf16, const float* gamma, const float* beta, cudaStream_t st);
@@ -74,23 +72,6 @@ struct FusedB1Params {
 };
 size_t fused_b1_smem_bytes(int D, int S, int n_need);
 int launch_fused_b1(const FusedB1Params& p, int D, cudaStream_t st);
-
-// ---- encoder megakernel (encoder_mega.cu): all encoder layers of a big-batch forward in one persistent launch ----
-struct EncoderMegaLayer {
-  const __nv_bfloat16 *in_w, *out_w, *l1_w, *l2_w;
-  const float *in_b, *out_b, *l1_b, *l2_b, *n2_w, *n2_b;
-  const float *post_w, *post_b;  // LayerNorm applied after the layer: next layer's norm1 or the final encoder norm
-};
-struct EncoderMegaArgs {
-  int D, S, B, n_layers;
-  EncoderMegaLayer layer[4];
-  float* X;                 // candidate-major tiles: residual stream (in: embedding)
-  __nv_bfloat16* Y;         // candidate-major tiles: in: norm1 of layer 0 applied to X
-  __nv_bfloat16 *QKV, *ATT, *HID;  // scratch, candidate-major tiles
-  __nv_bfloat16* ENC;       // out: (S * B, D) token-major final encoder norm
-};
-int encoder_mega_cpt(int S);  // batch rows per 128-row tile (0: S not supported)
-int launch_encoder_mega(const EncoderMegaArgs& a, cudaStream_t st);
 
 // ---- LayerNorm family ---------------------------------------------------------------------------------
 // y1 = LN(x; g1, b1) (optional), y2 = LN(y1; g2[grp], b2[grp]) (optional, grp = row / rows_per_group, skipped where g2[grp]==0)

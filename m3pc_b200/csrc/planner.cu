@@ -203,6 +203,12 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const __grid_consta
   }
   const float Z = block_sum(z, redv);
   block_argmax(kbest, ki, redv, redi);
+  // non-finite scores (every comparison false): the indices are still the 0x7fffffff sentinels.  Never index with them --
+  // report candidate 0 and NaN actions, which the host can test for (the reference raises from torch.multinomial instead).
+  const bool bad_k = ki == 0x7fffffff;
+  if (mi == 0x7fffffff) mi = 0;
+  if (bad_k) ki = 0;
+  const float nanv = __int_as_float(0x7fc00000);
   // 3. U[a] = sum w_n a0[n, a]
   for (int a = 0; a < p.A; ++a) {
     float u = 0.f;
@@ -212,11 +218,12 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const __grid_consta
     }
     const float U = block_sum(u, redv);
     if (tid == 0) {
+      const float sa = bad_k ? nanv : candv[static_cast<size_t>(ki) * stride_a0 + a];
       eval_action[a] = U / Z;
-      sample_action[a] = candv[static_cast<size_t>(ki) * stride_a0 + a];
+      sample_action[a] = sa;
       if (p.partials) {
         p.partials[8 + a] = U;
-        p.partials[8 + p.A + a] = candv[static_cast<size_t>(ki) * stride_a0 + a];
+        p.partials[8 + p.A + a] = sa;
       }
     }
   }

@@ -1,8 +1,9 @@
 // fp32 GEMM on CUDA cores: C[M,N] = epilogue(A[M,K] * W[N,K]^T).
 //
-// Used (a) for the reference-grade precision mode (M3PC_PREC_FP32: every contraction of the MTM in fp32, the
-// arithmetic type of the reference) and (b) for the TwinQ critic MLPs (finetune_omtm/model.py:146-171), whose
-// Q-values enter the candidate scores directly and therefore stay in fp32 in both modes.
+// Used for the reference-grade precision mode (M3PC_PREC_FP32): every contraction of the MTM and of the TwinQ critic
+// (finetune_omtm/model.py:146-171) in fp32, the arithmetic type of the reference.  In bf16 mode the critic's two hidden
+// layers run on the tcgen05 GEMM instead (bf16 operands, fp32 accumulate; engine.cu:critic) when its width is a multiple of
+// 128, and only fall back to this kernel otherwise; the final 256 -> 1 layer and min(q1, q2) are fp32 in both modes.
 // Plain register-blocked tiling (64x64x16 per 256-thread CTA, 4x4 outputs per thread); arbitrary M, N, K.
 #include "common.cuh"
 

@@ -206,6 +206,5 @@ __device__ __forceinline__ float gelu_erf_tanh(float x) {
 // host: K-major bf16 operand map (box = 64 k x box_rows rows, SWIZZLE_128B) and output map (box = 32 rows x 64 bytes, SWIZZLE_64B)
 int make_tmap(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
 int make_tmap_out(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t cols, bool f32);
-int gemm_num_sms();
 
 }  // namespace m3pc

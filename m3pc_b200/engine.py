@@ -34,6 +34,10 @@ def _dev_f32(t: torch.Tensor, what: str) -> torch.Tensor:
 class PlanEngine:
     """One engine per (process, device).  Mirrors ``m3pc_create`` .. ``m3pc_destroy``."""
 
+    #: ``m3pc_set_option`` values applied to every engine right after ``m3pc_create`` (parity tests switch between the
+    #: result-equivalent launch sequences with it; empty in production)
+    default_options: Dict[str, int] = {}
+
     def __init__(self, *, n_embd: int, n_head: int, n_enc_layer: int, n_dec_layer: int, traj_length: int, obs_dim: int,
                  act_dim: int, precision: str = "bf16", max_batch: int = 1024, chunk: int = 0, critic_hidden: int = 0,
                  device: Optional[torch.device] = None):
@@ -53,6 +57,8 @@ class PlanEngine:
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):
             nat.check(self.lib.m3pc_create(C.byref(self._h), C.byref(cfg)), "m3pc_create")
+        for name, value in type(self).default_options.items():
+            self.set_option(name, value)
         self.finalized = False
         self.has_critic = False
         # persistent small outputs
@@ -88,6 +94,10 @@ class PlanEngine:
         self.set_param("critic.obs_mean", obs_mean)
         self.set_param("critic.obs_std", obs_std)
         self.has_critic = True
+
+    def set_option(self, name: str, value: int) -> None:
+        """``m3pc_set_option``: pick between result-equivalent launch sequences (see include/m3pc.h for the names)."""
+        nat.check(self.lib.m3pc_set_option(self._h, name.encode(), int(value)), f"m3pc_set_option({name})")
 
     def finalize(self) -> None:
         with torch.cuda.device(self.device):

@@ -42,6 +42,9 @@ class PlannerMixin:
     debug_plans: bool = False
     last_plan_debug: Optional[dict] = None
     seed: int = 0
+    #: True on the zero-shot Learner: the states window also carries the stored future waypoints
+    #: (zeroshot_omtm/learner.py:97-106); read by rollout.DeviceEpisodes when it cuts windows on the device
+    _future_obs_windows: bool = False
     #: global candidate id of this process's first candidate / total (candidate sharding across ranks)
     cand_offset: int = 0
 
@@ -55,6 +58,7 @@ class PlannerMixin:
             self.mtm.bind_planner(self.tokenizer_manager, critic, max_batch=max_batch)
             self.__dict__["_planner_bound"] = self.mtm
             self.__dict__["_plan_counter"] = 0
+            self.__dict__.pop("_rtg_tok", None)  # cached return-to-go tokens were normalised with the previous statistics
             rt = self.tokenizer_manager.tokenizers["returns"]
             self.__dict__["_rt_norm"] = (rt._data_mean.detach().double().cpu().numpy(), rt._data_std.detach().double().cpu().numpy(), bool(rt.normalize))
         return self.mtm.sync_engine()
@@ -211,55 +215,23 @@ class PlannerMixin:
         ev, sm = self._plan_device("mtm_sampling", horizon, 0.0, wb.d_states, wb.d_actions, wb.d_rewards, wb.d_returns)
         return ev.clone()[None, :] if eval else sm.clone()[None, :]
 
-    @torch.no_grad()
-    def action_sample_batch(self, histories, percentage=1.0, horizon=4, plan=True, eval=False, rtg=None):
-        """``action_sample`` for E lock-step environments in one ``m3pc_plan`` launch sequence (SURVEY.md section 8f rank 1;
-        the reference plans one environment per call, learner.py:329-417).  ``histories`` is a sequence of E history dicts that
-        share the planning-horizon regime; ``rtg`` a scalar or one value per environment.  Returns (E, act): row e is what
-        ``action_sample(histories[e], ...)`` returns (``eval_action`` if ``eval`` else ``sample_action``).  The E windows are
-        built in one pinned staging buffer and travel in one H2D copy; E * act floats come back."""
-        if eval == True:  # noqa: E712
-            assert rtg is not None
+    @staticmethod
+    def _rtg_of(rtg, e: int):
+        """``rtg`` may be a scalar (shared) or one value per environment (list / tuple / ndarray)."""
+        if isinstance(rtg, (list, tuple)):
+            return rtg[e]
+        if isinstance(rtg, np.ndarray) and rtg.ndim > 0:
+            return rtg.reshape(-1)[e if rtg.size > 1 else 0]
+        return rtg
+
+    def _stage_and_plan(self, histories, percentage, plan: bool, rtg, future_obs: bool = False):
+        """Shared body of ``action_sample_batch`` / ``action_sample_async``: E windows into ONE pinned staging buffer
+        (learner.py:346-385 per window), one H2D copy, one ``m3pc_plan`` launch sequence.  Returns (eval (E,A), sample (E,A))
+        engine-owned device tensors."""
         E = len(histories)
         if E < 1:
-            raise ValueError("action_sample_batch needs at least one history")
+            raise ValueError("need at least one history")
         if E > int(getattr(self, "max_envs", 1)):
-            raise ValueError(f"{E} environments but the Learner was built with max_envs={getattr(self, 'max_envs', 1)}")
-        if E == 1:
-            out = self.action_sample(histories[0], percentage, horizon, plan, eval, rtg if not isinstance(rtg, (list, tuple)) else rtg[0])
-            return out.reshape(1, -1)
-        self._engine()
-        horizons = {self._clamped_horizon(hist) for hist in histories}
-        if len(horizons) != 1:
-            raise ValueError("lock-step environments must share the planning horizon (same path_length regime)")
-        horizon = horizons.pop()
-        h0 = histories[0]
-        wb, slot = self._window_buffers(h0["observations"].shape[-1], h0["actions"].shape[-1], n_env=E)
-        for e_, hist in enumerate(histories):
-            self._fill_window(slot.h_states[e_], slot.h_actions[e_], slot.h_rewards[e_], slot.h_returns[e_], hist, horizon, percentage,
-                              rtg[e_] if isinstance(rtg, (list, tuple)) else rtg)
-        self._upload_window(wb, slot)
-        if plan:
-            assert self.cfg.plan_guidance in _PLAN_GUIDANCE
-            lmbda = 0.6 if self.cfg.plan_guidance == "rtg_guiding" else self.cfg.lmbda
-            guidance = self.cfg.plan_guidance
-        else:
-            lmbda, guidance = 0.0, "mtm_sampling"
-        ev, sm = self._plan_device(guidance, horizon, lmbda, wb.d_states, wb.d_actions, wb.d_rewards, wb.d_returns, n_env=E)
-        return ev.clone() if eval else sm.clone()
-
-
-    @torch.no_grad()
-    def action_sample_async(self, histories, percentage=1.0, plan=True, eval=False, rtg=None) -> "PlanTicket":
-        """``action_sample_batch`` without the host synchronisation (SURVEY.md section 8f rank 3): the window upload, the plan and
-        the device-to-host copy of the E actions are enqueued on the current stream and a ticket is returned at once;
-        ``ticket.result()`` waits for that copy only.  The reference's callers block in ``action.cpu()`` every step
-        (replay_buffer.py:211-214, learner.py:681-689); with a ticket the caller can step other environments meanwhile
-        (``m3pc_b200.rollout``)."""
-        if eval == True:  # noqa: E712
-            assert rtg is not None
-        E = len(histories)
-        if E < 1 or E > int(getattr(self, "max_envs", 1)):
             raise ValueError(f"{E} environments but the Learner was built with max_envs={getattr(self, 'max_envs', 1)}")
         self._engine()
         horizons = {self._clamped_horizon(hist) for hist in histories}
@@ -271,17 +243,41 @@ class PlannerMixin:
         for e_, hist in enumerate(histories):
             v = (slot.h_states, slot.h_actions, slot.h_rewards, slot.h_returns) if E == 1 else \
                 (slot.h_states[e_], slot.h_actions[e_], slot.h_rewards[e_], slot.h_returns[e_])
-            self._fill_window(*v, hist, horizon, percentage, rtg[e_] if isinstance(rtg, (list, tuple, np.ndarray)) else rtg)
+            self._fill_window(*v, hist, horizon, percentage, self._rtg_of(rtg, e_), future_obs=future_obs)
         self._upload_window(wb, slot)
         if plan:
             assert self.cfg.plan_guidance in _PLAN_GUIDANCE
-            lmbda = 0.6 if self.cfg.plan_guidance == "rtg_guiding" else self.cfg.lmbda
+            lmbda = 0.6 if self.cfg.plan_guidance == "rtg_guiding" else self.cfg.lmbda  # learner.py:405-407 drops cfg.lmbda
             guidance = self.cfg.plan_guidance
         else:
             lmbda, guidance = 0.0, "mtm_sampling"
-        ev, sm = self._plan_device(guidance, horizon, lmbda, wb.d_states, wb.d_actions, wb.d_rewards, wb.d_returns, n_env=E)
-        pool = self.__dict__.setdefault("_tickets", {})
-        free = pool.setdefault(E, [])
+        return self._plan_device(guidance, horizon, lmbda, wb.d_states, wb.d_actions, wb.d_rewards, wb.d_returns, n_env=E)
+
+    @torch.no_grad()
+    def action_sample_batch(self, histories, percentage=1.0, horizon=4, plan=True, eval=False, rtg=None):
+        """``action_sample`` for E lock-step environments in one ``m3pc_plan`` launch sequence (SURVEY.md section 8f rank 1;
+        the reference plans one environment per call, learner.py:329-417).  ``histories`` is a sequence of E history dicts that
+        share the planning-horizon regime; ``rtg`` a scalar or one value per environment (list, tuple or ndarray).  Returns
+        (E, act): row e is what ``action_sample(histories[e], ...)`` returns (``eval_action`` if ``eval`` else
+        ``sample_action``).  The E windows are built in one pinned staging buffer and travel in one H2D copy; E * act floats
+        come back."""
+        if eval == True:  # noqa: E712
+            assert rtg is not None
+        ev, sm = self._stage_and_plan(histories, percentage, plan, rtg)
+        return (ev if eval else sm).clone().reshape(len(histories), -1)
+
+    @torch.no_grad()
+    def action_sample_async(self, histories, percentage=1.0, plan=True, eval=False, rtg=None) -> "PlanTicket":
+        """``action_sample_batch`` without the host synchronisation (SURVEY.md section 8f rank 3): the window upload, the plan and
+        the device-to-host copy of the E actions are enqueued on the current stream and a ticket is returned at once;
+        ``ticket.result()`` waits for that copy only.  The reference's callers block in ``action.cpu()`` every step
+        (replay_buffer.py:211-214, learner.py:681-689); with a ticket the caller can step other environments meanwhile
+        (``m3pc_b200.rollout``)."""
+        if eval == True:  # noqa: E712
+            assert rtg is not None
+        ev, sm = self._stage_and_plan(histories, percentage, plan, rtg)
+        E = len(histories)
+        free = self.__dict__.setdefault("_tickets", {}).setdefault(E, [])
         ticket = free.pop() if free else PlanTicket(E, ev.shape[-1], free)
         ticket._submit(ev if eval else sm)
         return ticket

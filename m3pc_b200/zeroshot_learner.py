@@ -19,6 +19,8 @@ from .tokenizers import TokenizerManager
 
 
 class Learner(PlannerMixin):
+    _future_obs_windows = True  # the states window holds future waypoints (zeroshot_omtm/learner.py:97-106, :188-197)
+
     def __init__(self, cfg, env, data_shapes, model_config, pretrain_model_path, obs_mean, obs_std,
                  tokenizer_manager: TokenizerManager, discrete_map: Dict[str, bool], max_envs: int = 1):
         self.cfg = cfg
@@ -49,7 +51,7 @@ class Learner(PlannerMixin):
                 views = (slot.h_states, slot.h_actions, slot.h_rewards, slot.h_returns)
             else:
                 views = (slot.h_states[e], slot.h_actions[e], slot.h_rewards[e], slot.h_returns[e])
-            self._fill_window(*views, hist, horizon, percentage, rtg if not isinstance(rtg, (list, tuple)) else rtg[e], future_obs=True)
+            self._fill_window(*views, hist, horizon, percentage, self._rtg_of(rtg, e), future_obs=True)
         self._upload_window(wb, slot)
         T = self.cfg.traj_length
         ev, sm, dbg = eng.backward_plan(mode=mode, horizon=horizon, win_states=wb.d_states.view(E, T, -1), win_actions=wb.d_actions.view(E, T, -1),

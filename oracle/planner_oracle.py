@@ -98,6 +98,9 @@ class PlannerOracle:
     critic_sd: Optional[Mapping[str, torch.Tensor]] = None
     obs_mean: Optional[torch.Tensor] = None
     obs_std: Optional[torch.Tensor] = None
+    #: test hook: (N,h,A) candidate actions used INSTEAD of the ones derived from ``eps`` -- lets a test score the candidates
+    #: a device run drew from its own Philox stream (the reference has no such hook; everything downstream is unchanged)
+    cand_override: Optional[torch.Tensor] = None
 
     # -- model call: tokenizer_manager.decode(self.mtm(tokenizer_manager.encode(traj), mask)) --
     def _model(self, traj, mask):
@@ -143,11 +146,15 @@ class PlannerOracle:
         T, N = self.traj_length, self.action_samples
         batch = {k: v.repeat(N, 1, 1) for k, v in traj.items()}
         dist = self._model(traj, create_rcbc_mask(T, T - h))["actions"]
-        if cand_kind == "dist":
+        if self.cand_override is not None:
+            sample_actions = None
+        elif cand_kind == "dist":
             sample_actions = self._candidates_from_dist(dist, h, eps)
         else:  # noise_adding_lambda, learner.py:156-167: eps has shape (N,h,A)
             mean = torch.tanh(dist["mu"])[0, T - h :, 0, :]
             sample_actions = torch.clamp(mean + eps * 0.09, -0.99999, 0.99999)
+        if self.cand_override is not None:
+            sample_actions = self.cand_override.to(self.dtype).reshape(N, h, -1)
         batch["actions"] = batch["actions"].clone()
         batch["actions"][:, T - h :, :] = sample_actions
         dec = self._model(batch, create_fd_mask(T, T - h))

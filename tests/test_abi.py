@@ -65,6 +65,16 @@ def test_invalid_arguments_are_rejected_without_a_gpu(lib):
     assert lib.m3pc_destroy(None) == 0
 
 
+def test_release_library_reads_no_environment_switch(lib):
+    """Tuning switches (kernel A/B selection, timing-only variants that corrupt results) exist only in the -DM3PC_TUNING build
+    (libm3pc_tuning.so); the shipped library holds no M3PC_* environment variable name and therefore reads none."""
+    assert nat.LIB_PATH.endswith("libm3pc.so")
+    blob = open(nat.LIB_PATH, "rb").read()
+    names = set(re.findall(rb"\x00(M3PC_[A-Z][A-Z0-9_]{3,})\x00", blob))  # a getenv() argument is a string of its own
+    assert not names, f"environment switch names in the release library: {sorted(names)}"
+    assert lib.m3pc_set_option(None, b"graphs", 0) == -1  # argument validation without a GPU
+
+
 def test_no_cpu_fallback(lib):
     import torch
     if torch.cuda.is_available():

@@ -445,7 +445,7 @@ def test_philox_noise_is_shard_invariant_and_seeded():
 def test_plan_scaled_model_last_decoder_layer_restricted(precision, monkeypatch):
     """BASELINE.json config 5 (D=1024, 8 heads, 4+2 layers, T=16, h=8): with more than one decoder layer only the LAST layer
     is restricted to the consumed rows.  Checked against the float64 oracle (which computes every row of every layer) and
-    against the same engine with the restriction switched off (M3PC_DEC_FULL=1)."""
+    against the same engine with the restriction switched off (m3pc_set_option "restrict_deep_decoder" 0)."""
     from oracle import planner_oracle as po
     N, temp = 24, 0.01
     shape, L = _learner("hopper", "rtg_guiding", N, temp, precision, scaled=True)
@@ -466,7 +466,8 @@ def test_plan_scaled_model_last_decoder_layer_restricted(precision, monkeypatch)
     assert float((J - ref["expect_return"]).abs().max()) <= tol * max(1.0, float(ref["expect_return"].abs().max()))
     assert rel(ev, ref["eval_action"]) < (2e-4 if precision == "fp32" else 4e-2)
     n_restricted = L.mtm.sync_engine().last_launch_count()
-    monkeypatch.setenv("M3PC_DEC_FULL", "1")
+    from m3pc_b200.engine import PlanEngine
+    monkeypatch.setitem(PlanEngine.default_options, "restrict_deep_decoder", 0)
     _, Lf = _learner("hopper", "rtg_guiding", N, temp, precision, scaled=True)
     Lf.cfg.horizon = 8
     Lf.injected_noise, Lf.debug_plans = noise, True
@@ -660,10 +661,82 @@ def test_zeroshot_candidate_draws_per_environment(precision):
 
 
 def test_plan_with_fused_residual_layernorm_forced_at_small_shapes(monkeypatch):
-    """The engine uses the fused residual GEMM + LayerNorm kernel from 1024 rows up; M3PC_FUSED_LN_MIN_ROWS=129 forces it at
+    """The engine uses the fused residual GEMM + LayerNorm kernel from 1024 rows up; option "fused_ln_min_rows" = 129 forces it at
     test sizes so the oracle comparison covers its wiring (out-projection + norm2, linear2 + next norm1 / final encoder norm,
     the table-residual form of the shared-history block, the restricted decoder layer)."""
-    monkeypatch.setenv("M3PC_FUSED_LN_MIN_ROWS", "129")
+    from m3pc_b200.engine import PlanEngine
+    monkeypatch.setitem(PlanEngine.default_options, "fused_ln_min_rows", 129)
     test_plan_internals_vs_fp64_oracle("bf16", "walker2d", "critic_lambda_guiding", 1.0, 130, 50)
     test_plan_internals_vs_fp64_oracle("bf16", "hopper", "rtg_guiding", 0.01, 200, 50)
     test_env_batched_plan_rows_equal_single_env_plans("bf16", "walker2d", "critic_lambda_guiding", 1.0, 96, 5, 0)
+
+
+def test_plan_graphs_are_dropped_when_parameters_change(monkeypatch):
+    """A captured plan graph has the weight / tokenizer / critic arena addresses and the scalar statistics baked into its
+    kernel nodes.  Replaying it after ``load_state_dict`` / ``mark_dirty`` (after every optimiser step) must
+    use the NEW parameters: m3pc_set_param / m3pc_finalize_params drop the graphs.  Checked against an engine that never
+    captures (option "graphs" = 0) loaded with the same new parameters."""
+    from m3pc_b200.engine import PlanEngine
+    from m3pc_b200.tokenizers import manager_from_stats
+    shape, L = _learner("walker2d", "critic_lambda_guiding", 256, 1.0, "bf16")
+    hist = syn.make_history(shape, seed=4, path_length=80)
+    L.seed = 3
+
+    def run(Lx):
+        Lx.__dict__["_plan_counter"] = 0  # same Philox key every call
+        return Lx.action_sample(hist, plan=True, eval=True, rtg=3.0).double().cpu()
+
+    a = [run(L) for _ in range(4)]  # eager, capture + replay, replay, replay
+    np.testing.assert_allclose(a[3].numpy(), a[0].numpy(), atol=1e-6)
+    # new weights (a different arena content, same size), new tokenizer statistics, new critic, then an in-place update
+    sd2 = {k: torch.from_numpy(v) for k, v in syn.make_state_dict(shape, 5).items()}
+    L.mtm.load_state_dict(sd2)
+    L.tokenizer_manager = manager_from_stats(syn.make_tokenizer_stats(shape, 9))
+    L.__dict__["_planner_bound"] = None  # re-bind the new tokenizer manager
+    with torch.no_grad():
+        for p in L.iql.qf.parameters():
+            p.mul_(0.5)
+    b = [run(L) for _ in range(3)]
+    with torch.no_grad():
+        L.mtm.encoder.layers[0].linear1.weight.mul_(1.25)
+        L.mtm.output_head_dict["rewards"][3].bias.add_(0.3)
+    L.mtm.mark_dirty()
+    c = [run(L) for _ in range(3)]
+    monkeypatch.setitem(PlanEngine.default_options, "graphs", 0)
+    _, R = _learner("walker2d", "critic_lambda_guiding", 256, 1.0, "bf16")
+    R.seed = 3
+    R.mtm.load_state_dict(sd2)
+    R.tokenizer_manager = manager_from_stats(syn.make_tokenizer_stats(shape, 9))
+    with torch.no_grad():
+        for p in R.iql.qf.parameters():
+            p.mul_(0.5)
+    rb = run(R)
+    with torch.no_grad():
+        R.mtm.encoder.layers[0].linear1.weight.mul_(1.25)
+        R.mtm.output_head_dict["rewards"][3].bias.add_(0.3)
+    R.mtm.mark_dirty()
+    rc = run(R)
+    assert float((a[0] - rb).abs().max()) > 1e-3 and float((rb - rc).abs().max()) > 1e-5  # the updates really change the plan
+    for x in b:
+        np.testing.assert_allclose(x.numpy(), rb.numpy(), atol=1e-6)
+    for x in c:
+        np.testing.assert_allclose(x.numpy(), rc.numpy(), atol=1e-6)
+
+
+def test_select_survives_non_finite_scores():
+    """NaN scores must not turn into an out-of-bounds read (which would poison the CUDA context): the plan returns NaN actions
+    and candidate index 0, and the next plan on the same handle works."""
+    shape, L = _learner("hopper", "rtg_guiding", 128, 0.01, "bf16")
+    hist = syn.make_history(shape, seed=4, path_length=80)
+    good = L.action_sample(hist, plan=True, eval=True, rtg=3.0).clone()
+    bad_hist = dict(hist, observations=hist["observations"].copy())
+    bad_hist["observations"][:] = np.nan
+    L.debug_plans = True
+    ev = L.action_sample(bad_hist, plan=True, eval=True, rtg=3.0)
+    sm = L.action_sample(bad_hist, plan=True, eval=False, rtg=3.0)
+    torch.cuda.synchronize()
+    assert bool(torch.isnan(ev).all()) and bool(torch.isnan(sm).all())
+    assert L.last_plan_debug["indices"].tolist() == [0, 0]
+    L.debug_plans = False
+    again = L.action_sample(hist, plan=True, eval=True, rtg=3.0)
+    assert bool(torch.isfinite(again).all()) and again.shape == good.shape
