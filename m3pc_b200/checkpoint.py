@@ -30,14 +30,21 @@ class CheckpointError(ValueError):
     """The file is readable but does not hold what the planning path needs."""
 
 
-def _torch_load(path: str):
+def _torch_load(path: str, trust_pickle: bool = False):
+    """``torch.load`` restricted to tensors and plain containers (``weights_only=True``).  A file that needs anything else --
+    i.e. one whose pickle stream names arbitrary Python globals, which is how a crafted checkpoint executes code -- is
+    REFUSED with a ``CheckpointError``; there is no silent retry.  ``trust_pickle=True`` is the explicit opt-in for files the
+    caller produced themselves (e.g. an optimiser state holding custom objects)."""
     if not os.path.exists(path):
         raise FileNotFoundError(path)
+    if trust_pickle:
+        return torch.load(path, map_location="cpu", weights_only=False)
     try:
         return torch.load(path, map_location="cpu", weights_only=True)
-    except pickle.UnpicklingError:
-        # optimiser state of old checkpoints can hold non-tensor python objects; the files are the user's own training output
-        return torch.load(path, map_location="cpu", weights_only=False)
+    except pickle.UnpicklingError as exc:
+        raise CheckpointError(f"{path}: not loadable as tensors + plain containers ({str(exc).splitlines()[0][:200]}). The file "
+                              "references Python objects outside torch's safe allow-list; loading it would run its pickle "
+                              "stream unrestricted. If you wrote this file yourself, pass trust_pickle=True.") from exc
 
 
 def _strip_prefix(sd: Mapping[str, torch.Tensor], prefix: str) -> Dict[str, torch.Tensor]:
@@ -111,10 +118,10 @@ def validate_mtm_state_dict(sd: Mapping[str, torch.Tensor], data_shapes, n_embd:
             raise CheckpointError(f"MTM checkpoint: non-finite values in {k}")
 
 
-def load_mtm_checkpoint(path: str) -> Dict[str, torch.Tensor]:
+def load_mtm_checkpoint(path: str, trust_pickle: bool = False) -> Dict[str, torch.Tensor]:
     """``torch.load(path)["model"]`` (learner.py:33-35) as fp32 CPU tensors; a DistributedDataParallel ``module.`` prefix is dropped.
     Also accepts a bare state dict (what ``torch.save(omtm.state_dict())`` writes)."""
-    blob = _torch_load(path)
+    blob = _torch_load(path, trust_pickle)
     if isinstance(blob, Mapping) and "model" in blob and isinstance(blob["model"], Mapping):
         sd = blob["model"]
     elif isinstance(blob, Mapping) and blob and all(isinstance(v, torch.Tensor) for v in blob.values()):
@@ -126,17 +133,17 @@ def load_mtm_checkpoint(path: str) -> Dict[str, torch.Tensor]:
     return {k: v.detach().to(torch.float32).contiguous() for k, v in sd.items()}
 
 
-def checkpoint_step(path: str) -> Optional[int]:
+def checkpoint_step(path: str, trust_pickle: bool = False) -> Optional[int]:
     """The ``step`` the trainer stored next to the weights (finetune.py:323), or None."""
-    blob = _torch_load(path)
+    blob = _torch_load(path, trust_pickle)
     s = blob.get("step") if isinstance(blob, Mapping) else None
     return int(s) if s is not None else None
 
 
-def load_iql_checkpoint(path: str) -> Dict[str, torch.Tensor]:
+def load_iql_checkpoint(path: str, trust_pickle: bool = False) -> Dict[str, torch.Tensor]:
     """The TwinQ state dict (``q1.net.{0,2,4}.*``, ``q2.net.{0,2,4}.*``) out of ``iql_<step>.pt`` (model.py:310-320).  The value
     function, actor and optimiser states in the file belong to training and are not on the planning path."""
-    blob = _torch_load(path)
+    blob = _torch_load(path, trust_pickle)
     if not isinstance(blob, Mapping) or "qf" not in blob:
         raise CheckpointError(f"{path}: expected ImplicitQLearning.state_dict() with a 'qf' entry (model.py:310-320)")
     sd = _strip_prefix(blob["qf"], "module.")
@@ -200,13 +207,13 @@ def data_shapes_from_statistics(stats: Mapping[str, DataStatistics]) -> Dict[str
 
 
 def build_learner(cfg, model_config, mtm_path: str, stats_path: str, *, iql_path: Optional[str] = None, obs_mean=None, obs_std=None,
-                  zeroshot: bool = False, max_envs: int = 1, env=None):
+                  zeroshot: bool = False, max_envs: int = 1, env=None, trust_pickle: bool = False):
     """The three files -> a ready planner: what finetune.py:176-224 / unseen.py:176-224 assemble from the dataset, the pretrained
     path and the IQL trainer, without the dataset or the trainer.  ``obs_mean`` / ``obs_std`` default to the states statistics
     (the replay buffer's normaliser, replay_buffer.py, is computed from the same observations)."""
     stats = load_trajectory_statistics(stats_path)
     shapes = data_shapes_from_statistics(stats)
-    sd = load_mtm_checkpoint(mtm_path)
+    sd = load_mtm_checkpoint(mtm_path, trust_pickle)
     validate_mtm_state_dict(sd, shapes, model_config.n_embd, model_config.n_enc_layer, model_config.n_dec_layer, cfg.traj_length)
     tm = tokenizer_manager_from_statistics(stats)
     om = stats["states"].mean if obs_mean is None else obs_mean
@@ -220,5 +227,5 @@ def build_learner(cfg, model_config, mtm_path: str, stats_path: str, *, iql_path
         L = FLearner(cfg, env, shapes, model_config, None, om, os_, tm, discrete_map, max_envs=max_envs)
     L.mtm.load_state_dict(sd)
     if iql_path is not None and hasattr(L, "iql"):
-        L.iql.qf.load_state_dict(load_iql_checkpoint(iql_path))
+        L.iql.qf.load_state_dict(load_iql_checkpoint(iql_path, trust_pickle))
     return L

@@ -48,20 +48,57 @@ class PlannerMixin:
     #: global candidate id of this process's first candidate / total (candidate sharding across ranks)
     cand_offset: int = 0
 
+    #: precision of the shadow engine when ``self.mtm`` is the REFERENCE's trainable omtm (hybrid drop-in)
+    planner_precision: str = "bf16"
+
+    @staticmethod
+    def _versions(module) -> int:
+        """Sum of the parameters' in-place version counters: moves on every optimiser step / ``load_state_dict`` / ``.mul_()``."""
+        return sum(p._version for p in module.parameters()) if module is not None else 0
+
+    def _planner_model(self):
+        """The engine-backed ``omtm`` the planners run on.  ``self.mtm`` itself when it is this package's module; otherwise
+        (``self.mtm`` is the REFERENCE's trainable omtm, mtm_model.py:324 -- the Learner keeps training it with its own
+        ``compute_mtm_loss`` / ``mtm_update``, learner.py:419-538) an inference-only shadow with the same config whose
+        parameters are re-copied from ``self.mtm.state_dict()`` whenever a parameter's version counter has moved, i.e. after
+        every optimiser step.  No ``mark_dirty`` call is needed in that mode."""
+        m = self.mtm
+        if isinstance(m, omtm):
+            return m
+        d = self.__dict__
+        if d.get("_shadow_of") is not m:
+            from .mtm_model import omtmConfig
+            c = m.config
+            cfg = omtmConfig(n_embd=c.n_embd, n_head=c.n_head, n_enc_layer=c.n_enc_layer, n_dec_layer=c.n_dec_layer, dropout=c.dropout,
+                             norm=c.norm, latent_dim=getattr(c, "latent_dim", None), precision=self.planner_precision)
+            shadow = cfg.create(dict(m.data_shapes), m.max_len, {k: False for k in m.data_shapes})
+            d["_shadow"], d["_shadow_of"], d["_shadow_version"] = shadow.to(m.pos_embed.device), m, None
+        ver = self._versions(m)
+        if d["_shadow_version"] != ver:
+            d["_shadow"].load_state_dict(m.state_dict())
+            d["_shadow_version"] = ver
+        return d["_shadow"]
+
     def _engine(self):
-        if self.__dict__.get("_planner_bound") is not self.mtm:
-            critic = getattr(getattr(self, "iql", None), "qf", None)
+        model = self._planner_model()
+        critic = getattr(getattr(self, "iql", None), "qf", None)
+        if model is not self.mtm:  # hybrid mode: the reference's TwinQ is trained in place by iql.update (model.py:286-308)
+            cver = self._versions(critic)
+            if self.__dict__.get("_critic_version") != cver:
+                self.__dict__["_critic_version"] = cver
+                model.mark_dirty()
+        if self.__dict__.get("_planner_bound") is not model:
             # forward planners batch max_envs windows x action_samples candidates; the backward planners batch max_envs rows
             max_envs = int(getattr(self, "max_envs", 1))
             max_batch = int(getattr(self.cfg, "action_samples", 1)) * (max_envs if getattr(self, "_envs_times_candidates", False) else 1)
             max_batch = max(max_batch, max_envs)
-            self.mtm.bind_planner(self.tokenizer_manager, critic, max_batch=max_batch)
-            self.__dict__["_planner_bound"] = self.mtm
+            model.bind_planner(self.tokenizer_manager, critic, max_batch=max_batch)
+            self.__dict__["_planner_bound"] = model
             self.__dict__["_plan_counter"] = 0
             self.__dict__.pop("_rtg_tok", None)  # cached return-to-go tokens were normalised with the previous statistics
             rt = self.tokenizer_manager.tokenizers["returns"]
             self.__dict__["_rt_norm"] = (rt._data_mean.detach().double().cpu().numpy(), rt._data_std.detach().double().cpu().numpy(), bool(rt.normalize))
-        return self.mtm.sync_engine()
+        return model.sync_engine()
 
     def _returns_tok(self, returns: np.ndarray) -> np.ndarray:
         """Tokenise the return-to-go exactly like the reference: float64 arithmetic, one rounding to fp32

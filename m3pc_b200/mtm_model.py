@@ -192,11 +192,15 @@ class omtm(nn.Module):
     def sync_engine(self) -> PlanEngine:
         """Upload parameters (and, for the planners, tokenizer statistics and TwinQ weights) if anything changed."""
         tokenizer_manager, critic, max_batch = self.__dict__.get("_bound", (None, None, None))
-        e = self.engine(max_batch=max_batch, critic_hidden=critic.hidden_dim if critic is not None else 0)
+        critic_hidden = 0
+        if critic is not None:  # this package's TwinQ keeps hidden_dim; the reference's (finetune_omtm/model.py:146-160) only its layers
+            critic_hidden = int(getattr(critic, "hidden_dim", 0) or critic.q1.net[0].out_features)
+        e = self.engine(max_batch=max_batch, critic_hidden=critic_hidden)
         if not self._engine_synced or not e.finalized:
             e.load_state_dict(self.state_dict())
             if tokenizer_manager is not None:
-                e.load_tokenizer_stats(tokenizer_manager.engine_stats())
+                from .tokenizers import engine_stats
+                e.load_tokenizer_stats(engine_stats(tokenizer_manager))
             else:  # omtm.forward alone never normalises; identity statistics keep the handle complete
                 dims = {k: s[1] for k, s in self.data_shapes.items()}
                 e.load_tokenizer_stats({k: {"mean": np.zeros(dims[k], np.float32), "std": np.ones(dims[k], np.float32)}

@@ -92,16 +92,24 @@ class TokenizerManager(torch.nn.Module):
 
     def engine_stats(self) -> Dict[str, Dict[str, np.ndarray]]:
         """mean/std per normalised modality, in the form ``PlanEngine.load_tokenizer_stats`` takes."""
-        out = {}
-        for k, tok in self.tokenizers.items():
-            if not isinstance(tok, ContinuousTokenizer):
-                raise NotImplementedError(f"tokenizer for {k!r} is {type(tok).__name__}: only ContinuousTokenizer is supported")
-            d = tok._data_mean.numel()
-            if tok.normalize:
-                out[k] = {"mean": tok._data_mean.detach().cpu().numpy(), "std": tok._data_std.detach().cpu().numpy()}
-            else:
-                out[k] = {"mean": np.zeros(d, np.float32), "std": np.ones(d, np.float32)}
-        return out
+        return engine_stats(self)
+
+
+def engine_stats(manager) -> Dict[str, Dict[str, np.ndarray]]:
+    """``TokenizerManager.engine_stats`` for this package's manager OR the reference's own
+    (research/omtm/tokenizers/base.py:64-99 with ContinuousTokenizer, continuous.py:31-62): both keep ``_data_mean`` /
+    ``_data_std`` / ``normalize`` per tokenizer.  Any other tokenizer type is rejected (only ContinuousTokenizer is configured
+    by the shipped configs and supported by the engine)."""
+    out = {}
+    for k, tok in manager.tokenizers.items():
+        if type(tok).__name__ != "ContinuousTokenizer" or not hasattr(tok, "_data_mean"):
+            raise NotImplementedError(f"tokenizer for {k!r} is {type(tok).__name__}: only ContinuousTokenizer is supported")
+        d = tok._data_mean.numel()
+        if tok.normalize:
+            out[k] = {"mean": tok._data_mean.detach().cpu().numpy(), "std": tok._data_std.detach().cpu().numpy()}
+        else:
+            out[k] = {"mean": np.zeros(d, np.float32), "std": np.ones(d, np.float32)}
+    return out
 
 
 def manager_from_stats(stats: Dict[str, Dict[str, np.ndarray]]) -> TokenizerManager:
