@@ -227,6 +227,46 @@ int m3pc_layernorm(const float* x, const float* gamma, const float* beta, void* 
 /* Bidirectional attention over token-major qkv (S*B rows, 3*D cols), head_dim 128; out (S*B, D). */
 int m3pc_attention(const void* qkv, void* out, int32_t B, int32_t S, int32_t n_head, int32_t is_bf16, void* stream);
 
+/* ---- the fused memory-bound kernels of the path, one entry each ----
+ * The activation layout these expose is the library's internal one: token-major matrices, row = token * batch + b, fp32
+ * residual stream (x) and operands in the activation type of the handle (bf16 for M3PC_PREC_BF16, else fp32). */
+
+/* K1 -- tokens -> encoder input: omtm.trajectory_encoding + the kept-token gather of forward_encoder (mtm_model.py:546-557,
+ * :619-632) + norm1 of the first encoder block.  tok_*, masks as in m3pc_forward.  S = number of kept tokens (modality-major).
+ *   x_out  device fp32 (S*batch, D): W_enc x + b + per-dim + pos[t] of every kept token
+ *   y_out  device (S*batch, D) activation type: LayerNorm(x_out; encoder.layers.0.norm1) */
+int m3pc_embed_gather(m3pc_handle_t h, int32_t batch, const float* tok_states, const float* tok_actions, const float* tok_rewards,
+                      const float* tok_returns, const uint8_t* masks, float* x_out, void* y_out, void* stream);
+/* K4 -- encoder output -> decoder input: mask-token scatter + decoder_embed + per-dim + pos (mtm_model.py:646-696).
+ *   enc_out device (S*batch, D) activation type: final-normed encoder output of the kept tokens, token-major
+ *   x_out   device fp32 (4T*batch, D): row block j = decoder token j (modality-major, time-minor); masked tokens get the
+ *           batch-constant row W_dec mask_token + b + per-dim + pos[t].  batch <= the engine's chunk. */
+int m3pc_decoder_scatter_embed(m3pc_handle_t h, int32_t batch, const void* enc_out, const uint8_t* masks, float* x_out, void* stream);
+/* K5 -- decoder block output -> predictions: final decoder norm, per-modality head LayerNorm -> Linear -> GELU -> Linear
+ * (mtm_model.py:397-433, :708-714) and the DiagGaussianActor mu / std (mtm_model.py:313-321).
+ *   x_dec device fp32 (4T*batch, D): residual stream after the last decoder block, BEFORE decoder.norm
+ *   out_* as in m3pc_forward, (batch, T, d); any may be NULL.  batch <= the engine's chunk. */
+int m3pc_heads(m3pc_handle_t h, int32_t batch, const float* x_dec, float* out_states, float* out_act_mu, float* out_act_std,
+               float* out_rewards, float* out_returns, void* stream);
+/* K6 -- candidate action sequences (finetune_omtm/learner.py:285-287, :156-167):
+ *   noise_mode 0: cand[n,t,:] = tanh(mu[T-h+t] + std[T-h+t] * eps[n,t,:]);  1: clamp(tanh(mu[T-h+t]) + 0.09 eps[n,t,:], +-0.99999)
+ *   mu, std device (T, A); eps device (n_cand, h, A) or NULL = Philox keyed by (seed, cand_offset + n); out (n_cand, h, A). */
+int m3pc_sample_candidates(const float* mu, const float* std, const float* eps, uint64_t seed, int32_t n_cand, int32_t horizon, int32_t act_dim,
+                           int32_t traj_length, int32_t noise_mode, int32_t cand_offset, float* out_candidates, void* stream);
+/* K7 -- TwinQ on every (candidate, step): q[n*h + t] = min(Q1, Q2)((s_hat - obs_mean) / obs_std, a) with
+ * s_hat = states_pred[n, T-h+t] * tok_std + tok_mean (finetune_omtm/learner.py:250-252, model.py:146-171).
+ *   states_pred device (n_cand, T, obs) raw head output; candidates device (n_cand, h, A); out_q device (n_cand*h). */
+int m3pc_twinq(m3pc_handle_t h, const float* states_pred, const float* candidates, int32_t n_cand, int32_t horizon, float* out_q, void* stream);
+/* K8 -- TD(lambda) score + softmax selection (finetune_omtm/learner.py:301-325) of ONE shard of candidates:
+ *   rewards_pred (n_cand, T) raw head output; exactly one of returns_pred (n_cand, T) [rtg_guiding: V_t = 1000 * return] and
+ *   qvals (n_cand*h) [critic guidance]; candidates (n_cand, h, A); expq (n_cand) injected Exp(1) draws or NULL = Philox;
+ *   norm_stats HOST float[4] = {rewards mean, rewards std, returns mean, returns std} of the tokenizers;
+ *   out_J (n_cand); out_eval_action / out_sample_action (A); out_partials (M3PC_PARTIAL_FLOATS) or NULL; out_indices (2) or NULL. */
+int m3pc_score_select(const float* rewards_pred, const float* returns_pred, const float* qvals, const float* candidates, const float* expq,
+                      const float* norm_stats, float discount, float lmbda, float temperature, int32_t n_cand, int32_t horizon,
+                      int32_t traj_length, int32_t act_dim, uint64_t seed, int32_t cand_offset, float* out_J, float* out_eval_action,
+                      float* out_sample_action, float* out_partials, int32_t* out_indices, void* stream);
+
 /* Device-side time (ms) spent between the first and last kernel of the most recent m3pc_plan / m3pc_forward
  * on this handle, measured with CUDA events on the caller's stream (valid after the stream is synchronised). */
 int m3pc_last_device_ms(m3pc_handle_t h, float* ms);

@@ -671,7 +671,7 @@ struct NeedSet {
 
 // decoder_embed of the encoder outputs: one grouped GEMM per run of kept tokens of one modality (mtm_model.py:646-661).
 // `compact`: write rows in encoder-token order (row block = dec_src[j]); otherwise in decoder order (row block = j).
-int decoder_embed(m3pc_engine* e, const void* enc_out, const int* dec_src, int Bc, bool compact, cudaStream_t st) {
+int decoder_embed(m3pc_engine* e, const void* enc_out, const int* dec_src, int Bc, bool compact, cudaStream_t st, float* xout = nullptr) {
   const int D = e->D, T = e->T;
   const size_t ab = act_bytes(e);
   GemmJob jobs[MAX_TOK];
@@ -686,7 +686,7 @@ int decoder_embed(m3pc_engine* e, const void* enc_out, const int* dec_src, int B
     ge.rows_per_group = Bc;
     ge.flags = EPI_OUT_F32 | EPI_ROWTABLE;
     const char* a = reinterpret_cast<const char*>(enc_out) + static_cast<size_t>(dec_src[j]) * Bc * D * ab;
-    float* c = e->X.as<float>() + static_cast<size_t>(compact ? dec_src[j] : j) * Bc * D;
+    float* c = (xout != nullptr ? xout : e->X.as<float>()) + static_cast<size_t>(compact ? dec_src[j] : j) * Bc * D;
     jobs[n++] = GemmJob{a, e->dec_w[k], e->dec_w16[k], c, len * Bc, D, D, ge};
     j += len;
   }
@@ -943,22 +943,64 @@ int decode_deep_restricted(m3pc_engine* e, const FwdIO& io, const void* enc_out,
   return restricted_last_layer(e, io, e->dec.layers[e->Ld - 1], ident, Sd, need, b0, Bc, st);
 }
 
+// Token tables of a mask layout (omtm._index / process_masks, mtm_model.py:534-591): kept tokens keep their order, modality-major;
+// every inference mask keeps per-modality order, so the restore permutation reduces to "decoder token j <- encoder row dec_src[j]".
+struct TokTables {
+  int enc_mod[MAX_TOK], enc_t[MAX_TOK], dec_src[MAX_TOK];
+  int S = 0;
+};
+TokTables token_tables(const uint8_t* mask, int T) {
+  TokTables tt;
+  for (int k = 0; k < 4; ++k)
+    for (int t = 0; t < T; ++t) {
+      if (mask[k * T + t]) {
+        tt.enc_mod[tt.S] = k;
+        tt.enc_t[tt.S] = t;
+        tt.dec_src[k * T + t] = tt.S++;
+      } else {
+        tt.dec_src[k * T + t] = -1;
+      }
+    }
+  return tt;
+}
+
+// K1 parameters: one EmbedTok per kept token (trajectory_encoding + the gather of forward_encoder, mtm_model.py:546-557, 619-632)
+EmbedParams embed_params(const m3pc_engine* e, const FwdIO& io, const TokTables& tt, int b0, int Bc) {
+  const int D = e->D, T = e->T;
+  EmbedParams ep{};
+  ep.n_tok = tt.S;
+  ep.B = Bc;
+  ep.b0 = b0;
+  for (int s = 0; s < tt.S; ++s) {
+    const int k = tt.enc_mod[s], t = tt.enc_t[s], d = e->dims[k];
+    const ModSrc& ms = io.src[k];
+    EmbedTok& tk = ep.tok[s];
+    if (ms.base2 != nullptr && t >= ms.t_split) {
+      tk.src = ms.base2 + static_cast<size_t>(b0) * ms.bstride2 + static_cast<size_t>(t - ms.t_split) * d;
+      tk.bstride = static_cast<int>(ms.bstride2);
+    } else if (ms.bdiv > 0) {
+      tk.src = ms.base + static_cast<size_t>(t) * d;  // the kernel adds ((b0 + b) / bdiv) * bstride
+      tk.bstride = static_cast<int>(ms.bstride);
+      tk.bdiv = ms.bdiv;
+    } else {
+      tk.src = ms.base + static_cast<size_t>(b0) * ms.bstride + static_cast<size_t>(t) * d;
+      tk.bstride = static_cast<int>(ms.bstride);
+    }
+    tk.wt = e->enc_wt[k];
+    tk.cvec = e->enc_cvec + (static_cast<size_t>(k) * T + t) * D;
+    tk.nmean = ms.normalize ? e->tok_mean[k] : nullptr;
+    tk.nstd = ms.normalize ? e->tok_std[k] : nullptr;
+    tk.d = d;
+  }
+  return ep;
+}
+
 int forward_chunk(m3pc_engine* e, const FwdIO& io, int b0, int Bc, cudaStream_t st) {
   const int D = e->D, T = e->T;
   const size_t ab = act_bytes(e);
-  // ---- token tables from the masks (mtm_model.py:534-544: kept tokens keep their order, modality-major) ----
-  int enc_mod[MAX_TOK], enc_t[MAX_TOK], dec_src[MAX_TOK];
-  int S = 0;
-  for (int k = 0; k < 4; ++k)
-    for (int t = 0; t < T; ++t) {
-      if (io.mask[k * T + t]) {
-        enc_mod[S] = k;
-        enc_t[S] = t;
-        dec_src[k * T + t] = S++;
-      } else {
-        dec_src[k * T + t] = -1;
-      }
-    }
+  const TokTables tt = token_tables(io.mask, T);
+  const int S = tt.S;
+  const int *enc_mod = tt.enc_mod, *enc_t = tt.enc_t, *dec_src = tt.dec_src;
   M3PC_REQUIRE(S > 0, "forward: every token is masked");
 
   // ---- which head rows does the caller consume? ----
@@ -1040,31 +1082,7 @@ int forward_chunk(m3pc_engine* e, const FwdIO& io, int b0, int Bc, cudaStream_t 
   }
 
   // ---- K1: embed + gather + first LayerNorm ----
-  EmbedParams ep{};
-  ep.n_tok = S;
-  ep.B = Bc;
-  ep.b0 = b0;
-  for (int s = 0; s < S; ++s) {
-    const int k = enc_mod[s], t = enc_t[s], d = e->dims[k];
-    const ModSrc& ms = io.src[k];
-    EmbedTok& tk = ep.tok[s];
-    if (ms.base2 != nullptr && t >= ms.t_split) {
-      tk.src = ms.base2 + static_cast<size_t>(b0) * ms.bstride2 + static_cast<size_t>(t - ms.t_split) * d;
-      tk.bstride = static_cast<int>(ms.bstride2);
-    } else if (ms.bdiv > 0) {
-      tk.src = ms.base + static_cast<size_t>(t) * d;  // the kernel adds ((b0 + b) / bdiv) * bstride
-      tk.bstride = static_cast<int>(ms.bstride);
-      tk.bdiv = ms.bdiv;
-    } else {
-      tk.src = ms.base + static_cast<size_t>(b0) * ms.bstride + static_cast<size_t>(t) * d;
-      tk.bstride = static_cast<int>(ms.bstride);
-    }
-    tk.wt = e->enc_wt[k];
-    tk.cvec = e->enc_cvec + (static_cast<size_t>(k) * T + t) * D;
-    tk.nmean = ms.normalize ? e->tok_mean[k] : nullptr;
-    tk.nstd = ms.normalize ? e->tok_std[k] : nullptr;
-    tk.d = d;
-  }
+  const EmbedParams ep = embed_params(e, io, tt, b0, Bc);
   const LayerW& first = e->Le > 0 ? e->enc.layers[0] : e->dec.layers[0];
   // shared-history analysis: the leading encoder tokens whose source row is shared by whole groups of batch rows (one window
   // for the whole batch: bstride 0; one window per environment: bdiv rows each) -- the chunk must hold whole groups
@@ -1135,11 +1153,12 @@ int forward(m3pc_engine* e, const FwdIO& io, int B, cudaStream_t st) {
 // K7: TwinQ on all (candidate, step) rows at once (the reference calls it h times on N rows, learner.py:250-252).
 // bf16 mode: the two hidden layers run on the tcgen05 GEMM (bf16 operands, fp32 accumulate, second layer written in fp32);
 // fp32 mode: CUDA-core fp32 GEMMs.  The final 256 -> 1 layer and min(q1, q2) are fp32 in both.
-int critic(m3pc_engine* e, int N, int h, cudaStream_t st) {
+int critic(m3pc_engine* e, int N, int h, cudaStream_t st, const float* states_pred = nullptr, const float* cand = nullptr, float* q_out = nullptr) {
   const int rows = N * h, in = e->obs + e->act, Hq = e->QH;
+  float* qv = q_out != nullptr ? q_out : e->qvals.as<float>();
   CriticInParams ci{};
-  ci.states_pred = e->pred_states.as<float>();
-  ci.cand = e->cand.as<float>();
+  ci.states_pred = states_pred != nullptr ? states_pred : e->pred_states.as<float>();
+  ci.cand = cand != nullptr ? cand : e->cand.as<float>();
   ci.tok_mean = e->tok_mean[M3PC_STATES];
   ci.tok_std = e->tok_std[M3PC_STATES];
   ci.obs_mean = e->obs_mean;
@@ -1165,7 +1184,7 @@ int critic(m3pc_engine* e, int N, int h, cudaStream_t st) {
     }
     M3PC_TRY(gemm_group(e, l1, 2, st));
     M3PC_TRY(gemm_group(e, l2, 2, st));
-    return launch_critic_out(outs[0], outs[1], e->q_w[0][2], e->q_b[0][2], e->q_w[1][2], e->q_b[1][2], e->qvals.as<float>(), rows, Hq, st);
+    return launch_critic_out(outs[0], outs[1], e->q_w[0][2], e->q_b[0][2], e->q_w[1][2], e->q_b[1][2], qv, rows, Hq, st);
   }
   for (int q = 0; q < 2; ++q) {
     GemmEpilogue ge;
@@ -1182,7 +1201,7 @@ int critic(m3pc_engine* e, int N, int h, cudaStream_t st) {
       M3PC_TRY(gemm_fp32(e->qa.as<float>(), e->q_w[q][1], outs[q], rows, Hq, Hq, ge, st));
     }
   }
-  return launch_critic_out(outs[0], outs[1], e->q_w[0][2], e->q_b[0][2], e->q_w[1][2], e->q_b[1][2], e->qvals.as<float>(), rows, Hq, st);
+  return launch_critic_out(outs[0], outs[1], e->q_w[0][2], e->q_b[0][2], e->q_w[1][2], e->q_b[1][2], qv, rows, Hq, st);
 }
 
 void set_window_sources(m3pc_engine* e, FwdIO& io, const float* ws, const float* wa, const float* wr, const float* wrt, long stride_mul) {
@@ -1647,6 +1666,124 @@ int m3pc_layernorm(const float* x, const float* gamma, const float* beta, void* 
 int m3pc_attention(const void* qkv, void* out, int32_t B, int32_t S, int32_t n_head, int32_t is_bf16, void* stream) {
   M3PC_REQUIRE(qkv && out, "null argument");
   return m3pc::launch_attention(qkv, out, B, S, n_head, is_bf16 != 0, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---- kernel-level entries K1 / K4 / K5 / K6 / K7 / K8: the same launchers m3pc_forward / m3pc_plan use ----
+namespace {
+int io_from_tokens(m3pc_handle_t h, m3pc::FwdIO& io, const float* ts, const float* ta, const float* tr, const float* tt, const uint8_t* masks) {
+  M3PC_REQUIRE(h != nullptr && h->finalized, "kernel-level call before m3pc_finalize_params");
+  M3PC_REQUIRE(masks != nullptr, "null masks");
+  const int T = h->T;
+  io.src[M3PC_STATES] = m3pc::ModSrc{ts, static_cast<long>(T) * h->obs, false};
+  io.src[M3PC_ACTIONS] = m3pc::ModSrc{ta, static_cast<long>(T) * h->act, false};
+  io.src[M3PC_REWARDS] = m3pc::ModSrc{tr, static_cast<long>(T), false};
+  io.src[M3PC_RETURNS] = m3pc::ModSrc{tt, static_cast<long>(T), false};
+  for (int i = 0; i < 4 * T; ++i) {
+    M3PC_REQUIRE(masks[i] <= 1, "mask entries must be 0 or 1");
+    io.mask[i] = masks[i];
+  }
+  return M3PC_OK;
+}
+}  // namespace
+
+int m3pc_embed_gather(m3pc_handle_t h, int32_t batch, const float* tok_states, const float* tok_actions, const float* tok_rewards,
+                      const float* tok_returns, const uint8_t* masks, float* x_out, void* y_out, void* stream) {
+  M3PC_REQUIRE(tok_states && tok_actions && tok_rewards && tok_returns && x_out && y_out, "null argument");
+  m3pc::FwdIO io{};
+  M3PC_TRY(io_from_tokens(h, io, tok_states, tok_actions, tok_rewards, tok_returns, masks));
+  M3PC_REQUIRE(batch >= 1 && batch <= h->cfg.max_batch, "batch exceeds cfg.max_batch");
+  const m3pc::TokTables tt = m3pc::token_tables(io.mask, h->T);
+  M3PC_REQUIRE(tt.S > 0, "every token is masked");
+  const m3pc::EmbedParams ep = m3pc::embed_params(h, io, tt, 0, batch);
+  const m3pc::LayerW& first = h->enc.layers[0];
+  return m3pc::launch_embed(ep, h->D, x_out, y_out, h->bf16, first.n1_w, first.n1_b, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int m3pc_decoder_scatter_embed(m3pc_handle_t h, int32_t batch, const void* enc_out, const uint8_t* masks, float* x_out, void* stream) {
+  M3PC_REQUIRE(h != nullptr && h->finalized && enc_out && masks && x_out, "bad argument");
+  M3PC_REQUIRE(batch >= 1 && batch <= h->chunk, "batch exceeds the engine's chunk (workspace rows)");
+  const int T = h->T, D = h->D;
+  for (int i = 0; i < 4 * T; ++i) M3PC_REQUIRE(masks[i] <= 1, "mask entries must be 0 or 1");
+  const m3pc::TokTables tt = m3pc::token_tables(masks, T);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  m3pc::FillParams fp{};
+  fp.B = batch;
+  for (int j = 0; j < 4 * T; ++j)
+    if (tt.dec_src[j] < 0) {
+      fp.row[fp.n] = h->dec_maskrow + static_cast<size_t>(j) * D;
+      fp.bstride[fp.n] = 0;
+      fp.tok[fp.n] = j;
+      ++fp.n;
+    }
+  if (fp.n > 0) M3PC_TRY(m3pc::launch_fill_rows(fp, D, x_out, st));
+  if (tt.S == 0) return M3PC_OK;
+  return m3pc::decoder_embed(h, enc_out, tt.dec_src, batch, false, st, x_out);
+}
+
+int m3pc_heads(m3pc_handle_t h, int32_t batch, const float* x_dec, float* out_states, float* out_act_mu, float* out_act_std,
+               float* out_rewards, float* out_returns, void* stream) {
+  M3PC_REQUIRE(h != nullptr && h->finalized && x_dec, "bad argument");
+  M3PC_REQUIRE(batch >= 1 && batch <= h->chunk, "batch exceeds the engine's chunk (workspace rows)");
+  M3PC_REQUIRE((out_act_mu == nullptr) == (out_act_std == nullptr), "out_act_mu and out_act_std go together");
+  const int T = h->T, Sd = 4 * T;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  m3pc::FwdIO io{};
+  io.out_states = out_states; io.out_mu = out_act_mu; io.out_std = out_act_std; io.out_rewards = out_rewards; io.out_returns = out_returns;
+  m3pc::NeedSet need;
+  const float* outp[4] = {out_states, out_act_mu, out_rewards, out_returns};
+  int all_tok[m3pc::MAX_TOK];
+  for (int j = 0; j < Sd; ++j) all_tok[j] = j;
+  for (int k = 0; k < 4; ++k) {
+    need.q0[k] = k * T;  // row block of (k, t = 0) in decoder order
+    need.t0[k] = 0;
+    need.nt[k] = outp[k] != nullptr ? T : 0;
+  }
+  need.n = Sd;
+  M3PC_TRY(m3pc::final_norms(h, x_dec, Sd, all_tok, batch, st));
+  return m3pc::heads(h, io, need, h->Y.p, h->Y2.p, 0, batch, st);
+}
+
+int m3pc_sample_candidates(const float* mu, const float* std, const float* eps, uint64_t seed, int32_t n_cand, int32_t horizon, int32_t act_dim,
+                           int32_t traj_length, int32_t noise_mode, int32_t cand_offset, float* out_candidates, void* stream) {
+  M3PC_REQUIRE(mu && std && out_candidates, "null argument");
+  M3PC_REQUIRE(n_cand >= 1 && horizon >= 1 && horizon <= traj_length && traj_length <= M3PC_MAX_T && act_dim >= 1 && act_dim <= M3PC_MAX_ACT,
+               "shape out of range");
+  M3PC_REQUIRE(noise_mode == 0 || noise_mode == 1, "noise_mode must be 0 (tanh(mu + std eps)) or 1 (clamp(tanh(mu) + 0.09 eps))");
+  m3pc::CandParams cp{};
+  cp.mu = mu; cp.std = std; cp.eps = eps; cp.cand = out_candidates;
+  cp.N = n_cand; cp.h = horizon; cp.A = act_dim; cp.T = traj_length;
+  cp.noise_mode = noise_mode; cp.seed = seed; cp.cand_offset = cand_offset;
+  return m3pc::launch_candidates(cp, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int m3pc_twinq(m3pc_handle_t h, const float* states_pred, const float* candidates, int32_t n_cand, int32_t horizon, float* out_q, void* stream) {
+  M3PC_REQUIRE(h != nullptr && h->finalized && states_pred && candidates && out_q, "bad argument");
+  M3PC_REQUIRE(h->has_critic, "no critic parameters were loaded");
+  M3PC_REQUIRE(n_cand >= 1 && n_cand <= h->cfg.max_batch && horizon >= 1 && horizon <= h->T, "shape out of range");
+  return m3pc::critic(h, n_cand, horizon, reinterpret_cast<cudaStream_t>(stream), states_pred, candidates, out_q);
+}
+
+int m3pc_score_select(const float* rewards_pred, const float* returns_pred, const float* qvals, const float* candidates, const float* expq,
+                      const float* norm_stats, float discount, float lmbda, float temperature, int32_t n_cand, int32_t horizon,
+                      int32_t traj_length, int32_t act_dim, uint64_t seed, int32_t cand_offset, float* out_J, float* out_eval_action,
+                      float* out_sample_action, float* out_partials, int32_t* out_indices, void* stream) {
+  M3PC_REQUIRE(rewards_pred && candidates && norm_stats && out_J && out_eval_action && out_sample_action, "null argument");
+  M3PC_REQUIRE((returns_pred != nullptr) != (qvals != nullptr), "exactly one of returns_pred (rtg_guiding) and qvals (critic guidance) must be given");
+  M3PC_REQUIRE(n_cand >= 1 && horizon >= 1 && horizon <= traj_length && traj_length <= M3PC_MAX_T && act_dim >= 1 && act_dim <= M3PC_MAX_ACT,
+               "shape out of range");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  m3pc::ScoreParams sp{};
+  sp.rewards_pred = rewards_pred; sp.returns_pred = returns_pred; sp.qvals = qvals;
+  sp.rw_mean = norm_stats[0]; sp.rw_std = norm_stats[1]; sp.rt_mean = norm_stats[2]; sp.rt_std = norm_stats[3];
+  sp.discount = discount; sp.lmbda = lmbda;
+  sp.N = n_cand; sp.h = horizon; sp.T = traj_length; sp.J = out_J;
+  M3PC_TRY(m3pc::launch_score(sp, st));
+  m3pc::SelectParams sl{};
+  sl.n_env = 1; sl.J = out_J; sl.cand = candidates; sl.expq = expq;
+  sl.N = n_cand; sl.h = horizon; sl.A = act_dim;
+  sl.temperature = temperature; sl.seed = seed; sl.cand_offset = cand_offset;
+  sl.eval_action = out_eval_action; sl.sample_action = out_sample_action; sl.partials = out_partials; sl.indices = out_indices;
+  return m3pc::launch_select(sl, st);
 }
 
 int m3pc_last_device_ms(m3pc_handle_t h, float* ms) {

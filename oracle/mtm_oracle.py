@@ -121,10 +121,13 @@ def encoder_layer(x: torch.Tensor, sd: Mapping[str, torch.Tensor], p: str, n_hea
     return x + F.linear(h, sd[p + ".linear2.weight"], sd[p + ".linear2.bias"])
 
 
-def transformer(x: torch.Tensor, sd: Mapping[str, torch.Tensor], p: str, n_layer: int, n_head: int) -> torch.Tensor:
-    """nn.TransformerEncoder(layers, norm=LayerNorm): the stack followed by the final norm."""
+def transformer(x: torch.Tensor, sd: Mapping[str, torch.Tensor], p: str, n_layer: int, n_head: int, stages=None) -> torch.Tensor:
+    """nn.TransformerEncoder(layers, norm=LayerNorm): the stack followed by the final norm.
+    ``stages`` (test hook): receives the residual stream before the final norm under ``p + "_x"``."""
     for i in range(n_layer):
         x = encoder_layer(x, sd, f"{p}.layers.{i}", n_head)
+    if stages is not None:
+        stages[p + "_x"] = x
     return layer_norm(x, sd[p + ".norm.weight"], sd[p + ".norm.bias"])
 
 
@@ -167,7 +170,7 @@ def mtm_forward(
         feats.append(emb[k][:, ids])
     x = torch.cat(feats, dim=1)
     stages["enc_in"] = x
-    x = transformer(x, sd, "encoder", n_enc_layer, n_head)
+    x = transformer(x, sd, "encoder", n_enc_layer, n_head, stages)
     stages["enc_out"] = x
     enc = OrderedDict()
     idx = 0
@@ -188,7 +191,7 @@ def mtm_forward(
         dec_in.append(e)
     x = torch.cat(dec_in, dim=1)
     stages["dec_in"] = x
-    x = transformer(x, sd, "decoder", n_dec_layer, n_head)
+    x = transformer(x, sd, "decoder", n_dec_layer, n_head, stages)
     stages["dec_out"] = x
 
     out: Dict[str, object] = {}
