@@ -156,10 +156,32 @@ typedef struct {
   float* dbg_expect_return; /* device (n_cand) or NULL: J_n before the max subtraction */
   float* dbg_candidates;    /* device (n_cand,h,A) or NULL */
   int32_t* dbg_indices;     /* device (2) or NULL: [argmax_n J_n, sampled idx] (global ids) */
-  void* reserved1[4];
+  int32_t exchange;         /* 1 (n_env <= 1, after m3pc_exchange_connect): this call plans ONE SHARD of the candidates; its selection
+                               kernel stores the shard record into every rank's exchange buffer over peer memory (NVLink), waits for
+                               the records of all ranks and merges them, so out_eval_action / out_sample_action / dbg_indices hold
+                               the GLOBAL result on every rank -- no collective launch, nothing outside the captured CUDA graph.
+                               Every rank of the group must issue the same sequence of exchange plans. */
+  int32_t reserved0;
+  void* reserved1[3];
 } m3pc_plan_args_t;
 
 int m3pc_plan(m3pc_handle_t h, const m3pc_plan_args_t* args, void* stream);
+
+/* Peer exchange of the per-shard records ("only per-shard best scores/indices are combined ... over
+ * NVLink").  The reference is single-GPU (finetune.py:154); this is the one exchange step candidate sharding adds.
+ *   m3pc_exchange_local    allocates this handle's exchange buffer (once) and returns a CUDA IPC handle for it
+ *                          (M3PC_IPC_HANDLE_BYTES bytes, for peers in other processes) and/or its device pointer (peers in the
+ *                          same process); either output may be NULL.
+ *   m3pc_exchange_connect  wires the group: `ipc_handles` = world handles concatenated in rank order (e.g. gathered with
+ *                          torch.distributed.all_gather_object) -- opened with cudaIpcOpenMemHandle, which enables peer
+ *                          access -- OR `device_ptrs` = world device pointers valid on this device; the other must be NULL.
+ *                          Resets the epoch sequence: all ranks (re)connect together.  world <= 32.
+ *   m3pc_exchange_status   epochs completed, and the epoch of a wait that timed out (0 = none; a rank whose peer never
+ *                          launched its plan gives up after 2 s and returns NaN actions instead of hanging the GPU). */
+#define M3PC_IPC_HANDLE_BYTES 64
+int m3pc_exchange_local(m3pc_handle_t h, uint8_t* out_ipc_handle, void** out_device_ptr);
+int m3pc_exchange_connect(m3pc_handle_t h, int32_t rank, int32_t world, const uint8_t* ipc_handles, void* const* device_ptrs);
+int m3pc_exchange_status(m3pc_handle_t h, uint64_t* out_epoch, uint64_t* out_failed_epoch);
 
 /* Combine `n_shards` records (device, n_shards*M3PC_PARTIAL_FLOATS, e.g. the output of an NCCL all-gather)
  * into the global eval / sample action: log-sum-exp merge of the per-shard softmax partials. */

@@ -21,6 +21,7 @@ PREC_BF16, PREC_FP32 = 0, 1
 GUIDE_RTG, GUIDE_CRITIC, GUIDE_NOISE_CRITIC, GUIDE_SAMPLING = 0, 1, 2, 3
 MAX_T, MAX_ACT, MAX_OBS = 16, 32, 128
 PARTIAL_FLOATS = 8 + 2 * MAX_ACT
+IPC_HANDLE_BYTES = 64
 
 GUIDANCE = {
     "rtg_guiding": GUIDE_RTG,
@@ -32,7 +33,7 @@ GUIDANCE = {
 #: every symbol include/m3pc.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = (
     "m3pc_last_error", "m3pc_version", "m3pc_create", "m3pc_destroy", "m3pc_set_param", "m3pc_finalize_params", "m3pc_set_option",
-    "m3pc_forward", "m3pc_plan", "m3pc_merge_partials", "m3pc_backward_plan", "m3pc_backward_plan_draws", "m3pc_ring_append", "m3pc_ring_windows", "m3pc_gemm_bf16", "m3pc_gemm_bf16_grouped", "m3pc_gemm_ln_bf16", "m3pc_gemm_fp32",
+    "m3pc_forward", "m3pc_plan", "m3pc_merge_partials", "m3pc_exchange_local", "m3pc_exchange_connect", "m3pc_exchange_status", "m3pc_backward_plan", "m3pc_backward_plan_draws", "m3pc_ring_append", "m3pc_ring_windows", "m3pc_gemm_bf16", "m3pc_gemm_bf16_grouped", "m3pc_gemm_ln_bf16", "m3pc_gemm_fp32",
     "m3pc_layernorm", "m3pc_attention", "m3pc_embed_gather", "m3pc_decoder_scatter_embed", "m3pc_heads", "m3pc_sample_candidates", "m3pc_twinq",
     "m3pc_score_select", "m3pc_last_device_ms", "m3pc_last_launch_count", "m3pc_set_profile", "m3pc_get_profile",
 )
@@ -58,7 +59,7 @@ class PlanArgs(C.Structure):
         ("eps", C.c_void_p), ("expq", C.c_void_p), ("seed", C.c_uint64),
         ("out_eval_action", C.c_void_p), ("out_sample_action", C.c_void_p), ("out_partials", C.c_void_p),
         ("dbg_expect_return", C.c_void_p), ("dbg_candidates", C.c_void_p), ("dbg_indices", C.c_void_p),
-        ("reserved1", C.c_void_p * 4),
+        ("exchange", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_void_p * 3),
     ]
 
 
@@ -100,6 +101,9 @@ def lib() -> C.CDLL:
     L.m3pc_forward.argtypes = [vp, i32, f32p, f32p, f32p, f32p, vp, f32p, f32p, f32p, f32p, f32p, vp]
     L.m3pc_plan.argtypes = [vp, C.POINTER(PlanArgs), vp]
     L.m3pc_merge_partials.argtypes = [vp, f32p, i32, C.c_float, f32p, f32p, vp, vp]
+    L.m3pc_exchange_local.argtypes = [vp, vp, C.POINTER(vp)]
+    L.m3pc_exchange_connect.argtypes = [vp, i32, i32, vp, vp]
+    L.m3pc_exchange_status.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.m3pc_backward_plan.argtypes = [vp, i32, i32, i32, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, vp]
     L.m3pc_backward_plan_draws.argtypes = [vp, i32, i32, i32, i32, f32p, f32p, f32p, f32p, f32p, C.c_uint64, f32p, f32p, vp]
     L.m3pc_ring_append.argtypes = [f32p, i32, i32, i32, i32, i32, f32p, f32p, f32p, vp]

@@ -148,7 +148,7 @@ struct m3pc_engine {
 
   // CUDA-graph replay of m3pc_plan (production path: on-device Philox noise, no debug outputs)
   struct PlanKey {
-    int guidance, horizon, n_cand, cand_offset, n_env;
+    int guidance, horizon, n_cand, cand_offset, n_env, exchange;
     float discount, temperature, lmbda;
     const void *ws, *wa, *wr, *wt, *ev, *sm, *pt;
     bool operator<(const PlanKey& o) const { return std::memcmp(this, &o, sizeof(PlanKey)) < 0; }
@@ -162,6 +162,12 @@ struct m3pc_engine {
   bool use_graphs = true;
   DevBuf seed_scalar;
   const unsigned long long* seed_ptr_active = nullptr;  // non-null while (re)building / replaying a graph
+
+  // peer exchange of per-shard records (candidate sharding over GPUs; kernels.cuh ExchangeParams)
+  DevBuf xch_buf, xch_epoch;
+  void* xch_peer[XCH_MAX_RANKS] = {};
+  std::vector<void*> xch_opened;  // cudaIpcOpenMemHandle'd peers (closed in the destructor)
+  int xch_rank = 0, xch_world = 0;
 
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaStream_t cap_stream = nullptr;  // private stream the plan graphs are captured on
@@ -183,6 +189,7 @@ struct m3pc_engine {
 
   ~m3pc_engine() {
     drop_graphs();
+    for (void* q : xch_opened) cudaIpcCloseMemHandle(q);
     if (cap_stream) cudaStreamDestroy(cap_stream);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -1218,7 +1225,9 @@ int plan_body(m3pc_engine* e, const m3pc_plan_args_t* a, cudaStream_t st) {
   const int E = a->n_env > 1 ? a->n_env : 1;  // lock-step environments planned by this call
   const long R = static_cast<long>(E) * N;    // pass-2 rows: environment-major, candidate-minor
   M3PC_REQUIRE(a->n_env >= 0, "n_env must be >= 0");
-  M3PC_REQUIRE(E == 1 || (a->out_partials == nullptr && a->cand_offset == 0), "n_env > 1 cannot be combined with candidate sharding");
+  M3PC_REQUIRE(E == 1 || (a->out_partials == nullptr && a->cand_offset == 0 && a->exchange == 0), "n_env > 1 cannot be combined with candidate sharding");
+  M3PC_REQUIRE(a->exchange == 0 || a->exchange == 1, "exchange must be 0 or 1");
+  M3PC_REQUIRE(a->exchange == 0 || (e->xch_world >= 1 && a->guidance != M3PC_GUIDE_SAMPLING), "exchange requested but m3pc_exchange_connect was not called (or plan = False)");
   M3PC_REQUIRE(E <= e->cfg.max_batch, "n_env exceeds cfg.max_batch");
   M3PC_REQUIRE(h >= 1 && h <= T, "horizon must be in [1, traj_length]");
   M3PC_REQUIRE(a->guidance >= 0 && a->guidance <= 3, "unknown guidance");
@@ -1305,6 +1314,13 @@ int plan_body(m3pc_engine* e, const m3pc_plan_args_t* a, cudaStream_t st) {
   sl.temperature = a->temperature; sl.seed = a->seed; sl.cand_offset = a->cand_offset; sl.seed_ptr = e->seed_ptr_active;
   sl.eval_action = a->out_eval_action; sl.sample_action = a->out_sample_action;
   sl.partials = a->out_partials; sl.indices = a->dbg_indices;
+  if (a->exchange) {
+    for (int g = 0; g < e->xch_world; ++g) sl.xch.peer[g] = e->xch_peer[g];
+    sl.xch.rank = e->xch_rank;
+    sl.xch.world = e->xch_world;
+    sl.xch.epoch = e->xch_epoch.as<unsigned long long>();
+    sl.xch.timeout_ns = 2000000000ull;  // 2 s: a peer that never launches its plan must not hang this GPU
+  }
   return launch_select(sl, st);
 }
 
@@ -1320,6 +1336,7 @@ int plan(m3pc_engine* e, const m3pc_plan_args_t* a, cudaStream_t st) {
   m3pc_engine::PlanKey key;
   std::memset(&key, 0, sizeof(key));
   key.guidance = a->guidance; key.horizon = a->horizon; key.n_cand = a->n_cand; key.cand_offset = a->cand_offset; key.n_env = a->n_env > 1 ? a->n_env : 1;
+  key.exchange = a->exchange;
   key.discount = a->discount; key.temperature = a->temperature; key.lmbda = a->lmbda;
   key.ws = a->win_states; key.wa = a->win_actions; key.wr = a->win_rewards; key.wt = a->win_returns_tok;
   key.ev = a->out_eval_action; key.sm = a->out_sample_action; key.pt = a->out_partials;
@@ -1573,6 +1590,72 @@ int m3pc_merge_partials(m3pc_handle_t h, const float* partials, int32_t n_shards
   M3PC_REQUIRE(h != nullptr && partials && out_eval_action && out_sample_action && n_shards >= 1, "bad argument");
   return m3pc::launch_merge(partials, n_shards, h->act, temperature, out_eval_action, out_sample_action, out_indices,
                             reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---- peer exchange wiring (candidate sharding over GPUs) ----
+namespace {
+int xch_alloc(m3pc_handle_t h) {
+  if (h->xch_buf.p != nullptr) return M3PC_OK;
+  M3PC_TRY(h->xch_buf.alloc(m3pc::XCH_BYTES));
+  M3PC_CHECK_CUDA(cudaMemset(h->xch_buf.p, 0, m3pc::XCH_BYTES));
+  M3PC_TRY(h->xch_epoch.alloc(16));
+  M3PC_CHECK_CUDA(cudaMemset(h->xch_epoch.p, 0, 16));
+  M3PC_CHECK_CUDA(cudaDeviceSynchronize());
+  return M3PC_OK;
+}
+}  // namespace
+
+int m3pc_exchange_local(m3pc_handle_t h, uint8_t* out_ipc_handle, void** out_device_ptr) {
+  M3PC_REQUIRE(h != nullptr, "null handle");
+  M3PC_TRY(xch_alloc(h));
+  if (out_ipc_handle != nullptr) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == M3PC_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+    cudaIpcMemHandle_t ih;
+    M3PC_CHECK_CUDA(cudaIpcGetMemHandle(&ih, h->xch_buf.p));
+    std::memcpy(out_ipc_handle, &ih, sizeof(ih));
+  }
+  if (out_device_ptr != nullptr) *out_device_ptr = h->xch_buf.p;
+  return M3PC_OK;
+}
+
+int m3pc_exchange_connect(m3pc_handle_t h, int32_t rank, int32_t world, const uint8_t* ipc_handles, void* const* device_ptrs) {
+  M3PC_REQUIRE(h != nullptr, "null handle");
+  M3PC_REQUIRE(world >= 1 && world <= m3pc::XCH_MAX_RANKS && rank >= 0 && rank < world, "rank / world out of range");
+  M3PC_REQUIRE((ipc_handles != nullptr) != (device_ptrs != nullptr), "give either IPC handles (peers in other processes) or device pointers (same process)");
+  M3PC_TRY(xch_alloc(h));
+  M3PC_CHECK_CUDA(cudaDeviceSynchronize());
+  h->drop_graphs();  // captured plans hold the previous peer table
+  for (void* q : h->xch_opened) cudaIpcCloseMemHandle(q);
+  h->xch_opened.clear();
+  for (int g = 0; g < world; ++g) {
+    if (g == rank) {
+      h->xch_peer[g] = h->xch_buf.p;
+    } else if (device_ptrs != nullptr) {
+      M3PC_REQUIRE(device_ptrs[g] != nullptr, "null peer pointer");
+      h->xch_peer[g] = device_ptrs[g];
+    } else {
+      cudaIpcMemHandle_t ih;
+      std::memcpy(&ih, ipc_handles + static_cast<size_t>(g) * sizeof(ih), sizeof(ih));
+      void* q = nullptr;
+      M3PC_CHECK_CUDA(cudaIpcOpenMemHandle(&q, ih, cudaIpcMemLazyEnablePeerAccess));
+      h->xch_opened.push_back(q);
+      h->xch_peer[g] = q;
+    }
+  }
+  // a (re)connected group starts a fresh epoch sequence; every rank must (re)connect together
+  M3PC_CHECK_CUDA(cudaMemset(h->xch_buf.p, 0, m3pc::XCH_BYTES));
+  M3PC_CHECK_CUDA(cudaMemset(h->xch_epoch.p, 0, 16));
+  M3PC_CHECK_CUDA(cudaDeviceSynchronize());
+  h->xch_rank = rank;
+  h->xch_world = world;
+  return M3PC_OK;
+}
+
+int m3pc_exchange_status(m3pc_handle_t h, uint64_t* out_epoch, uint64_t* out_failed_epoch) {
+  M3PC_REQUIRE(h != nullptr && h->xch_buf.p != nullptr && out_epoch && out_failed_epoch, "bad argument (or exchange not set up)");
+  M3PC_CHECK_CUDA(cudaMemcpy(out_epoch, h->xch_epoch.p, 8, cudaMemcpyDeviceToHost));
+  M3PC_CHECK_CUDA(cudaMemcpy(out_failed_epoch, reinterpret_cast<const char*>(h->xch_buf.p) + m3pc::XCH_ERR_OFFSET, 8, cudaMemcpyDeviceToHost));
+  return M3PC_OK;
 }
 
 int m3pc_backward_plan(m3pc_handle_t h, int32_t mode, int32_t n_env, int32_t horizon, const float* win_states, const float* win_actions,

@@ -177,6 +177,25 @@ struct ScoreParams {
 };
 int launch_score(const ScoreParams& p, cudaStream_t st);
 
+// Peer exchange of the per-shard records (candidate sharding over GPUs): every rank owns one buffer that
+// ALL ranks can store into (peer-mapped over NVLink: CUDA IPC between processes, plain pointers inside one process):
+//     float    rec [2][world][M3PC_PARTIAL_FLOATS]     record of rank g for plans of parity s at rec[s][g]
+//     uint64   flag[2][world]                           epoch of the record that is complete in rec[s][g]
+// The select kernel of rank r stores its record into slot [epoch & 1][r] of every rank's buffer (its own included), publishes
+// it with a system-scope release store of the epoch, waits until all `world` flags of its own buffer show the epoch and merges
+// the records -- ONE kernel does the selection, the all-gather and the merge; no NCCL launch, nothing outside the CUDA graph.
+// Two slots suffice: a rank can only be one plan ahead of the slowest rank (it needs everybody's record to finish a plan).
+constexpr int XCH_MAX_RANKS = 32;
+constexpr size_t XCH_FLAG_OFFSET = sizeof(float) * 2 * XCH_MAX_RANKS * M3PC_PARTIAL_FLOATS;
+constexpr size_t XCH_ERR_OFFSET = XCH_FLAG_OFFSET + sizeof(unsigned long long) * 2 * XCH_MAX_RANKS;  // uint64: epoch of a timed-out wait
+constexpr size_t XCH_BYTES = XCH_ERR_OFFSET + 64;
+struct ExchangeParams {
+  void* peer[XCH_MAX_RANKS];      // exchange buffer of every rank, as addressable from THIS device
+  int rank, world;                // world == 0: no exchange
+  unsigned long long* epoch;      // device scalar of this handle: plans exchanged so far
+  unsigned long long timeout_ns;  // give up (NaN actions, error word set) instead of spinning forever if a peer never arrives
+};
+
 // One thread block per environment e (grid = n_env): J, cand, expq are offset by e*N, the outputs by e*A (indices by 2e).
 struct SelectParams {
   int n_env;          // >= 1
@@ -192,6 +211,7 @@ struct SelectParams {
   float* sample_action;  // (A)
   float* partials;       // (M3PC_PARTIAL_FLOATS) or null
   int* indices;          // (2) or null
+  ExchangeParams xch;    // xch.world > 0 (n_env == 1 only): exchange + merge inside the kernel; the outputs are the GLOBAL result
 };
 int launch_select(const SelectParams& p, cudaStream_t st);
 int launch_merge(const float* partials, int n_shards, int A, float temperature, float* eval_action, float* sample_action, int* indices,

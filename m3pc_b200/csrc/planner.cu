@@ -169,11 +169,54 @@ __device__ __forceinline__ void block_argmax(float& v, int& idx, float* redv, in
   }
 }
 
+// log-sum-exp merge of per-shard records, by ONE thread; `ld` reads a record float (plain or cache-volatile)
+template <typename Ld>
+__device__ __forceinline__ void merge_records(Ld ld, int n_shards, int A, float temperature, float* eval_action, float* sample_action, int* indices) {
+  float m = -INFINITY;
+  for (int g = 0; g < n_shards; ++g) m = fmaxf(m, ld(g, 0));
+  float Z = 0.f, kbest = -INFINITY, jbest = -INFINITY;
+  int kg = 0, ji = 0;
+  for (int g = 0; g < n_shards; ++g) {
+    const float sc = expf((ld(g, 0) - m) * temperature);
+    Z += ld(g, 1) * sc;
+    const float key = ld(g, 4) * sc;
+    if (key > kbest) { kbest = key; kg = g; }
+    if (ld(g, 2) > jbest) { jbest = ld(g, 2); ji = __float_as_int(ld(g, 3)); }
+  }
+  for (int a = 0; a < A; ++a) {
+    float U = 0.f;
+    for (int g = 0; g < n_shards; ++g) U += ld(g, 8 + a) * expf((ld(g, 0) - m) * temperature);
+    eval_action[a] = U / Z;
+    sample_action[a] = ld(kg, 8 + A + a);
+  }
+  if (indices) {
+    indices[0] = ji;
+    indices[1] = __float_as_int(ld(kg, 5));
+  }
+}
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const __grid_constant__ SelectParams p) {
   PDL_PROLOGUE();
   __shared__ float redv[32];
   __shared__ int redi[32];
+  __shared__ float rec[M3PC_PARTIAL_FLOATS];  // this shard's record (exchange mode)
+  __shared__ int xch_failed;
   const int tid = threadIdx.x;
+  const bool exchange = p.xch.world > 0;
   const int stride_a0 = p.h * p.A;
   const unsigned long long seed = p.seed_ptr ? *p.seed_ptr : p.seed;
   // one block per environment: this block's slice of every per-candidate array
@@ -219,62 +262,81 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const __grid_consta
     const float U = block_sum(u, redv);
     if (tid == 0) {
       const float sa = bad_k ? nanv : candv[static_cast<size_t>(ki) * stride_a0 + a];
-      eval_action[a] = U / Z;
-      sample_action[a] = sa;
-      if (p.partials) {
-        p.partials[8 + a] = U;
-        p.partials[8 + p.A + a] = sa;
+      if (!exchange) {
+        eval_action[a] = U / Z;
+        sample_action[a] = sa;
       }
+      rec[8 + a] = U;
+      rec[8 + p.A + a] = sa;
     }
   }
   if (tid == 0) {
-    if (p.partials) {
-      p.partials[0] = m;
-      p.partials[1] = Z;
-      p.partials[2] = m;
-      p.partials[3] = __int_as_float(p.cand_offset + mi);
-      p.partials[4] = kbest;
-      p.partials[5] = __int_as_float(p.cand_offset + ki);
-      p.partials[6] = static_cast<float>(p.N);
-      p.partials[7] = 0.f;
-    }
-    if (p.indices) {
+    rec[0] = m;
+    rec[1] = Z;
+    rec[2] = m;
+    rec[3] = __int_as_float(p.cand_offset + mi);
+    rec[4] = kbest;
+    rec[5] = __int_as_float(p.cand_offset + ki);
+    rec[6] = static_cast<float>(p.N);
+    rec[7] = 0.f;
+    if (p.indices && !exchange) {
       p.indices[2 * env + 0] = p.cand_offset + mi;
       p.indices[2 * env + 1] = p.cand_offset + ki;
     }
+    xch_failed = 0;
+  }
+  __syncthreads();
+  const int n_rec = 8 + 2 * p.A;
+  if (p.partials)
+    for (int f = tid; f < n_rec; f += SEL_THREADS) p.partials[f] = rec[f];
+  if (!exchange) return;
+
+  // ---- all-gather of the records over peer memory + merge (one block: n_env == 1) ----
+  const ExchangeParams& x = p.xch;
+  const unsigned long long ep = *x.epoch + 1ull;  // epochs start at 1: the flags are zero-initialised
+  const int slot = static_cast<int>(ep & 1ull);
+  for (int i = tid; i < x.world * n_rec; i += SEL_THREADS) {
+    const int g = i / n_rec, f = i - g * n_rec;
+    float* dst = reinterpret_cast<float*>(x.peer[g]) + (static_cast<size_t>(slot) * XCH_MAX_RANKS + x.rank) * M3PC_PARTIAL_FLOATS + f;
+    __stcg(dst, rec[f]);  // peer-mapped (NVLink) or local global memory
+  }
+  __threadfence_system();  // every thread's record stores are visible system-wide before the flag is
+  __syncthreads();
+  if (tid < x.world) {
+    unsigned long long* pf = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(x.peer[tid]) + XCH_FLAG_OFFSET) + slot * XCH_MAX_RANKS + x.rank;
+    st_release_sys_u64(pf, ep);
+    const unsigned long long* mf = reinterpret_cast<const unsigned long long*>(reinterpret_cast<const char*>(x.peer[x.rank]) + XCH_FLAG_OFFSET) + slot * XCH_MAX_RANKS + tid;
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys_u64(mf) < ep) {
+      if (global_timer_ns() - t0 > x.timeout_ns) {  // a peer never arrived: fail loudly instead of hanging the GPU
+        xch_failed = 1;
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (xch_failed) {
+      *reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(x.peer[x.rank]) + XCH_ERR_OFFSET) = ep;
+      for (int a = 0; a < p.A; ++a) eval_action[a] = sample_action[a] = nanv;
+    } else {
+      const float* base = reinterpret_cast<const float*>(x.peer[x.rank]) + static_cast<size_t>(slot) * XCH_MAX_RANKS * M3PC_PARTIAL_FLOATS;
+      // cache-volatile loads: the lines were written by peers through NVLink, L1 may still hold the slot's previous contents
+      merge_records([base](int g, int f) { return __ldcv(base + g * M3PC_PARTIAL_FLOATS + f); }, x.world, p.A, p.temperature, eval_action,
+                    sample_action, p.indices);
+    }
+    *x.epoch = ep;
   }
 }
 
-// log-sum-exp merge of per-shard records; one warp is plenty (n_shards <= 32... loop otherwise)
+// merge of records gathered by another transport (e.g. an NCCL all-gather of out_partials): m3pc_merge_partials
 __global__ void merge_kernel(const float* __restrict__ partials, int n_shards, int A, float temperature, float* eval_action,
                              float* sample_action, int* indices) {
   PDL_PROLOGUE();
   if (threadIdx.x != 0) return;
-  float m = -INFINITY;
-  for (int g = 0; g < n_shards; ++g) m = fmaxf(m, partials[g * M3PC_PARTIAL_FLOATS + 0]);
-  float Z = 0.f, kbest = -INFINITY, jbest = -INFINITY;
-  int kg = 0, ji = 0;
-  for (int g = 0; g < n_shards; ++g) {
-    const float* P = partials + g * M3PC_PARTIAL_FLOATS;
-    const float sc = expf((P[0] - m) * temperature);
-    Z += P[1] * sc;
-    const float key = P[4] * sc;
-    if (key > kbest) { kbest = key; kg = g; }
-    if (P[2] > jbest) { jbest = P[2]; ji = __float_as_int(P[3]); }
-  }
-  for (int a = 0; a < A; ++a) {
-    float U = 0.f;
-    for (int g = 0; g < n_shards; ++g) {
-      const float* P = partials + g * M3PC_PARTIAL_FLOATS;
-      U += P[8 + a] * expf((P[0] - m) * temperature);
-    }
-    eval_action[a] = U / Z;
-    sample_action[a] = partials[kg * M3PC_PARTIAL_FLOATS + 8 + A + a];
-  }
-  if (indices) {
-    indices[0] = ji;
-    indices[1] = __float_as_int(partials[kg * M3PC_PARTIAL_FLOATS + 5]);
-  }
+  merge_records([partials](int g, int f) { return partials[g * M3PC_PARTIAL_FLOATS + f]; }, n_shards, A, temperature, eval_action, sample_action,
+                indices);
 }
 
 __global__ void set_seed_kernel(unsigned long long* dst, unsigned long long seed) { *dst = seed; }
@@ -394,7 +456,8 @@ int launch_score(const ScoreParams& p, cudaStream_t st) {
 }
 int launch_select(const SelectParams& p, cudaStream_t st) {
   M3PC_REQUIRE(p.A <= M3PC_MAX_ACT && p.N >= 1 && p.n_env >= 1, "select: bad shape");
-  M3PC_REQUIRE(p.n_env == 1 || p.partials == nullptr, "select: per-shard records are single-environment only");
+  M3PC_REQUIRE(p.n_env == 1 || (p.partials == nullptr && p.xch.world == 0), "select: per-shard records are single-environment only");
+  M3PC_REQUIRE(p.xch.world >= 0 && p.xch.world <= XCH_MAX_RANKS, "select: too many ranks");
   M3PC_CHECK_CUDA(launch_k(select_kernel, dim3(p.n_env), dim3(SEL_THREADS), 0, st, p));
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;

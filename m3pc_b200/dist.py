@@ -5,7 +5,12 @@ The path shards in two ways:
   * environments / independent plans -- embarrassingly parallel, no collective at all (``bench.py`` default);
   * candidates of ONE plan -- rank g owns global candidates [lo, hi) (``shard_range``); pass 1 (B = 1) is replicated,
     noise is indexed by global candidate id, and the only exchange is an all-gather of one per-shard record of
-    ``PARTIAL_FLOATS`` floats (``gather_partials``) followed by a log-sum-exp merge (device: ``m3pc_merge_partials``).
+    ``PARTIAL_FLOATS`` floats followed by a log-sum-exp merge.  Production transport: ``connect_exchange`` wires the engines'
+    peer-mapped exchange buffers once (CUDA IPC handles travel through ``torch.distributed``), after which
+    ``engine.plan(..., exchange=True)`` does selection + all-gather + merge in ONE kernel over NVLink peer memory, inside the
+    plan's CUDA graph.  ``gather_partials`` (an NCCL all-gather launched from the host) + ``m3pc_merge_partials`` is the plain
+    transport kept for comparison and for the gloo CPU tests.
+  * weights: ``broadcast_parameters`` sends rank 0's parameters to every rank in one flat NCCL broadcast at load.
 
 ``merge_partials_host`` is the numpy statement of that merge; tests use it to check the device kernel and the gloo path.
 """
@@ -42,6 +47,51 @@ def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
     base, rem = divmod(int(n_total), int(world))
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def all_gather_bytes(payload: bytes, group=None) -> list:
+    """Every rank's ``payload`` in rank order (host side plumbing: IPC handles at connect time)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return [payload]
+    out = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, payload, group=group)
+    return out
+
+
+def connect_exchange(engine, group=None) -> Tuple[int, int]:
+    """Wire ``engine`` (one per process, one process per GPU of ONE node) into the peer exchange of its process group: gather
+    the CUDA IPC handles of all exchange buffers and open them (``m3pc_exchange_connect``).  Returns (rank, world)."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    handle, _ = engine.exchange_local()
+    engine.exchange_connect(rank, world, ipc_handles=all_gather_bytes(handle, group))
+    if dist.is_initialized() and world > 1:
+        dist.barrier(group=group)  # nobody plans before everybody has mapped everybody (the buffers were just zeroed)
+    return rank, world
+
+
+def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> int:
+    """north_star: "weights are broadcast once".  All parameters and buffers of ``module`` leave rank ``src`` as ONE flat
+    tensor (one NCCL broadcast over NVLink; gloo on CPU) and are copied back into place on the receivers.  Returns the number
+    of bytes broadcast.  Call before the first plan (the engine packs its bf16 arena from these tensors on first use)."""
+    tensors = [p.data for p in module.parameters()] + [b for b in module.buffers()]
+    if not tensors:
+        return 0
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return sum(t.numel() * t.element_size() for t in tensors)
+    dev = tensors[0].device
+    flat = torch.cat([t.detach().reshape(-1).to(torch.float32) for t in tensors]).to(dev)
+    dist.broadcast(flat, src=src, group=group)
+    if dist.get_rank(group) != src:
+        o = 0
+        with torch.no_grad():
+            for t in tensors:
+                n = t.numel()
+                t.copy_(flat[o:o + n].reshape(t.shape).to(t.dtype))
+                o += n
+        if hasattr(module, "mark_dirty"):
+            module.mark_dirty()
+    return int(flat.numel() * 4)
 
 
 def gather_partials(record: torch.Tensor) -> torch.Tensor:

@@ -148,16 +148,22 @@ class PlanEngine:
     def plan(self, *, guidance: str, horizon: int, n_cand: int, win_states: torch.Tensor, win_actions: torch.Tensor,
              win_rewards: torch.Tensor, win_returns_tok: torch.Tensor, discount: float, temperature: float, lmbda: float,
              eps: Optional[torch.Tensor] = None, expq: Optional[torch.Tensor] = None, seed: int = 0, cand_offset: int = 0,
-             debug: bool = False, want_partials: bool = False, n_env: int = 1):
+             debug: bool = False, want_partials: bool = False, n_env: int = 1, exchange: bool = False):
         """One M^3PC plan on one window (learner.py:103-327).  All tensors are CUDA fp32, contiguous.
         Returns (eval_action, sample_action, dbg) -- the action tensors are engine-owned and overwritten by the next call.
 
         ``n_env = E > 1`` plans E lock-step environments in the same launch sequence: windows carry a leading E axis,
         ``eps`` is (E*n_cand, h, A), ``expq`` (E*n_cand,), and the returned actions are (E, A); row e equals the
-        single-window call on window e."""
+        single-window call on window e.
+
+        ``exchange=True`` (after ``exchange_connect``): this call plans ONE SHARD (``n_cand`` candidates starting at global id
+        ``cand_offset``); the selection kernel exchanges the shard records with every rank over peer memory and merges them, so
+        the returned actions (and ``dbg["indices"]``) are the GLOBAL result on every rank."""
         if not self.finalized:
             self.finalize()
         E = int(n_env)
+        if exchange and E > 1:
+            raise ValueError("exchange (candidate sharding) plans one environment per call")
         if E < 1:
             raise ValueError("n_env must be >= 1")
         if E > 1 and (want_partials or cand_offset):
@@ -190,6 +196,7 @@ class PlanEngine:
             a.expq = expq.data_ptr()
         a.seed = int(seed) & (2 ** 64 - 1)
         a.out_eval_action, a.out_sample_action = ev_out.data_ptr(), sm_out.data_ptr()
+        a.exchange = 1 if exchange else 0
         dbg = {}
         if (want_partials or debug) and E == 1:
             a.out_partials = self._partials.data_ptr()
@@ -212,6 +219,37 @@ class PlanEngine:
             nat.check(self.lib.m3pc_merge_partials(self._h, g.data_ptr(), n, float(temperature), self._eval.data_ptr(),
                                                    self._sample.data_ptr(), self._indices.data_ptr(), _stream()), "m3pc_merge_partials")
         return self._eval, self._sample, self._indices
+
+    # ------------------------------------------------------------------ peer exchange (candidate sharding over GPUs)
+    def exchange_local(self):
+        """(CUDA IPC handle bytes, device pointer) of this engine's exchange buffer (``m3pc_exchange_local``)."""
+        buf = (C.c_uint8 * nat.IPC_HANDLE_BYTES)()
+        ptr = C.c_void_p()
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.m3pc_exchange_local(self._h, buf, C.byref(ptr)), "m3pc_exchange_local")
+        return bytes(buf), int(ptr.value)
+
+    def exchange_connect(self, rank: int, world: int, ipc_handles: Optional[Sequence[bytes]] = None,
+                         device_ptrs: Optional[Sequence[int]] = None) -> None:
+        """Wire the group (``m3pc_exchange_connect``): ``ipc_handles`` -- one per rank, in rank order, from peers in OTHER
+        processes -- or ``device_ptrs`` -- exchange-buffer pointers of engines in THIS process."""
+        with torch.cuda.device(self.device):
+            if ipc_handles is not None:
+                blob = b"".join(ipc_handles)
+                if len(blob) != world * nat.IPC_HANDLE_BYTES:
+                    raise ValueError("need one IPC handle per rank")
+                arr = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+                nat.check(self.lib.m3pc_exchange_connect(self._h, int(rank), int(world), arr, None), "m3pc_exchange_connect")
+            else:
+                ptrs = (C.c_void_p * world)(*[int(p) for p in device_ptrs])
+                nat.check(self.lib.m3pc_exchange_connect(self._h, int(rank), int(world), None, ptrs), "m3pc_exchange_connect")
+
+    def exchange_status(self):
+        """(plans exchanged so far, epoch of a wait that timed out or 0)."""
+        ep, bad = C.c_uint64(), C.c_uint64()
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.m3pc_exchange_status(self._h, C.byref(ep), C.byref(bad)), "m3pc_exchange_status")
+        return int(ep.value), int(bad.value)
 
     def backward_plan(self, *, mode: str, horizon: int, win_states: torch.Tensor, win_actions: torch.Tensor, win_rewards: torch.Tensor,
                       win_returns_tok: torch.Tensor, eps: Optional[torch.Tensor] = None, debug: bool = False, n_draws: Optional[int] = None,

@@ -87,3 +87,51 @@ def test_world_size_2_gloo_all_gather_and_merge():
         ref_ev, ref_amax, ref_sidx = _unsharded(J, a0, q, 1.0)
         np.testing.assert_allclose(ret["ev"], ref_ev, rtol=2e-5, atol=2e-6)
         assert ret["amax"] == ref_amax and ret["sidx"] == ref_sidx
+
+
+def _worker_plumbing(rank, world, port, ret):
+    """Host-side plumbing of the peer exchange and of the weight broadcast on gloo: every rank ends up with all handles in rank
+    order, and with rank 0's parameters."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    mdist.init_from_env("gloo")
+    got = mdist.all_gather_bytes(bytes([rank]) * 64)
+    assert got == [bytes([g]) * 64 for g in range(world)]
+
+    class FakeEngine:  # records what connect_exchange hands to m3pc_exchange_connect
+        def exchange_local(self):
+            return bytes([100 + rank]) * 64, 0
+
+        def exchange_connect(self, r, w, ipc_handles=None, device_ptrs=None):
+            self.args = (r, w, list(ipc_handles))
+
+    fe = FakeEngine()
+    assert mdist.connect_exchange(fe) == (rank, world)
+    assert fe.args == (rank, world, [bytes([100 + g]) * 64 for g in range(world)])
+    torch.manual_seed(rank)  # different initial weights per rank
+    m = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.LayerNorm(7))
+    m.register_buffer("pos", torch.randn(3, 2))
+    nbytes = mdist.broadcast_parameters(m, src=0)
+    assert nbytes == 4 * (5 * 7 + 7 + 7 + 7 + 6)
+    flat = torch.cat([p.detach().reshape(-1) for p in m.parameters()] + [m.pos.reshape(-1)]).double()
+    lo_t, hi_t = flat.clone(), flat.clone()
+    dist.all_reduce(lo_t, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi_t, op=dist.ReduceOp.MAX)
+    assert torch.equal(lo_t, hi_t)
+    if rank == 0:
+        torch.manual_seed(0)
+        ref = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.LayerNorm(7))
+        assert torch.equal(ref[0].weight, m[0].weight)  # the source keeps its own values
+        ret["ok"] = True
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_exchange_plumbing_and_weight_broadcast():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker_plumbing, args=(2, port, ret), nprocs=2, join=True)
+        assert ret["ok"]

@@ -740,3 +740,60 @@ def test_select_survives_non_finite_scores():
     L.debug_plans = False
     again = L.action_sample(hist, plan=True, eval=True, rtg=3.0)
     assert bool(torch.isfinite(again).all()) and again.shape == good.shape
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_peer_exchange_in_the_select_kernel_matches_one_call(world, monkeypatch):
+    """Candidate sharding with the production transport: `world` engines (one per shard, here in ONE process on one GPU, each on
+    its own stream; peers wired by device pointer) plan their shards with exchange = 1 -- selection, all-gather of the records
+    over peer memory and the merge happen inside each shard's select kernel.  Every shard must return the result of the
+    unsharded call, for several consecutive plans (epoch / slot alternation) and through CUDA-graph replay."""
+    from m3pc_b200 import dist as mdist
+    from m3pc_b200.engine import PlanEngine
+    # Several ranks share ONE GPU here: a rank's select kernel spins until its peers' records arrive, and a peer's COOPERATIVE
+    # B = 1 kernel (one CTA on every SM, all co-resident) could not start next to that spinning block.  With one GPU per rank
+    # (the real deployment, tools/multigpu_check.sh) this cannot happen; here pass 1 uses the per-op launches instead.
+    monkeypatch.setitem(PlanEngine.default_options, "fused_b1", 0)
+    N, temp, guidance = 1024, 0.01, "rtg_guiding"
+    shape, L0 = _learner("halfcheetah", guidance, N, temp, "bf16")
+    full = L0._engine()
+    T, A, h = shape.traj_length, shape.act_dim, 4
+    shards = []
+    for r in range(world):
+        _, Lr = _learner("halfcheetah", guidance, N // world + 1, temp, "bf16")
+        shards.append(Lr._engine())
+    ptrs = [e.exchange_local()[1] for e in shards]
+    for r, e in enumerate(shards):
+        e.exchange_connect(r, world, device_ptrs=ptrs)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    g = torch.Generator(device="cuda").manual_seed(0)
+    # persistent window buffers: a plan's CUDA graph is keyed on their addresses
+    ws, wa = torch.empty(T, shape.obs_dim, device="cuda"), torch.empty(T, A, device="cuda")
+    wr, wt = torch.empty(T, device="cuda"), torch.full((T,), 0.7, device="cuda")
+    for it in range(6):
+        ws.copy_(torch.randn(T, shape.obs_dim, device="cuda", generator=g))
+        wa.copy_(torch.rand(T, A, device="cuda", generator=g) * 2 - 1)
+        wr.copy_(torch.randn(T, device="cuda", generator=g))
+        common = dict(guidance=guidance, horizon=h, win_states=ws, win_actions=wa, win_rewards=wr, win_returns_tok=wt, discount=0.99,
+                      temperature=temp, lmbda=0.6, seed=77 + it)
+        inject = it < 2  # eager with injected noise first, then Philox through the graph path
+        if inject:
+            eps, q = torch.randn(N, h, A, device="cuda", generator=g), torch.empty(N, device="cuda").exponential_(1.0, generator=g)
+        ev, sm, d = full.plan(n_cand=N, eps=eps if inject else None, expq=q if inject else None, debug=inject, **common)
+        ev, sm = ev.clone(), sm.clone()
+        torch.cuda.synchronize()
+        outs = []
+        for r, e in enumerate(shards):
+            lo, hi = mdist.shard_range(N, r, world)
+            with torch.cuda.stream(streams[r]):
+                e_ev, e_sm, e_d = e.plan(n_cand=hi - lo, cand_offset=lo, eps=eps[lo:hi].contiguous() if inject else None,
+                                         expq=q[lo:hi].contiguous() if inject else None, debug=inject, exchange=True, **common)
+                outs.append((e_ev.clone(), e_sm.clone(), e_d["indices"].clone() if inject else None))
+        torch.cuda.synchronize()
+        for r, (e_ev, e_sm, e_idx) in enumerate(outs):
+            np.testing.assert_allclose(e_ev.cpu().numpy(), ev.cpu().numpy(), atol=2e-5, err_msg=f"plan {it} rank {r}")
+            assert torch.equal(e_sm, sm), (it, r)
+            if inject:
+                assert e_idx.tolist() == d["indices"].tolist()
+    for e in shards:
+        assert e.exchange_status() == (6, 0)
