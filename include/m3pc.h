@@ -104,6 +104,10 @@ int m3pc_finalize_params(m3pc_handle_t h);
  *   "fused_ln_min_rows" 1024   smallest GEMM (rows) the fused kernel is used for (>= 129)
  *   "restrict_deep_decoder" 1  decoders with > 1 layer: last layer on the consumed rows only (0: every row)
  *   "dedupe_history" 1         first encoder block: history tokens once per environment (0: once per candidate)
+ *   "gemm_ln_unit_rows" 0      rows per CTA-pair unit of the fused residual GEMM + LayerNorm kernel: 128 = two accumulators in
+ *                              tensor memory (the epilogue of a unit overlaps the MMAs of the next), 256 = one accumulator with
+ *                              1/3 less operand traffic per FLOP, 0 = chosen per launch from K and the row count
+ *                              (process-wide; bit-identical results)
  * The release library reads no environment variable. */
 int m3pc_set_option(m3pc_handle_t h, const char* name, int32_t value);
 

@@ -161,6 +161,7 @@ inline const char* tune_env(const char*) { return nullptr; }
 // predecessor has completed and flushed its writes.  Rule: EVERY thread of EVERY kernel executes pdl_wait() before its first
 // global-memory access and before it can exit (a grid that finished without waiting would release ITS dependents early).
 // The trigger is issued right after the wait, so at most one dependent grid is pre-staged at a time.
+extern int g_ln_unit_rows;  // gemm_ln.cu
 extern bool g_use_pdl;  // M3PC_NO_PDL=1 turns the attribute off (the device-side instructions are then no-ops)
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -884,9 +884,8 @@ int restricted_last_layer(m3pc_engine* e, const FwdIO& io, const LayerW& w, cons
   }
   M3PC_TRY(launch_fill_rows(fp, D, e->XS.as<float>(), st));
   const int rows = need.n * Bc;
-  // out-projection + norm2 (g) MLP.  Not the fused kernel: on the 7/13 of the rows this layer keeps, the double-buffered 256 x 256
-  // tiles + LayerNorm kernel are as fast or faster (measured 577 vs 589 us per one-window plan, 89 vs 93 us at 8 environments)
-  M3PC_TRY(gemm_res_ln(e, e->ATT.p, w.out_w, w.out_w16, w.out_b, e->XS.as<float>(), e->Y.p, w.n2_w, w.n2_b, nullptr, 1, rows, D, st, false));
+  // out-projection + norm2 (fused: the 128-row-unit kernel hides its epilogue under the next unit's MMAs), then (g) the MLP
+  M3PC_TRY(gemm_res_ln(e, e->ATT.p, w.out_w, w.out_w16, w.out_b, e->XS.as<float>(), e->Y.p, w.n2_w, w.n2_b, nullptr, 1, rows, D, st));
   ge = GemmEpilogue{};
   ge.bias = w.l1_b;
   ge.flags = EPI_GELU;
@@ -905,6 +904,32 @@ int restricted_last_layer(m3pc_engine* e, const FwdIO& io, const LayerW& w, cons
 int decode_restricted(m3pc_engine* e, const FwdIO& io, const void* enc_out, const int* dec_src, int S, const NeedSet& need, int b0, int Bc,
                       cudaStream_t st) {
   const LayerW& w = e->dec.layers[0];
+  const int D = e->D, T = e->T;
+  int min_run = 1 << 30;  // shortest run of consecutive kept tokens of one modality
+  for (int j = 0; j < 4 * T;) {
+    if (dec_src[j] < 0) { ++j; continue; }
+    int len = 1;
+    while (j + len < (j / T + 1) * T && dec_src[j + len] == dec_src[j] + len) ++len;
+    min_run = std::min(min_run, len);
+    j += len;
+  }
+  // every run must be large enough for the fused kernel, so that one batch size always takes one path
+  if (e->bf16 && e->fuse_ln && D == 512 && static_cast<long>(min_run) * Bc >= e->fuse_ln_min_rows) {
+    // (a) + (b) in one kernel per run of kept tokens of a modality: X = dec_cvec[token] + enc_out W_dec^T (compact, encoder order),
+    // Y = LN1(X) -- the table-residual form of the fused residual GEMM + LayerNorm kernel (no residual traffic at all)
+    const size_t ab = act_bytes(e);
+    for (int j = 0; j < 4 * T;) {
+      if (dec_src[j] < 0) { ++j; continue; }
+      const int k = j / T;
+      int len = 1;
+      while (j + len < (k + 1) * T && dec_src[j + len] == dec_src[j] + len) ++len;
+      const size_t r0 = static_cast<size_t>(dec_src[j]) * Bc;
+      M3PC_TRY(gemm_res_ln(e, reinterpret_cast<const char*>(enc_out) + r0 * D * ab, e->dec_w[k], e->dec_w16[k], nullptr, e->X.as<float>() + r0 * D,
+                           reinterpret_cast<char*>(e->Y.p) + r0 * D * ab, w.n1_w, w.n1_b, e->dec_cvec + static_cast<size_t>(j) * D, Bc, len * Bc, D, st));
+      j += len;
+    }
+    return restricted_last_layer(e, io, w, dec_src, S, need, b0, Bc, st);
+  }
   // (a) decoder embedding of the kept tokens, compact (encoder order) -> X[0 : S*Bc)
   M3PC_TRY(decoder_embed(e, enc_out, dec_src, Bc, true, st));
   // (b) LN1 -> Y
@@ -915,7 +940,7 @@ int decode_restricted(m3pc_engine* e, const FwdIO& io, const void* enc_out, cons
   ln.g1 = w.n1_w;
   ln.b1 = w.n1_b;
   ln.y1 = e->Y.p;
-  M3PC_TRY(launch_layernorm(ln, e->D, e->bf16, st));
+  M3PC_TRY(launch_layernorm(ln, D, e->bf16, st));
   return restricted_last_layer(e, io, w, dec_src, S, need, b0, Bc, st);
 }
 
@@ -1546,6 +1571,10 @@ int m3pc_set_option(m3pc_handle_t h, const char* name, int32_t value) {
   else if (n == "fused_ln_min_rows") h->fuse_ln_min_rows = std::max(129, static_cast<int>(value));
   else if (n == "restrict_deep_decoder") h->restrict_deep = value != 0;
   else if (n == "dedupe_history") h->dedupe_history = value != 0;
+  else if (n == "gemm_ln_unit_rows") {
+    M3PC_REQUIRE(value == 0 || value == 128 || value == 256, "gemm_ln_unit_rows must be 0 (per launch), 128 or 256");
+    m3pc::g_ln_unit_rows = value;
+  }
   else {
     m3pc::set_error("m3pc_set_option: unknown option '" + n + "'");
     return M3PC_ERR_INVALID;

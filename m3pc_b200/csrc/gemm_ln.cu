@@ -5,16 +5,27 @@
 //
 // Reference call sites: the out-projection / linear2 of nn.TransformerEncoderLayer followed by the next pre-LN norm
 // (mtm_model.py:379-409; norm_first: x = x + sa(norm1(x)); x = x + ff(norm2(x))).  The unfused path writes X through a TMA
-// reduce-add (read-modify-write of 4 KB per row) and a separate LayerNorm kernel reads it again; here a CTA pair owns 256
-// rows x ALL 512 columns -- exactly the pair's tensor memory (2 x 256 fp32 columns per CTA) -- so the epilogue sees whole
-// rows: it loads the residual tile through the TMA, adds, stores X, keeps the updated rows in TMEM (tcgen05.st), exchanges
-// the row statistics between the four column-slice warps of a row, and writes the normalised bf16 operand of the next GEMM.
-// 6 KB of HBM traffic per row and one launch instead of 8 KB and two.  The accumulator is single-buffered (TMEM is full),
-// so the epilogue of a row block is not overlapped with the MMAs of the next one; the operand ring keeps prefetching.
+// reduce-add (read-modify-write of 4 KB per row) and a separate LayerNorm kernel reads it again; here a CTA pair owns ALL 512
+// columns of its rows, so the epilogue sees whole rows: it loads the residual tile through the TMA, adds, stores X, keeps the
+// updated rows in TMEM (tcgen05.st), exchanges the row statistics between the warps that share a row, and writes the
+// normalised bf16 operand of the next GEMM.  6 KB of HBM traffic per row and one launch instead of 8 KB and two.
 //
-// Structure (per CTA of the pair, 18 warps): warp 0 lane 0 = TMA producer (A: own 128 rows; W: own 128 rows of each 256-row
-// half), warp 1 lane 0 of the leader = MMA issuer (two tcgen05.mma cta_group::2 M256 x N256 x K16 per k-step, one per
-// column half), warps 2..17 = epilogue (TMEM lane quarter = warp % 4, column slice of 128 = (warp - 2) / 4).
+// Two unit sizes (template parameter ROWS, chosen per launch in gemm_ln_bf16):
+//   ROWS = 256  M = 256 MMAs; the unit's accumulator is the pair's whole tensor memory (128 lanes x 512 columns per CTA), so the
+//               epilogue of a unit and the MMAs of the next take turns.  Least operand traffic per FLOP: right for long K.
+//   ROWS = 128  M = 128 MMAs (cta_group::2).  Each CTA's 64 x N slice of D is stored as 128 lanes x N/2 columns (lanes 0-63:
+//               columns [0, N/2); lanes 64-127: columns [N/2, N) -- the "2x2" datapath layout), so a 128-row x 512-column unit
+//               takes 256 TMEM columns per CTA and TWO fit: the epilogue of unit u runs under the MMAs of unit u + 1.  Same tensor
+//               pipe rate; W is streamed once per 128 rows instead of once per 256.  Right for K = 512, where the launch is
+//               bound by the epilogue's 6 KB per row, and for launches too small to fill whole rounds of 256-row units.
+// Per-element arithmetic (k order of the accumulation, fp32 epilogue) is the same in both: results are bit-identical.
+//
+// Structure (per CTA of the pair, 18 warps): warp 0 lane 0 = TMA producer (A: own ROWS / 2 rows; W: own 128 rows of each
+// 256-row half), warp 1 lane 0 of the leader = MMA issuer (two tcgen05.mma cta_group::2 M = ROWS, N = 256, K = 16 per k-step,
+// one per column half), warps 2..17 = epilogue (TMEM lane quarter q = warp % 4, group g = (warp - 2) / 4):
+//   ROWS = 256  rows q * 32 + lane of the CTA's 128, columns g * 128 .. + 128 (a row is shared by 4 warps)
+//   ROWS = 128  rows (q & 1) * 32 + lane of the CTA's 64, columns h * 256 + s * 128 + c0 .. + 64 with s = q >> 1 (lane half),
+//               h = g >> 1 (which N = 256 MMA), c0 = (g & 1) * 64 (a row is shared by 8 warps)
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -23,24 +34,13 @@ namespace m3pc {
 int make_tmap(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
 int make_tmap_out(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t cols, bool f32);
 
+int g_ln_unit_rows = 0;  // rows per CTA-pair unit of the fused kernel: 0 = chosen per launch (gemm_ln_bf16), or 128 / 256 forced; m3pc_set_option "gemm_ln_unit_rows"
+
 namespace {
 
 constexpr int LN_N = 512;
 constexpr int LN_EPI_WARPS = 16;
 constexpr int LN_THREADS = 32 * (2 + LN_EPI_WARPS);
-constexpr int LN_STAGES = 3;
-
-struct SmemLn {
-  static constexpr int kABlk = BM * BK * 2;        // 16 KB: this CTA's 128 rows of one A k-block
-  static constexpr int kBBlk = 128 * BK * 2;       // 16 KB: this CTA's 128 rows of one 256-row half of W
-  static constexpr int kStageBytes = kABlk + 2 * kBBlk;
-  static constexpr int kBoxBytes = 32 * 64;        // one staged chunk: 32 rows x 64 bytes (16 fp32 / 32 bf16 columns), SWIZZLE_64B
-  static constexpr int kStoreOffset = LN_STAGES * kStageBytes;
-  static constexpr int kConstOffset = kStoreOffset + LN_EPI_WARPS * 2 * kBoxBytes;  // bias | gamma | beta, 512 floats each
-  static constexpr int kStatsOffset = kConstOffset + 3 * LN_N * 4;                  // float2 [128 rows][4 slices]
-  static constexpr int kBarOffset = kStatsOffset + 128 * 4 * 8;
-  static constexpr int kTotal = kBarOffset + 512 + 1024;
-};
 
 struct LnGemmParams {
   CUtensorMap ta, tw, tx, ty;
@@ -69,16 +69,38 @@ __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
+template <int ROWS, int STAGES, int NBOX>
+struct SmemLn {
+  static constexpr int kABlk = (ROWS / 2) * BK * 2;  // this CTA's ROWS / 2 rows of one A k-block
+  static constexpr int kBBlk = 128 * BK * 2;         // 16 KB: this CTA's 128 rows of one 256-row half of W
+  static constexpr int kStageBytes = kABlk + 2 * kBBlk;
+  static constexpr int kBoxBytes = 32 * 64;
+  static constexpr int kStoreOffset = STAGES * kStageBytes;
+  static constexpr int kConstOffset = kStoreOffset + LN_EPI_WARPS * NBOX * kBoxBytes;
+  static constexpr int kStatsOffset = kConstOffset + 3 * LN_N * 4;  // float2 [ROWS / 2 rows][8 column groups]
+  static constexpr int kBarOffset = kStatsOffset + (ROWS / 2) * 8 * 8;
+  static constexpr int kTotal = kBarOffset + 1024 + 1024;
+};
+
+template <int ROWS, int STAGES, int NBOX>
 __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid_constant__ LnGemmParams P) {
-  using L = SmemLn;
+  static_assert(ROWS == 128 || ROWS == 256, "unit rows");
+  using L = SmemLn<ROWS, STAGES, NBOX>;
+  constexpr int NACC = ROWS == 128 ? 2 : 1;         // accumulators in tensor memory
+  constexpr uint32_t ACC_COLS = LN_N / NACC;        // TMEM columns of one accumulator
+  constexpr int NSHARE = ROWS == 128 ? 8 : 4;       // warps that share a row
+  constexpr int WCOLS = LN_N / NSHARE;              // output columns per warp
+  // Row statistics are accumulated in a CANONICAL order that does not depend on ROWS: (sum, sum of squares) over each group of 64
+  // consecutive columns, ascending, then the eight groups added in column order -- so both unit sizes produce identical bits.
+  constexpr int NSLICE = 8;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);  // leader's copy is the one waited on
-  uint64_t* empty_bar = full_bar + LN_STAGES;
-  uint64_t* acc_full = empty_bar + LN_STAGES;
-  uint64_t* acc_empty = acc_full + 1;                                      // leader's copy counts both CTAs' epilogue warps
-  uint64_t* res_bar = acc_empty + 1;                                       // [LN_EPI_WARPS][2]: residual box landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * LN_EPI_WARPS);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* acc_full = empty_bar + STAGES;   // [2]
+  uint64_t* acc_empty = acc_full + 2;        // [2]; leader's copy counts both CTAs' epilogue warps
+  uint64_t* res_bar = acc_empty + 2;         // [LN_EPI_WARPS][NBOX]: residual box landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + NBOX * LN_EPI_WARPS);
   float* sconst = reinterpret_cast<float*>(smem + L::kConstOffset);
   float2* sstats = reinterpret_cast<float2*>(smem + L::kStatsOffset);
 
@@ -94,21 +116,22 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
     prefetch_tmap(&P.tx);
     prefetch_tmap(&P.ty);
 #pragma unroll
-    for (int s = 0; s < LN_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 2 * LN_EPI_WARPS);
-    for (int i = 0; i < 2 * LN_EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
+    for (int b = 0; b < NACC; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 2 * LN_EPI_WARPS);
+    }
+    for (int i = 0; i < NBOX * LN_EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 1) {  // all 512 TMEM columns: one 128-lane x 512-column fp32 accumulator per CTA
+  if (warp == 1) {  // all 512 TMEM columns: two accumulators of 256 columns (one 128-row x 512-column unit each)
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(LN_N) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
-  // epilogue constants are weights (never written by a preceding kernel): staged before the programmatic dependency wait
   for (int i = threadIdx.x; i < LN_N; i += LN_THREADS) {
     sconst[i] = P.bias != nullptr ? __ldg(P.bias + i) : 0.f;
     sconst[LN_N + i] = __ldg(P.gamma + i);
@@ -122,12 +145,12 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---- TMA producer (both CTAs) ----
+      // ---- TMA producer (both CTAs): own 64 rows of A, own 128 rows of each 256-row half of W ----
       const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[0]), 0);
       int s = 0;
       uint32_t ph = 0;
       for (int u = pair; u < P.n_units; u += n_pairs) {
-        const int m0 = (u * 2 + static_cast<int>(crank)) * BM;
+        const int m0 = (u * 2 + static_cast<int>(crank)) * (ROWS / 2);
         for (int kb = 0; kb < P.num_kb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           if (leader) mbar_arrive_expect_tx(&full_bar[s], 2u * L::kStageBytes);
@@ -136,19 +159,21 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
           tma_load_2d_2sm(dst, &P.ta, bar, kb * BK, m0);
           tma_load_2d_2sm(dst + L::kABlk, &P.tw, bar, kb * BK, static_cast<int>(crank) * 128);
           tma_load_2d_2sm(dst + L::kABlk + L::kBBlk, &P.tw, bar, kb * BK, 256 + static_cast<int>(crank) * 128);
-          if (++s == LN_STAGES) { s = 0; ph ^= 1; }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && leader) {
-      // ---- MMA issuer (leader only): both column halves per k-step ----
-      constexpr uint32_t idesc = make_idesc_mn(2 * BM, 256);
+      // ---- MMA issuer (leader only): M = ROWS across the pair, both N = 256 halves per k-step, accumulators alternate ----
+      constexpr uint32_t idesc = make_idesc_mn(ROWS, 256);
       int s = 0, it = 0;
       uint32_t ph = 0;
       for (int u = pair; u < P.n_units; u += n_pairs, ++it) {
-        mbar_wait(acc_empty, (static_cast<uint32_t>(it) & 1u) ^ 1u);
+        const uint32_t buf = static_cast<uint32_t>(it % NACC);
+        mbar_wait(&acc_empty[buf], (static_cast<uint32_t>(it / NACC) & 1u) ^ 1u);
         tc_fence_after();
+        const uint32_t d0 = tmem_base + buf * ACC_COLS;
         for (int kb = 0; kb < P.num_kb; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
@@ -158,24 +183,31 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
             const uint64_t da = make_smem_desc(a_addr + k * UMMA_K * 2);
-            umma_bf16_2sm(tmem_base, da, make_smem_desc(b0_addr + k * UMMA_K * 2), idesc, acc);
-            umma_bf16_2sm(tmem_base + 256u, da, make_smem_desc(b1_addr + k * UMMA_K * 2), idesc, acc);
+            umma_bf16_2sm(d0, da, make_smem_desc(b0_addr + k * UMMA_K * 2), idesc, acc);
+            umma_bf16_2sm(d0 + ACC_COLS / 2, da, make_smem_desc(b1_addr + k * UMMA_K * 2), idesc, acc);
           }
           umma_commit_2sm(&empty_bar[s]);
-          if (++s == LN_STAGES) { s = 0; ph ^= 1; }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit_2sm(acc_full);
+        umma_commit_2sm(&acc_full[buf]);
       }
     }
   } else {
-    // ---- epilogue warps (both CTAs): 32 rows (TMEM lane quarter) x 128 columns each ----
+    // ---- epilogue warps (both CTAs): 32 rows x WCOLS columns each ----
     const int ew = warp - 2;
-    const int quarter = warp & 3;
-    const int cgrp = ew >> 2;
-    uint8_t* sbuf = smem + L::kStoreOffset + ew * 2 * L::kBoxBytes;
-    uint64_t* rbar = res_bar + 2 * ew;
-    uint32_t rph[2] = {0u, 0u};
-    const uint32_t acc_empty_leader = mapa_u32(smem_u32(acc_empty), 0);
+    const int q = warp & 3;
+    const int grp = ew >> 2;
+    // ROWS = 128 ("2x2" layout): lanes [0, 64) hold columns [0, 128) of each N = 256 MMA and lanes [64, 128) columns [128, 256), so
+    // quarter q covers rows (q & 1) * 32 .. and the lane half q >> 1 selects the column half; ROWS = 256: lane = row
+    const int rowq = ROWS == 128 ? (q & 1) : q;         // which block of 32 rows of this CTA
+    const int lanehalf = ROWS == 128 ? (q >> 1) : 0;
+    const int colw = ROWS == 128 ? (grp >> 1) * 256 + lanehalf * 128 + (grp & 1) * 64 : grp * 128;   // first output column of this warp
+    const uint32_t tcol = static_cast<uint32_t>(ROWS == 128 ? (grp >> 1) * 128 + (grp & 1) * 64 : grp * 128);  // its TMEM column inside an accumulator
+    const int slice = colw / 64;                                                           // first 64-column group of this warp
+    uint8_t* sbuf = smem + L::kStoreOffset + ew * NBOX * L::kBoxBytes;
+    uint64_t* rbar = res_bar + NBOX * ew;
+    uint32_t rph = 0;  // bit b: parity of rbar[b]
+    const uint32_t acc_empty_leader = mapa_u32(smem_u32(&acc_empty[0]), 0);
     const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);  // SWIZZLE_64B: 16-byte chunk j of row r lives at j ^ ((r >> 1) & 3)
 #ifdef M3PC_TUNING
     const int tune = P.tune;
@@ -186,46 +218,47 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
     const float* sbias = sconst;
     const float* sgamma = sconst + LN_N;
     const float* sbeta = sconst + 2 * LN_N;
+    constexpr int NB1 = WCOLS / 16;             // residual / X boxes per warp per unit (16 fp32 columns each)
+    constexpr int NB2 = WCOLS / 32;             // Y boxes (32 bf16 columns each)
+    constexpr int NPRE = NBOX < NB1 ? NBOX : NB1;  // boxes requested before the accumulator is waited for
     int it = 0;
-    uint32_t nbox = 0;  // boxes handed to the TMA store so far (selects the staging buffer)
+    // Box buffers are used strictly round-robin (buffer = ns % NBOX for the ns-th bulk group this warp commits), which is what makes
+    // "wait until at most NBOX - 1 groups are still being read" the condition for reusing one.  With the residual coming through the
+    // TMA every unit starts from a drained state (ns = 0, all buffers free).
+    uint32_t ns = 0;
     for (int u = pair; u < P.n_units; u += n_pairs, ++it) {
-      const int row0 = (u * 2 + static_cast<int>(crank)) * BM + quarter * 32;
+      const uint32_t buf = static_cast<uint32_t>(it % NACC);
+      const int row0 = (u * 2 + static_cast<int>(crank)) * (ROWS / 2) + rowq * 32;
       const int row = row0 + lane;
       const bool live = row0 < P.M && !(tune & 8);
-      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(cgrp * 128);
-      // short K: the residual tile is pulled into L2 while the MMAs of this row block are still running (each box load then waits
-      // for an L2 hit instead of an HBM round trip).  Not for long K: the A stream evicts the prefetched lines before they are
-      // used and the tile is read from HBM twice (measured: 838 MB instead of 654 MB per launch at K = 2048).
-      if (from_x && live && lane < 8 && P.num_kb <= 8) tma_prefetch_l2_2d(&P.tx, cgrp * 128 + lane * 16, row0);
-      // the box of the first chunk travels all the way to shared memory before the accumulator is ready
+      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * ACC_COLS + tcol;
+      // residual boxes travel to shared memory while the MMAs of this unit (and the epilogue of the previous one) still run
+      if (from_x) ns = 0;
       if (from_x && live && lane == 0) {
-        bulk_wait_read<0>();  // the buffer's last store has been read
-        mbar_arrive_expect_tx(&rbar[nbox & 1], L::kBoxBytes);
-        tma_load_2d(sbuf + (nbox & 1) * L::kBoxBytes, &P.tx, &rbar[nbox & 1], cgrp * 128, row0);
+        bulk_wait_read<0>();  // every buffer's last store has been read
+#pragma unroll
+        for (int b = 0; b < NPRE; ++b) {
+          mbar_arrive_expect_tx(&rbar[b], L::kBoxBytes);
+          tma_load_2d(sbuf + b * L::kBoxBytes, &P.tx, &rbar[b], colw + b * 16, row0);
+        }
       }
-      mbar_wait(acc_full, static_cast<uint32_t>(it) & 1u);
+      mbar_wait(&acc_full[buf], static_cast<uint32_t>(it / NACC) & 1u);
       tc_fence_after();
       float s1 = 0.f, s2 = 0.f;
       if (live) {
         // ---- pass 1: x = acc + bias + residual -> X (TMA store) and back into TMEM; row sums ----
 #pragma unroll 1
-        for (int ci = 0; ci < 8; ++ci) {
-          const int col0 = cgrp * 128 + ci * 16;
-          const uint32_t b = nbox & 1;
-          uint8_t* buf = sbuf + b * L::kBoxBytes;
-          if (from_x && ci + 1 < 8 && lane == 0) {  // prefetch the next residual box into the other buffer
-            bulk_wait_read<0>();
-            mbar_arrive_expect_tx(&rbar[b ^ 1], L::kBoxBytes);
-            tma_load_2d(sbuf + (b ^ 1) * L::kBoxBytes, &P.tx, &rbar[b ^ 1], col0 + 16, row0);
-          }
-          __syncwarp();
+        for (int ci = 0; ci < NB1; ++ci) {
+          const int col0 = colw + ci * 16;
+          const int b = static_cast<int>(ns % NBOX);
+          uint8_t* bx = sbuf + b * L::kBoxBytes;
           uint32_t r[32];
           tmem_ld16(tacc + static_cast<uint32_t>(ci * 16), r);
           if (from_x) {
-            mbar_wait(&rbar[b], rph[b]);
-            rph[b] ^= 1u;
+            mbar_wait(&rbar[b], (rph >> b) & 1u);
+            rph ^= 1u << b;
           } else {
-            if (lane == 0) bulk_wait_read<1>();  // the store issued from this buffer two boxes ago has been read
+            if (lane == 0) bulk_wait_read<NBOX - 1>();  // the store issued from this buffer NBOX boxes ago has been read
             __syncwarp();
           }
           tmem_ld_wait();
@@ -233,7 +266,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
           const float* trow = (from_x || P.table == nullptr) ? nullptr : P.table + static_cast<size_t>(min(row, P.M - 1) / P.rows_per_group) * LN_N + col0;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            float4* slot = reinterpret_cast<float4*>(buf + lane * 64 + ((static_cast<uint32_t>(j) ^ sw) << 4));
+            float4* slot = reinterpret_cast<float4*>(bx + lane * 64 + ((static_cast<uint32_t>(j) ^ sw) << 4));
             const float4 res = from_x ? *slot : (trow != nullptr ? __ldg(reinterpret_cast<const float4*>(trow + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f));
             const float4 b4 = *reinterpret_cast<const float4*>(sbias + col0 + 4 * j);
             v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b4.x + res.x;
@@ -247,56 +280,68 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
             s1 += v[j];
             s2 = fmaf(v[j], v[j], s2);
           }
+          if ((ci & 3) == 3) {  // a 64-column group is complete
+            sstats[(rowq * 32 + lane) * NSLICE + slice + (ci >> 2)] = make_float2(s1, s2);
+            s1 = s2 = 0.f;
+          }
           tmem_st16(tacc + static_cast<uint32_t>(ci * 16), v);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            if (!(tune & 2)) tma_store_2d(&P.tx, buf, col0, row0);
+            if (!(tune & 2)) tma_store_2d(&P.tx, bx, col0, row0);
             bulk_commit();
+            if (from_x && ci + NBOX < NB1) {  // this buffer is needed again for a later residual box of the unit
+              bulk_wait_read<0>();
+              mbar_arrive_expect_tx(&rbar[b], L::kBoxBytes);
+              tma_load_2d(bx, &P.tx, &rbar[b], col0 + NBOX * 16, row0);
+            }
           }
-          ++nbox;
+          ++ns;
         }
         tmem_st_wait();
       }
-      // ---- row statistics across the four column-slice warps of this lane quarter ----
-      sstats[(quarter * 32 + lane) * 4 + cgrp] = make_float2(s1, s2);
-      named_bar_sync(1 + quarter, 128);
+      // ---- row statistics across the NSHARE warps that share these 32 rows ----
+      if (!live) {
+#pragma unroll
+        for (int g = 0; g < WCOLS / 64; ++g) sstats[(rowq * 32 + lane) * NSLICE + slice + g] = make_float2(0.f, 0.f);
+      }
+      named_bar_sync(1 + rowq, 32 * NSHARE);
       float mean, rstd;
       {
         float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const float2 p = sstats[(quarter * 32 + lane) * 4 + g];
-          t1 += p.x;
-          t2 += p.y;
+        for (int g = 0; g < NSLICE; ++g) {
+          const float2 pq = sstats[(rowq * 32 + lane) * NSLICE + g];
+          t1 += pq.x;
+          t2 += pq.y;
         }
         mean = t1 * (1.0f / LN_N);
         const float var = fmaxf(t2 * (1.0f / LN_N) - mean * mean, 0.f);
         rstd = rsqrtf(var + 1e-5f);
       }
-      named_bar_sync(1 + quarter, 128);  // everybody has read the statistics: the next row block may overwrite them
+      named_bar_sync(1 + rowq, 32 * NSHARE);  // everybody has read the statistics: the next unit may overwrite them
       if (live) {
         // ---- pass 2: y = (x - mean) * rstd * gamma + beta -> bf16 -> Y ----
 #pragma unroll 1
-        for (int ci = 0; ci < 4; ++ci) {
-          const int col0 = cgrp * 128 + ci * 32;
-          uint8_t* buf = sbuf + (nbox & 1) * L::kBoxBytes;
+        for (int ci = 0; ci < NB2; ++ci) {
+          const int col0 = colw + ci * 32;
+          uint8_t* bx = sbuf + (ns % NBOX) * L::kBoxBytes;
           uint32_t r[32];
           tmem_ld32(tacc + static_cast<uint32_t>(ci * 32), r);
-          if (lane == 0) bulk_wait_read<1>();
+          if (lane == 0) bulk_wait_read<NBOX - 1>();
           __syncwarp();
           tmem_ld_wait();
-          if (ci == 3) {  // the accumulator has been drained: the MMA warp may start the next row block
+          if (ci == NB2 - 1) {  // the accumulator has been drained: the MMA warp may reuse it
             tc_fence_before();
-            if (lane == 0) mbar_arrive_remote(acc_empty_leader);
+            if (lane == 0) mbar_arrive_remote(acc_empty_leader + 8u * buf);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float y[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int c = col0 + 8 * j + q;
-              y[q] = (__uint_as_float(r[8 * j + q]) - mean) * rstd * sgamma[c] + sbeta[c];
+            for (int e = 0; e < 8; ++e) {
+              const int c = col0 + 8 * j + e;
+              y[e] = (__uint_as_float(r[8 * j + e]) - mean) * rstd * sgamma[c] + sbeta[c];
             }
             __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]);
             __nv_bfloat162 p1 = __floats2bfloat162_rn(y[2], y[3]);
@@ -305,19 +350,19 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
             uint4 o;
             o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
             o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
-            *reinterpret_cast<uint4*>(buf + lane * 64 + ((static_cast<uint32_t>(j) ^ sw) << 4)) = o;
+            *reinterpret_cast<uint4*>(bx + lane * 64 + ((static_cast<uint32_t>(j) ^ sw) << 4)) = o;
           }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            if (!(tune & 4)) tma_store_2d(&P.ty, buf, col0, row0);
+            if (!(tune & 4)) tma_store_2d(&P.ty, bx, col0, row0);
             bulk_commit();
           }
-          ++nbox;
+          ++ns;
         }
       } else {
         tc_fence_before();
-        if (lane == 0) mbar_arrive_remote(acc_empty_leader);
+        if (lane == 0) mbar_arrive_remote(acc_empty_leader + 8u * buf);
       }
     }
     if (lane == 0) bulk_wait_all();
@@ -331,38 +376,22 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
   }
 }
 
-}  // namespace
-
-// X (M, 512) fp32 in place (or table rows as the residual), Y (M, 512) bf16 = LayerNorm(X).  K % 64 == 0.
-int gemm_ln_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, float* X, __nv_bfloat16* Y, const float* gamma,
-                 const float* beta, const float* table, int rows_per_group, int M, int K, cudaStream_t st) {
-  M3PC_REQUIRE(M > 0 && K > 0 && K % BK == 0, "gemm_ln: K must be a positive multiple of 64");
-  M3PC_REQUIRE(A && W && X && Y && gamma && beta, "gemm_ln: null operand");
-  M3PC_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) & 15) == 0,
-               "gemm_ln: operands must be 16-byte aligned");
-  M3PC_TRY(gemm_init_driver_api());
+template <int ROWS, int STAGES, int NBOX>
+int launch_ln(LnGemmParams& P, int M, cudaStream_t st) {
+  using L = SmemLn<ROWS, STAGES, NBOX>;
+  static_assert(L::kTotal <= 227 * 1024, "shared memory budget exceeded");
+  static_assert(L::kStoreOffset % 1024 == 0, "operand stages must keep 1024-byte alignment");
   static PerDevice<bool> configured;
   if (!configured.here()) {
-    static_assert(SmemLn::kTotal <= 227 * 1024, "shared memory budget exceeded");
-    M3PC_CHECK_CUDA(cudaFuncSetAttribute(gemm_ln_2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLn::kTotal));
+    M3PC_CHECK_CUDA(cudaFuncSetAttribute(gemm_ln_2sm_kernel<ROWS, STAGES, NBOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured.here() = true;
   }
-  LnGemmParams P{};
-  M3PC_TRY(make_tmap(&P.ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), BM));
-  M3PC_TRY(make_tmap(&P.tw, W, static_cast<uint64_t>(LN_N), static_cast<uint64_t>(K), 128));
-  M3PC_TRY(make_tmap_out(&P.tx, X, static_cast<uint64_t>(M), LN_N, true));
-  M3PC_TRY(make_tmap_out(&P.ty, Y, static_cast<uint64_t>(M), LN_N, false));
-  P.bias = bias; P.gamma = gamma; P.beta = beta; P.table = table;
-  P.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
-  P.M = M;
-  P.num_kb = K / BK;
-  P.n_units = ceil_div(M, 2 * BM);
-  if (const char* t = tune_env("M3PC_TUNE_LN")) P.tune = atoi(t);
+  P.n_units = ceil_div(M, ROWS);
   const int pairs = std::min(P.n_units, device_num_sms() / 2);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(LN_THREADS);
-  cfg.dynamicSmemBytes = SmemLn::kTotal;
+  cfg.dynamicSmemBytes = L::kTotal;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -373,9 +402,44 @@ int gemm_ln_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bi
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = g_use_pdl ? 2 : 1;
-  M3PC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_ln_2sm_kernel, P));
+  M3PC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_ln_2sm_kernel<ROWS, STAGES, NBOX>, P));
   M3PC_CHECK_LAUNCH();
   return M3PC_OK;
+}
+
+}  // namespace
+
+// X (M, 512) fp32 in place (or table rows as the residual), Y (M, 512) bf16 = LayerNorm(X).  K % 64 == 0.
+// Unit size (rows per CTA pair; bit-identical results, tests/test_gpu_parity.py::test_gemm_ln_unit_sizes_are_bit_identical):
+//   K <= 512   128-row units: the launch is bound by its epilogue traffic (6 KB per row), which then runs under the next unit's MMAs
+//              (measured at 106 496 rows: 125 us vs 135 us with 256-row units; profiles/r2g_gemm_ln_variants.txt)
+//   K  > 512   256-row units feed the tensor pipe with 1/3 less operand traffic per FLOP (238 vs 264 us) -- unless the launch is so
+//              small that whole 256-row units quantise badly on the 74 CTA pairs (26 624 rows: 104 units = 2 rounds, vs 3 half rounds)
+int gemm_ln_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, float* X, __nv_bfloat16* Y, const float* gamma,
+                 const float* beta, const float* table, int rows_per_group, int M, int K, cudaStream_t st) {
+  M3PC_REQUIRE(M > 0 && K > 0 && K % BK == 0, "gemm_ln: K must be a positive multiple of 64");
+  M3PC_REQUIRE(A && W && X && Y && gamma && beta, "gemm_ln: null operand");
+  M3PC_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) & 15) == 0,
+               "gemm_ln: operands must be 16-byte aligned");
+  M3PC_TRY(gemm_init_driver_api());
+  int rows = g_ln_unit_rows;
+  if (const char* t = tune_env("M3PC_LN_UNIT_ROWS")) rows = atoi(t);  // tuning build: A/B without a handle
+  if (rows != 128 && rows != 256) {
+    const int pairs = std::max(1, device_num_sms() / 2);
+    const double rounds256 = ceil_div(ceil_div(M, 256), pairs), rounds128 = 0.5 * ceil_div(ceil_div(M, 128), pairs);
+    rows = (K <= 512 || rounds128 + 0.25 < rounds256) ? 128 : 256;
+  }
+  LnGemmParams P{};
+  M3PC_TRY(make_tmap(&P.ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), rows / 2));
+  M3PC_TRY(make_tmap(&P.tw, W, static_cast<uint64_t>(LN_N), static_cast<uint64_t>(K), 128));
+  M3PC_TRY(make_tmap_out(&P.tx, X, static_cast<uint64_t>(M), LN_N, true));
+  M3PC_TRY(make_tmap_out(&P.ty, Y, static_cast<uint64_t>(M), LN_N, false));
+  P.bias = bias; P.gamma = gamma; P.beta = beta; P.table = table;
+  P.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
+  P.M = M;
+  P.num_kb = K / BK;
+  if (const char* t = tune_env("M3PC_TUNE_LN")) P.tune = atoi(t);
+  return rows == 128 ? launch_ln<128, 3, 2>(P, M, st) : launch_ln<256, 3, 2>(P, M, st);
 }
 
 }  // namespace m3pc

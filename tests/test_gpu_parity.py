@@ -797,3 +797,36 @@ def test_peer_exchange_in_the_select_kernel_matches_one_call(world, monkeypatch)
                 assert e_idx.tolist() == d["indices"].tolist()
     for e in shards:
         assert e.exchange_status() == (6, 0)
+
+
+@pytest.mark.parametrize("M,K,table_rows", [(26624, 512, 0), (26624, 2048, 0), (4000, 512, 1000), (777, 2048, 0)])
+def test_gemm_ln_unit_sizes_are_bit_identical(nat, M, K, table_rows):
+    """The fused residual GEMM + LayerNorm kernel picks 128- or 256-row units per launch (from K and the row count); scores must not
+    depend on that choice -- candidate shards of different sizes have to reproduce the unsharded plan bit for bit -- so both unit
+    sizes are required to give identical X and Y."""
+    from m3pc_b200.engine import engine_from_synthetic
+    shape = syn.shipped_shape("hopper")
+    eng = engine_from_synthetic(shape, syn.make_state_dict(shape, 0), syn.make_tokenizer_stats(shape, 1), max_batch=8)  # a handle for m3pc_set_option
+    L = nat.lib()
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(512, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bias, gamma, beta = torch.randn(512, device="cuda", generator=g), 1 + 0.2 * torch.randn(512, device="cuda", generator=g), 0.2 * torch.randn(512, device="cuda", generator=g)
+    X0 = 2.0 * torch.randn(M, 512, device="cuda", generator=g) + 0.5
+    table, grp = None, 1
+    if table_rows:
+        grp = table_rows
+        table = torch.randn((M + grp - 1) // grp, 512, device="cuda", generator=g)
+    outs = {}
+    try:
+        for rows in (128, 256, 0):
+            eng.set_option("gemm_ln_unit_rows", rows)
+            X, Y = X0.clone(), torch.full((M, 512), float("nan"), device="cuda", dtype=torch.bfloat16)
+            nat.check(L.m3pc_gemm_ln_bf16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), X.data_ptr(), Y.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                          table.data_ptr() if table is not None else None, grp, M, K, None), "m3pc_gemm_ln_bf16")
+            torch.cuda.synchronize()
+            outs[rows] = (X, Y)
+    finally:
+        eng.set_option("gemm_ln_unit_rows", 0)
+    assert torch.equal(outs[128][0], outs[256][0]) and torch.equal(outs[128][1], outs[256][1])
+    assert torch.equal(outs[0][0], outs[256][0]) and torch.equal(outs[0][1], outs[256][1])
