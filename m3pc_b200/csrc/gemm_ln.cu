@@ -19,6 +19,9 @@
 //               pipe rate; W is streamed once per 128 rows instead of once per 256.  Right for K = 512, where the launch is
 //               bound by the epilogue's 6 KB per row, and for launches too small to fill whole rounds of 256-row units.
 // Per-element arithmetic (k order of the accumulation, fp32 epilogue) is the same in both: results are bit-identical.
+// Tried and dropped (profiles/r2g_gemm_ln_variants.txt): pulling a unit's residual tile into L2 ahead of its epilogue
+// (cp.async.bulk.prefetch.tensor by the producer warp, 8 k-blocks before the unit's last MMA) -- 147 vs 125 us (K = 512) and
+// 252 vs 236 us (K = 2048) at 106 496 rows: the prefetched lines compete with the operand stream and are fetched twice.
 //
 // Structure (per CTA of the pair, 18 warps): warp 0 lane 0 = TMA producer (A: own ROWS / 2 rows; W: own 128 rows of each
 // 256-row half), warp 1 lane 0 of the leader = MMA issuer (two tcgen05.mma cta_group::2 M = ROWS, N = 256, K = 16 per k-step,
