@@ -262,7 +262,8 @@ class LinearEnv:
             t_end = time.perf_counter() + self.step_cost_s
             while time.perf_counter() < t_end:
                 pass
-        self.x = (self.A @ self.x + self.B @ np.asarray(action, dtype=np.float32)).astype(np.float32)
+        a = np.asarray(action, dtype=np.float32).reshape(-1)  # the reference hands (1, act) exploration actions to env.step
+        self.x = (self.A @ self.x + self.B @ a).astype(np.float32)
         self.t += 1
         reward = float(np.tanh(self.w @ self.x))
         return self.x.copy(), reward, self.t >= self.horizon, {}
