@@ -512,7 +512,7 @@ def run_ours(args, w, shape, rank, local_rank, world):
                    "step": (f"{E_head} lock-step environments x {n_total} candidates planned by ONE m3pc_plan launch sequence per GPU "
                             f"(Learner.action_sample_batch); the one-window call of the reference is reported under single_env") if E_head > 1 else
                            "one window per plan (Learner.action_sample)", "l2": "256 MiB flush write between timed plans (outside the per-plan event pairs)",
-                   "weights": weights_note, "chunk": args.chunk},
+                   "weights": weights_note, "chunk": args.chunk, "options": args.option},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": win_bytes, "d2h_bytes_per_step": 4 * A * E_head,
                 "p50_latency_ms": 1e3 * statistics.median(head.lat),
                 "api": ("Learner.action_sample_batch(E host numpy histories) -> .cpu()" if E_head > 1 else "Learner.action_sample(host numpy history) -> .cpu()")},
@@ -557,6 +557,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE",
+                    help="m3pc_set_option applied to every engine (A/B between result-equivalent launch sequences), e.g. fused_mlp=0")
     ap.add_argument("--lean", action="store_true", help="headline workload only: no north-star hopper key, no library baseline, no cand_shard")
     ap.add_argument("--cand-shard", action="store_true", help="also run the candidate-sharded config (halfcheetah 16384) on a single GPU")
     args = ap.parse_args()
@@ -572,6 +574,11 @@ def main():
         run_reference(args, w, shape, rank)
         return
     from m3pc_b200 import dist as mdist
+    if args.option:
+        from m3pc_b200.engine import PlanEngine
+        for kv in args.option:
+            k, v = kv.split("=")
+            PlanEngine.default_options[k] = int(v)
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # a box-level NCCL_DEBUG=VERSION would otherwise print to stdout, next to the JSON line
     mdist.init_from_env("nccl")
     try:

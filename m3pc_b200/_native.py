@@ -33,7 +33,7 @@ GUIDANCE = {
 #: every symbol include/m3pc.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = (
     "m3pc_last_error", "m3pc_version", "m3pc_create", "m3pc_destroy", "m3pc_set_param", "m3pc_finalize_params", "m3pc_set_option",
-    "m3pc_forward", "m3pc_plan", "m3pc_merge_partials", "m3pc_exchange_local", "m3pc_exchange_connect", "m3pc_exchange_status", "m3pc_backward_plan", "m3pc_backward_plan_draws", "m3pc_ring_append", "m3pc_ring_windows", "m3pc_gemm_bf16", "m3pc_gemm_bf16_grouped", "m3pc_gemm_ln_bf16", "m3pc_gemm_fp32",
+    "m3pc_forward", "m3pc_plan", "m3pc_merge_partials", "m3pc_exchange_local", "m3pc_exchange_connect", "m3pc_exchange_status", "m3pc_backward_plan", "m3pc_backward_plan_draws", "m3pc_ring_append", "m3pc_ring_windows", "m3pc_gemm_bf16", "m3pc_gemm_bf16_grouped", "m3pc_gemm_ln_bf16", "m3pc_mlp_fused_bf16", "m3pc_gemm_fp32",
     "m3pc_layernorm", "m3pc_attention", "m3pc_embed_gather", "m3pc_decoder_scatter_embed", "m3pc_heads", "m3pc_sample_candidates", "m3pc_twinq",
     "m3pc_score_select", "m3pc_last_device_ms", "m3pc_last_launch_count", "m3pc_set_profile", "m3pc_get_profile",
 )
@@ -111,6 +111,7 @@ def lib() -> C.CDLL:
     L.m3pc_gemm_bf16.argtypes = [vp, vp, f32p, vp, i32, i32, i32, i32, vp]
     L.m3pc_gemm_bf16_grouped.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.m3pc_gemm_ln_bf16.argtypes = [vp, vp, f32p, f32p, vp, f32p, f32p, f32p, i32, i32, i32, vp]
+    L.m3pc_mlp_fused_bf16.argtypes = [vp, vp, f32p, vp, f32p, f32p, i32, vp]
     L.m3pc_gemm_fp32.argtypes = [f32p, f32p, f32p, f32p, i32, i32, i32, i32, vp]
     L.m3pc_layernorm.argtypes = [f32p, f32p, f32p, vp, i32, i32, i32, vp]
     L.m3pc_attention.argtypes = [vp, vp, i32, i32, i32, i32, vp]

@@ -196,6 +196,9 @@ int gemm_init_driver_api();
 // gemm_ln.cu: X (M,512) fp32 <- R + A W^T + bias (R = X in place, or table[row / rows_per_group]); Y (M,512) bf16 <- LayerNorm(X)
 int gemm_ln_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, float* X, __nv_bfloat16* Y, const float* gamma,
                  const float* beta, const float* table, int rows_per_group, int M, int K, cudaStream_t st);
+// mlp_fused.cu: X (M,512) fp32 += GELU(Y W1^T + b1) W2^T + b2, the 2048-wide hidden kept on chip
+int mlp_fused_bf16(const __nv_bfloat16* Y, const __nv_bfloat16* W1, const float* b1, const __nv_bfloat16* W2, const float* b2, float* X, int M,
+                   cudaStream_t st);
 // several independent bf16 GEMMs in one launch of the CTA-pair kernel (decoder embedding runs, K/V + Q, heads, twin critics)
 struct GemmProblem {
   const __nv_bfloat16* A;

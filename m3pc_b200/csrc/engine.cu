@@ -140,6 +140,8 @@ struct m3pc_engine {
   bool dedupe_history = true;  // M3PC_NO_DEDUPE=1 disables
   DevBuf fb_xd, fb_bar;  // fused B = 1 path: decoder-embedding scratch, grid-barrier state
   bool use_fused_b1 = true;
+  bool fuse_mlp = false;      // linear1 + GELU + linear2 + residual in one kernel, hidden on chip (mlp_fused.cu); option "fused_mlp".
+                              // Off by default: measured 4 % slower per step than the two launches (profiles/r2l_fused_mlp.txt)
   bool fuse_ln = true;        // residual GEMM + LayerNorm in one kernel (gemm_ln.cu); M3PC_NO_FUSED_LN=1 disables
   int fuse_ln_min_rows = 1024;  // M3PC_FUSED_LN_MIN_ROWS overrides (the kernel-level parity tests call it at any size)
   bool restrict_deep = true;  // decoders with > 1 layer: last layer on the consumed rows only (M3PC_DEC_FULL=1 disables)
@@ -600,9 +602,47 @@ struct PostLn {
   void* y = nullptr;
 };
 
+// X += W2 GELU(W1 Y + b1) + b2 in ONE kernel with the 4D-wide hidden kept on chip (mlp_fused.cu), where it applies: bf16 mode,
+// n_embd 512, and -- like the fused residual + LayerNorm kernel -- from fuse_ln_min_rows rows up, so that the kernel choice does not
+// depend on how candidates are chunked or sharded.  Returns M3PC_OK + *done = true when it ran.
+int mlp_fused(m3pc_engine* e, const LayerW& w, const void* Y, float* X, int rows, cudaStream_t st, bool* done) {
+  *done = false;
+  if (!(e->bf16 && e->fuse_mlp && e->D == 512 && e->F == 2048 && rows >= e->fuse_ln_min_rows)) return M3PC_OK;
+  size_t slot = 0;
+  if (e->profile) {
+    slot = e->prof_used++;
+    if (slot >= e->prof_events.size()) {
+      cudaEvent_t a, c;
+      M3PC_CHECK_CUDA(cudaEventCreate(&a));
+      M3PC_CHECK_CUDA(cudaEventCreate(&c));
+      e->prof_events.push_back({a, c});
+      e->prof_flops.push_back(0.0);
+    }
+    e->prof_flops[slot] = 2.0 * 2.0 * rows * static_cast<double>(e->D) * e->F;
+    M3PC_CHECK_CUDA(cudaEventRecord(e->prof_events[slot].first, st));
+  }
+  M3PC_TRY(mlp_fused_bf16(reinterpret_cast<const __nv_bfloat16*>(Y), w.l1_w16, w.l1_b, w.l2_w16, w.l2_b, X, rows, st));
+  if (e->profile) M3PC_CHECK_CUDA(cudaEventRecord(e->prof_events[slot].second, st));
+  *done = true;
+  return M3PC_OK;
+}
+
 // second half of a pre-LN transformer block on `rows` token-major rows: expects Y = LN2(X); X += MLP(Y); then `post` (optional)
 int mlp_half(m3pc_engine* e, const LayerW& w, int rows, cudaStream_t st, const PostLn& post) {
   const int D = e->D, F = e->F;
+  bool fused = false;
+  M3PC_TRY(mlp_fused(e, w, e->Y.p, e->X.as<float>(), rows, st, &fused));
+  if (fused) {
+    if (post.y == nullptr) return M3PC_OK;
+    LnParams ln{};
+    ln.x = e->X.as<float>();
+    ln.rows = rows;
+    ln.g1 = post.g;
+    ln.b1 = post.b;
+    ln.y1 = post.y;
+    ln.rows_per_group = 1;
+    return launch_layernorm(ln, D, e->bf16, st);
+  }
   GemmEpilogue ep;
   ep.bias = w.l1_b;
   ep.flags = EPI_GELU;
@@ -886,14 +926,18 @@ int restricted_last_layer(m3pc_engine* e, const FwdIO& io, const LayerW& w, cons
   const int rows = need.n * Bc;
   // out-projection + norm2 (fused: the 128-row-unit kernel hides its epilogue under the next unit's MMAs), then (g) the MLP
   M3PC_TRY(gemm_res_ln(e, e->ATT.p, w.out_w, w.out_w16, w.out_b, e->XS.as<float>(), e->Y.p, w.n2_w, w.n2_b, nullptr, 1, rows, D, st));
-  ge = GemmEpilogue{};
-  ge.bias = w.l1_b;
-  ge.flags = EPI_GELU;
-  M3PC_TRY(gemm(e, e->Y.p, w.l1_w, w.l1_w16, e->HID.p, rows, F, D, ge, st));
-  ge = GemmEpilogue{};
-  ge.bias = w.l2_b;
-  ge.flags = EPI_RESIDUAL;
-  M3PC_TRY(gemm(e, e->HID.p, w.l2_w, w.l2_w16, e->XS.p, rows, D, F, ge, st));
+  bool fused_mlp_done = false;
+  M3PC_TRY(mlp_fused(e, w, e->Y.p, e->XS.as<float>(), rows, st, &fused_mlp_done));
+  if (!fused_mlp_done) {
+    ge = GemmEpilogue{};
+    ge.bias = w.l1_b;
+    ge.flags = EPI_GELU;
+    M3PC_TRY(gemm(e, e->Y.p, w.l1_w, w.l1_w16, e->HID.p, rows, F, D, ge, st));
+    ge = GemmEpilogue{};
+    ge.bias = w.l2_b;
+    ge.flags = EPI_RESIDUAL;
+    M3PC_TRY(gemm(e, e->HID.p, w.l2_w, w.l2_w16, e->XS.p, rows, D, F, ge, st));
+  }
   // (h) norms + heads
   M3PC_TRY(final_norms(e, e->XS.as<float>(), need.n, need.tok, Bc, st, io.out_mu != nullptr && need.nt[M3PC_ACTIONS] > 0));
   return heads(e, io, need, e->Y.p, e->Y2.p, b0, Bc, st);
@@ -1568,6 +1612,7 @@ int m3pc_set_option(m3pc_handle_t h, const char* name, int32_t value) {
   else if (n == "pdl") m3pc::g_use_pdl = value != 0;
   else if (n == "fused_b1") h->use_fused_b1 = value != 0;
   else if (n == "fused_ln") h->fuse_ln = value != 0;
+  else if (n == "fused_mlp") h->fuse_mlp = value != 0;
   else if (n == "fused_ln_min_rows") h->fuse_ln_min_rows = std::max(129, static_cast<int>(value));
   else if (n == "restrict_deep_decoder") h->restrict_deep = value != 0;
   else if (n == "dedupe_history") h->dedupe_history = value != 0;
@@ -1757,6 +1802,11 @@ int m3pc_gemm_ln_bf16(const void* A, const void* W, const float* bias, float* X,
                       const float* table, int32_t rows_per_group, int32_t M, int32_t K, void* stream) {
   return m3pc::gemm_ln_bf16(reinterpret_cast<const __nv_bfloat16*>(A), reinterpret_cast<const __nv_bfloat16*>(W), bias, X,
                             reinterpret_cast<__nv_bfloat16*>(Y), gamma, beta, table, rows_per_group, M, K, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int m3pc_mlp_fused_bf16(const void* Y, const void* W1, const float* b1, const void* W2, const float* b2, float* X, int32_t M, void* stream) {
+  return m3pc::mlp_fused_bf16(reinterpret_cast<const __nv_bfloat16*>(Y), reinterpret_cast<const __nv_bfloat16*>(W1), b1,
+                              reinterpret_cast<const __nv_bfloat16*>(W2), b2, X, M, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int m3pc_gemm_fp32(const float* A, const float* W, const float* bias, float* C, int32_t M, int32_t N, int32_t K, int32_t flags, void* stream) {
