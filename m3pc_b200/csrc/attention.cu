@@ -298,6 +298,51 @@ __global__ void __launch_bounds__(SH_WARPS * 32) attention_mma_shared_kernel(con
   const int bx_lo = static_cast<int>(static_cast<long long>(blockIdx.x) * nblk / gridDim.x);
   const int bx_hi = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * nblk / gridDim.x);
   int cur_grp = -1;
+  // Row descriptors, one per lane and slot: combined list [queries 0 .. n_q) | per-batch keys 0 .. n_b)] (n_q <= 16, n_b <= 32).
+  // The copy loops below fetch a row's address with two shuffles instead of re-deriving it (parameter loads, a division and a
+  // 64-bit multiply) for every 16-byte chunk -- the kernel was bound by exactly that integer work, not by memory
+  // (profiles/r2j: 'wait' / 'short_scoreboard' stalls on the address arithmetic, 6 % on the cp.async wait).
+  const char* rbase[2];
+  long long rstride[2], vdelta[2];
+  int rdiv[2];
+#pragma unroll
+  for (int sl = 0; sl < 2; ++sl) {
+    const int i = sl * 32 + lane;
+    rbase[sl] = nullptr; rstride[sl] = 0; vdelta[sl] = 0; rdiv[sl] = 0;
+    if (i < n_q) {
+      rbase[sl] = reinterpret_cast<const char*>(p.q[i].ptr) + h * HD * 2;
+      rstride[sl] = static_cast<long long>(p.q[i].bstride) * 2;
+      rdiv[sl] = p.q[i].bdiv;
+    } else if (i < n_q + n_b) {
+      const AttnTok& tk = p.k[i - n_q];
+      rbase[sl] = reinterpret_cast<const char*>(tk.ptr) + h * HD * 2;
+      rstride[sl] = static_cast<long long>(tk.bstride) * 2;
+      rdiv[sl] = tk.bdiv;
+      vdelta[sl] = reinterpret_cast<const char*>(p.v[i - n_q].ptr) - reinterpret_cast<const char*>(tk.ptr);
+    }
+  }
+  // pad rows are zeroed ONCE: per-batch K / V pad rows are never written again; Q pad rows later hold finite leftovers of the
+  // staged output, which only feed their own (discarded) score rows
+  for (int idx = lane; idx < 16 * 16; idx += 32)
+    if ((idx >> 4) >= n_q) *reinterpret_cast<uint4*>(sQ + swz(idx >> 4, idx & 15)) = make_uint4(0, 0, 0, 0);
+  for (int idx = lane; idx < BP * 16; idx += 32)
+    if ((idx >> 4) >= n_b) {
+      *reinterpret_cast<uint4*>(sKb + swz(idx >> 4, idx & 15)) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(sVb + swz(idx >> 4, idx & 15)) = make_uint4(0, 0, 0, 0);
+    }
+  __syncwarp();
+  const int cchunk = lane & 15, rhalf = lane >> 4;
+  const int D_out = p.n_head * HD;
+  auto row_ptr = [&](const char* const (&rp)[2], int i) -> const char* {  // address of combined row i for this iteration's batch row
+    unsigned long long v = reinterpret_cast<unsigned long long>(rp[0]);
+    unsigned lo = __shfl_sync(0xffffffffu, static_cast<unsigned>(v), i & 31), hi = __shfl_sync(0xffffffffu, static_cast<unsigned>(v >> 32), i & 31);
+    if (NTB > 1) {  // rows 32 .. 47 live in slot 1
+      const unsigned long long w = reinterpret_cast<unsigned long long>(rp[1]);
+      const unsigned lo1 = __shfl_sync(0xffffffffu, static_cast<unsigned>(w), i & 31), hi1 = __shfl_sync(0xffffffffu, static_cast<unsigned>(w >> 32), i & 31);
+      if (i >= 32) { lo = lo1; hi = hi1; }
+    }
+    return reinterpret_cast<const char*>((static_cast<unsigned long long>(hi) << 32) | lo);
+  };
 #pragma unroll 1
   for (int bx = bx_lo; bx < bx_hi; ++bx) {
     const int b_raw = bx * SH_WARPS + warp;
@@ -325,22 +370,32 @@ __global__ void __launch_bounds__(SH_WARPS * 32) attention_mma_shared_kernel(con
         }
       }
     }
-    for (int idx = lane; idx < 16 * 16; idx += 32) {  // queries of this warp's batch row
-      const int r = idx >> 4, c = idx & 15;
-      if (r < n_q)
-        cp_async16(uQ + swz(r, c), reinterpret_cast<const __nv_bfloat16*>(p.q[r].ptr) + tok_off(p.q[r], b) + h * HD + c * 8);
-      else
-        *reinterpret_cast<uint4*>(sQ + swz(r, c)) = make_uint4(0, 0, 0, 0);
+    const char* rp[2];  // this iteration's address of the lane's rows
+    long long vd[2];
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+      rp[sl] = rbase[sl] + static_cast<long long>(rdiv[sl] > 0 ? b / rdiv[sl] : b) * rstride[sl];
+      vd[sl] = vdelta[sl];
     }
-    for (int idx = lane; idx < BP * 16; idx += 32) {  // per-batch keys / values
-      const int r = idx >> 4, c = idx & 15;
-      const uint32_t off = swz(r, c);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {  // queries of this warp's batch row: rows rhalf + 2 i, the lane's 16-byte chunk of each
+      const int r = rhalf + 2 * i;
+      const char* src = row_ptr(rp, r);
+      if (r < n_q) cp_async16(uQ + swz(r, cchunk), src + cchunk * 16);
+    }
+#pragma unroll
+    for (int i = 0; i < BP / 2; ++i) {  // per-batch keys / values
+      const int r = rhalf + 2 * i, ri = n_q + r;
+      const char* src = row_ptr(rp, ri);
+      long long dv = __shfl_sync(0xffffffffu, vd[0], ri & 31);
+      if (NTB > 1) {
+        const long long dv1 = __shfl_sync(0xffffffffu, vd[1], ri & 31);
+        if (ri >= 32) dv = dv1;
+      }
       if (r < n_b) {
-        cp_async16(uKb + off, reinterpret_cast<const __nv_bfloat16*>(p.k[r].ptr) + tok_off(p.k[r], b) + h * HD + c * 8);
-        cp_async16(uVb + off, reinterpret_cast<const __nv_bfloat16*>(p.v[r].ptr) + tok_off(p.v[r], b) + h * HD + c * 8);
-      } else {
-        *reinterpret_cast<uint4*>(sKb + off) = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(sVb + off) = make_uint4(0, 0, 0, 0);
+        const uint32_t off = swz(r, cchunk);
+        cp_async16(uKb + off, src + cchunk * 16);
+        cp_async16(uVb + off, src + dv + cchunk * 16);
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -423,11 +478,12 @@ __global__ void __launch_bounds__(SH_WARPS * 32) attention_mma_shared_kernel(con
     }
     __syncwarp();
     if (live) {
-      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-      const int D = p.n_head * HD;
-      for (int idx = lane; idx < n_q * 16; idx += 32) {
-        const int r = idx >> 4, c = idx & 15;
-        *reinterpret_cast<uint4*>(out + (static_cast<size_t>(r) * p.B + b) * D + h * HD + c * 8) = *reinterpret_cast<const uint4*>(sQ + swz(r, c));
+      char* orow = reinterpret_cast<char*>(p.out) + ((static_cast<size_t>(rhalf) * p.B + b) * D_out + h * HD) * 2 + cchunk * 16;
+      const size_t ostep = static_cast<size_t>(2) * p.B * D_out * 2;  // two query rows further
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rhalf + 2 * i;
+        if (r < n_q) *reinterpret_cast<uint4*>(orow + i * ostep) = *reinterpret_cast<const uint4*>(sQ + swz(r, cchunk));
       }
     }
     __syncwarp();  // the copy-out has read this warp's tiles before the next block's loads overwrite them
@@ -485,7 +541,8 @@ int launch_attention_gather(const AttnParams& p, bool bf16, cudaStream_t st) {
     const int n_c = p.n_kv - p.n_kv_batch, ntb = (p.n_kv_batch + 15) / 16, ntc = (n_c + 15) / 16;
     bool ok = n_c >= 8 && ntb <= 2 && ntc <= 3;
     for (int j = 0; j < p.n_kv && ok; ++j)
-      ok = j < p.n_kv_batch ? true : ((p.k[j].bstride == 0 && p.v[j].bstride == 0 && p.k[j].bdiv == 0 && p.v[j].bdiv == 0) ||
+      ok = j < p.n_kv_batch ? (p.k[j].bstride == p.v[j].bstride && p.k[j].bdiv == p.v[j].bdiv)  // K and V of a token move together
+                            : ((p.k[j].bstride == 0 && p.v[j].bstride == 0 && p.k[j].bdiv == 0 && p.v[j].bdiv == 0) ||
                                       (p.k[j].bdiv > 0 && p.k[j].bdiv % SH_WARPS == 0 && p.v[j].bdiv == p.k[j].bdiv));
     if (ok) {
       switch (ntb * 10 + ntc) {
