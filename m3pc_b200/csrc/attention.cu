@@ -158,19 +158,45 @@ __global__ void __launch_bounds__(MMA_WARPS * 32) attention_mma_kernel(const __g
   const uint32_t uQ = smem_u32(sQ), uK = smem_u32(sK), uV = smem_u32(sV);
 
   // ---- stage Q, K, V: 16 chunks of 16 bytes per row; pad rows are zeroed ----
-  for (int idx = lane; idx < QP * 16; idx += 32) {
-    const int r = idx >> 4, c = idx & 15;
-    if (r < n_q)
-      cp_async16(uQ + swz(r, c), reinterpret_cast<const __nv_bfloat16*>(p.q[r].ptr) + tok_off(p.q[r], b) + h * HD + c * 8);
-    else
-      *reinterpret_cast<uint4*>(sQ + swz(r, c)) = make_uint4(0, 0, 0, 0);
+  // A row's address is derived ONCE, by the lane whose index is the row (parameter loads, the group division, a 64-bit multiply),
+  // and fetched with two shuffles by the lanes that copy its chunks -- not re-derived for each of its 16 chunks.
+  constexpr int QSL = (QP + 31) / 32, KSL = (KP + 31) / 32;
+  const char *qrow[QSL], *krow[KSL], *vrow[KSL];
+#pragma unroll
+  for (int sl = 0; sl < QSL; ++sl) {
+    const int i = sl * 32 + lane;
+    qrow[sl] = i < n_q ? reinterpret_cast<const char*>(p.q[i].ptr) + (tok_off(p.q[i], b) + h * HD) * 2 : nullptr;
   }
-  for (int idx = lane; idx < KP * 16; idx += 32) {
-    const int r = idx >> 4, c = idx & 15;
-    const uint32_t off = swz(r, c);
+#pragma unroll
+  for (int sl = 0; sl < KSL; ++sl) {
+    const int i = sl * 32 + lane;
+    krow[sl] = i < S ? reinterpret_cast<const char*>(p.k[i].ptr) + (tok_off(p.k[i], b) + h * HD) * 2 : nullptr;
+    vrow[sl] = i < S ? reinterpret_cast<const char*>(p.v[i].ptr) + (tok_off(p.v[i], b) + h * HD) * 2 : nullptr;
+  }
+  auto shfl_ptr = [](const char* ptr, int src) -> const char* {
+    const unsigned long long v = reinterpret_cast<unsigned long long>(ptr);
+    const unsigned lo = __shfl_sync(0xffffffffu, static_cast<unsigned>(v), src), hi = __shfl_sync(0xffffffffu, static_cast<unsigned>(v >> 32), src);
+    return reinterpret_cast<const char*>((static_cast<unsigned long long>(hi) << 32) | lo);
+  };
+  const int cchunk = lane & 15, rhalf = lane >> 4;
+#pragma unroll
+  for (int i = 0; i < QP / 2; ++i) {  // rows rhalf + 2 i: the slot of a row is a compile-time constant of i
+    const int r = rhalf + 2 * i;
+    const char* src = shfl_ptr(qrow[i >> 4], r & 31);
+    if (r < n_q)
+      cp_async16(uQ + swz(r, cchunk), src + cchunk * 16);
+    else
+      *reinterpret_cast<uint4*>(sQ + swz(r, cchunk)) = make_uint4(0, 0, 0, 0);
+  }
+#pragma unroll
+  for (int i = 0; i < KP / 2; ++i) {
+    const int r = rhalf + 2 * i;
+    const uint32_t off = swz(r, cchunk);
+    const char* ks = shfl_ptr(krow[i >> 4], r & 31);
+    const char* vs = shfl_ptr(vrow[i >> 4], r & 31);
     if (r < S) {
-      cp_async16(uK + off, reinterpret_cast<const __nv_bfloat16*>(p.k[r].ptr) + tok_off(p.k[r], b) + h * HD + c * 8);
-      cp_async16(uV + off, reinterpret_cast<const __nv_bfloat16*>(p.v[r].ptr) + tok_off(p.v[r], b) + h * HD + c * 8);
+      cp_async16(uK + off, ks + cchunk * 16);
+      cp_async16(uV + off, vs + cchunk * 16);
     } else {
       *reinterpret_cast<uint4*>(sK + off) = make_uint4(0, 0, 0, 0);
       *reinterpret_cast<uint4*>(sV + off) = make_uint4(0, 0, 0, 0);
