@@ -476,6 +476,14 @@ def run_ours(args, w, shape, rank, local_rank, world):
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md sustained)"
+    gemm_kernel = "gemm_bf16_2sm_kernel + gemm_ln_2sm_kernel (tcgen05 cta_group::2; the latter carries the residual add and the LayerNorm)"
+    if args.precision == "fp32":
+        # the fp32 mode runs its GEMMs on the FFMA pipe (sgemm.cu): its ceiling is SMs x 128 lanes x 2 flop x the SM clock under load
+        mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        peak_tf = sms * 128 * 2 * mhz * 1e6 / 1e12
+        peak_src = f"computed: {sms} SMs x 128 FFMA lanes x 2 x {mhz:.0f} MHz (the fp32 path does not use tensor cores)"
+        gemm_kernel = "sgemm_kernel (fp32 FFMA, 128x128 tiles; reference-grade precision mode, not the headline path)"
     ach_tf = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     fl_plan, fl_row = flops_per_plan(shape, n_total, w["guidance"], h)
     traffic, traffic_src = None, None
@@ -520,9 +528,9 @@ def run_ours(args, w, shape, rank, local_rank, world):
                        "p50_ms_device": statistics.median(single.per_step_ms), "p50_latency_ms_e2e": 1e3 * statistics.median(single.lat),
                        "launches_per_plan": single.launches, "api": "Learner.action_sample(host numpy history) -> .cpu()"},
         "gpu_launches": head.launches * K,
-        "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None,
+        "roofline": {"bound": "tensor" if args.precision == "bf16" else "fp32_ffma", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None,
                      "traffic": traffic, "traffic_source": traffic_src,
-                     "kernel": "gemm_bf16_2sm_kernel + gemm_ln_2sm_kernel (tcgen05 cta_group::2; the latter carries the residual add and the LayerNorm)",
+                     "kernel": gemm_kernel,
                      "launches_per_step": g_n // 3, "gemm_ms_per_step": g_ms / 3,
                      "gemm_flops_per_step": g_fl / 3, "gemm_flops_per_plan": g_fl / 3 / E_head, "peak_source": peak_src,
                      "whole_step_executed_frac": (g_fl / 3) / (dev_s / K) / (peak_tf * 1e12) if dev_s > 0 else None,

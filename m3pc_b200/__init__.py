@@ -5,7 +5,7 @@ Host-side mirror of the reference's model / planner API (``omtm``, ``omtmConfig`
 over a C-ABI CUDA library (``include/m3pc.h``, built from ``m3pc_b200/csrc``).  There is no CPU fallback:
 every compute entry point raises if the CUDA library or a GPU is missing.
 """
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 
 from . import synthetic  # noqa: F401  (numpy only)
 

@@ -1585,7 +1585,7 @@ int timed(m3pc_engine* e, cudaStream_t st, Fn&& fn) {
 extern "C" {
 
 const char* m3pc_last_error(void) { return m3pc::g_error.c_str(); }
-const char* m3pc_version(void) { return "m3pc-b200 0.1.0 (sm_100a)"; }
+const char* m3pc_version(void) { return "m3pc-b200 0.2.0 (sm_100a)"; }
 
 int m3pc_create(m3pc_handle_t* out, const m3pc_config_t* cfg) { return m3pc::create(out, cfg); }
 
