@@ -271,6 +271,16 @@ int m3pc_attention(const void* qkv, void* out, int32_t B, int32_t S, int32_t n_h
  *   y_out  device (S*batch, D) activation type: LayerNorm(x_out; encoder.layers.0.norm1) */
 int m3pc_embed_gather(m3pc_handle_t h, int32_t batch, const float* tok_states, const float* tok_actions, const float* tok_rewards,
                       const float* tok_returns, const uint8_t* masks, float* x_out, void* y_out, void* stream);
+/* K2 + K3 -- ONE pre-LN transformer block (nn.TransformerEncoderLayer(norm_first=True, activation="gelu"), built at
+ * mtm_model.py:379-409, run by forward_encoder :619-644 / forward_decoder :698-706): x += MHA(LN1(x)); x += W2 gelu(W1 LN2(x) + b1) + b2.
+ * The same launch sequence m3pc_forward uses for a block (QKV GEMM, attention, out-projection + residual + norm2, linear1 + GELU,
+ * linear2 + residual + the LayerNorm that follows).
+ *   stack   0 = encoder.layers[layer], 1 = decoder.layers[layer]
+ *   x       device fp32 (n_tok*batch, D), token-major (row = token * batch + b): the residual stream, updated in place
+ *   y_next  device (n_tok*batch, D) activation type or NULL: LayerNorm of the result by the NEXT block's norm1, or by the
+ *           stack's final norm after its last layer (the operand the next block / the decoder embedding / K5 consumes)
+ *   n_tok <= 4T (attention keys of one batch row), batch <= the engine's chunk, n_tok*batch <= 4T*chunk workspace rows. */
+int m3pc_block_forward(m3pc_handle_t h, int32_t stack, int32_t layer, int32_t batch, int32_t n_tok, float* x, void* y_next, void* stream);
 /* K4 -- encoder output -> decoder input: mask-token scatter + decoder_embed + per-dim + pos (mtm_model.py:646-696).
  *   enc_out device (S*batch, D) activation type: final-normed encoder output of the kept tokens, token-major
  *   x_out   device fp32 (4T*batch, D): row block j = decoder token j (modality-major, time-minor); masked tokens get the

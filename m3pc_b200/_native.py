@@ -34,7 +34,7 @@ GUIDANCE = {
 SYMBOLS = (
     "m3pc_last_error", "m3pc_version", "m3pc_create", "m3pc_destroy", "m3pc_set_param", "m3pc_finalize_params", "m3pc_set_option",
     "m3pc_forward", "m3pc_plan", "m3pc_merge_partials", "m3pc_exchange_local", "m3pc_exchange_connect", "m3pc_exchange_status", "m3pc_backward_plan", "m3pc_backward_plan_draws", "m3pc_ring_append", "m3pc_ring_windows", "m3pc_gemm_bf16", "m3pc_gemm_bf16_grouped", "m3pc_gemm_ln_bf16", "m3pc_mlp_fused_bf16", "m3pc_gemm_fp32",
-    "m3pc_layernorm", "m3pc_attention", "m3pc_embed_gather", "m3pc_decoder_scatter_embed", "m3pc_heads", "m3pc_sample_candidates", "m3pc_twinq",
+    "m3pc_layernorm", "m3pc_attention", "m3pc_embed_gather", "m3pc_decoder_scatter_embed", "m3pc_block_forward", "m3pc_heads", "m3pc_sample_candidates", "m3pc_twinq",
     "m3pc_score_select", "m3pc_last_device_ms", "m3pc_last_launch_count", "m3pc_set_profile", "m3pc_get_profile",
 )
 
@@ -118,6 +118,7 @@ def lib() -> C.CDLL:
     L.m3pc_embed_gather.argtypes = [vp, i32, f32p, f32p, f32p, f32p, vp, f32p, vp, vp]
     L.m3pc_decoder_scatter_embed.argtypes = [vp, i32, vp, vp, f32p, vp]
     L.m3pc_heads.argtypes = [vp, i32, f32p, f32p, f32p, f32p, f32p, f32p, vp]
+    L.m3pc_block_forward.argtypes = [vp, i32, i32, i32, i32, f32p, vp, vp]
     L.m3pc_sample_candidates.argtypes = [f32p, f32p, f32p, C.c_uint64, i32, i32, i32, i32, i32, i32, f32p, vp]
     L.m3pc_twinq.argtypes = [vp, f32p, f32p, i32, i32, f32p, vp]
     L.m3pc_score_select.argtypes = [f32p, f32p, f32p, f32p, f32p, vp, C.c_float, C.c_float, C.c_float, i32, i32, i32, i32, C.c_uint64, i32,

@@ -1861,6 +1861,29 @@ int m3pc_embed_gather(m3pc_handle_t h, int32_t batch, const float* tok_states, c
   return m3pc::launch_embed(ep, h->D, x_out, y_out, h->bf16, first.n1_w, first.n1_b, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int m3pc_block_forward(m3pc_handle_t h, int32_t stack, int32_t layer, int32_t batch, int32_t n_tok, float* x, void* y_next, void* stream) {
+  M3PC_REQUIRE(h != nullptr && h->finalized && x != nullptr, "bad argument");
+  M3PC_REQUIRE(stack == 0 || stack == 1, "stack must be 0 (encoder) or 1 (decoder)");
+  const m3pc::StackW& sw = stack == 0 ? h->enc : h->dec;
+  const int n_layer = stack == 0 ? h->Le : h->Ld;
+  M3PC_REQUIRE(layer >= 0 && layer < n_layer, "layer out of range");
+  M3PC_REQUIRE(batch >= 1 && batch <= h->chunk && n_tok >= 1 && n_tok <= 4 * h->T, "batch exceeds the engine's chunk, or more tokens than 4T");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t rows = static_cast<size_t>(batch) * n_tok, D = h->D, ab = m3pc::act_bytes(h);
+  const m3pc::LayerW& w = sw.layers[layer];
+  M3PC_CHECK_CUDA(cudaMemcpyAsync(h->X.p, x, rows * D * 4, cudaMemcpyDeviceToDevice, st));
+  m3pc::LnParams ln{};
+  ln.x = h->X.as<float>(); ln.rows = static_cast<int>(rows); ln.g1 = w.n1_w; ln.b1 = w.n1_b; ln.y1 = h->Y.p; ln.rows_per_group = 1;
+  M3PC_TRY(m3pc::launch_layernorm(ln, h->D, h->bf16, st));
+  m3pc::PostLn post;
+  if (y_next != nullptr)
+    post = layer + 1 < n_layer ? m3pc::PostLn{sw.layers[layer + 1].n1_w, sw.layers[layer + 1].n1_b, h->ENC.p} : m3pc::PostLn{sw.norm_w, sw.norm_b, h->ENC.p};
+  M3PC_TRY(m3pc::block(h, w, batch, n_tok, st, post));
+  M3PC_CHECK_CUDA(cudaMemcpyAsync(x, h->X.p, rows * D * 4, cudaMemcpyDeviceToDevice, st));
+  if (y_next != nullptr) M3PC_CHECK_CUDA(cudaMemcpyAsync(y_next, h->ENC.p, rows * D * ab, cudaMemcpyDeviceToDevice, st));
+  return M3PC_OK;
+}
+
 int m3pc_decoder_scatter_embed(m3pc_handle_t h, int32_t batch, const void* enc_out, const uint8_t* masks, float* x_out, void* stream) {
   M3PC_REQUIRE(h != nullptr && h->finalized && enc_out && masks && x_out, "bad argument");
   M3PC_REQUIRE(batch >= 1 && batch <= h->chunk, "batch exceeds the engine's chunk (workspace rows)");

@@ -71,6 +71,43 @@ def test_k1_embed_gather(nat, precision, mask_name, idx, B):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("stack,B,S", [(0, 150, 13), (0, 3, 17), (1, 40, 32), (0, 1100, 13)])
+def test_k2_k3_block_forward(nat, precision, stack, B, S):
+    """One transformer block of the handle through its own entry (K2 GEMMs + K3 attention + the fused LayerNorms) against the
+    oracle's restatement of nn.TransformerEncoderLayer (oracle/mtm_oracle.py:encoder_layer); 1100 x 13 rows takes the fused
+    residual-GEMM + LayerNorm kernels, the small cases the plain tiles."""
+    from oracle import mtm_oracle as mo
+    shape = syn.shipped_shape("walker2d")
+    eng = _engine(shape, precision, max_batch=max(256, B))
+    sd = mo.to_torch(syn.make_state_dict(shape, 0), torch.float64)
+    D = shape.n_embd
+    name = ("encoder", "decoder")[stack]
+    n_layer = (shape.n_enc_layer, shape.n_dec_layer)[stack]
+    torch.manual_seed(B + S)
+    x0 = torch.randn(B, S, D, dtype=torch.float64)
+    for layer in range(n_layer):
+        ref = mo.encoder_layer(x0, sd, f"{name}.layers.{layer}", shape.n_head)
+        nxt = f"{name}.layers.{layer + 1}.norm1" if layer + 1 < n_layer else f"{name}.norm"
+        ref_y = mo.layer_norm(ref, sd[nxt + ".weight"], sd[nxt + ".bias"])
+        x = tok_major(x0).float().cuda()
+        y = torch.full((S * B, D), float("nan"), device="cuda", dtype=torch.bfloat16 if precision == "bf16" else torch.float32)
+        nat.check(nat.lib().m3pc_block_forward(eng._h, stack, layer, B, S, x.data_ptr(), y.data_ptr(), None))
+        torch.cuda.synchronize()
+        tol = TOL[precision]
+        assert rel(x, tok_major(ref)) < tol, (layer, rel(x, tok_major(ref)))
+        assert rel(y, tok_major(ref_y)) < (2e-5 if precision == "fp32" else 2e-2), layer
+        # without the trailing LayerNorm the residual stream is the same
+        x2 = tok_major(x0).float().cuda()
+        nat.check(nat.lib().m3pc_block_forward(eng._h, stack, layer, B, S, x2.data_ptr(), None, None))
+        torch.cuda.synchronize()
+        assert rel(x2, x) < (1e-6 if precision == "fp32" else 2e-3)
+    with pytest.raises(ValueError):
+        nat.check(nat.lib().m3pc_block_forward(eng._h, 2, 0, B, S, x.data_ptr(), None, None))
+    with pytest.raises(ValueError):
+        nat.check(nat.lib().m3pc_block_forward(eng._h, stack, n_layer, B, S, x.data_ptr(), None, None))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("mask_name,idx,B", [("fd", 4, 200), ("pi", 3, 33), ("rcbc", 0, 2)])
 def test_k4_decoder_scatter_embed(nat, precision, mask_name, idx, B):
     from oracle import planner_oracle as po

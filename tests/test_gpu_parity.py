@@ -36,7 +36,9 @@ def nat():
 
 
 # ------------------------------------------------------------------------------------------------ kernels
-@pytest.mark.parametrize("M,N,K,flags", [(17, 1536, 512, 0), (200, 512, 2048, 1), (333, 256, 23, 4), (64, 1, 256, 0), (1000, 512, 512, 2)])
+@pytest.mark.parametrize("M,N,K,flags", [(17, 1536, 512, 0), (200, 512, 2048, 1), (333, 256, 23, 4), (64, 1, 256, 0), (1000, 512, 512, 2),
+                                         # the 128 x 128 tiling: ragged rows / columns / K, one slab, every epilogue
+                                         (128, 128, 16, 0), (129, 130, 17, 2), (1000, 2048, 512, 1), (4099, 257, 100, 6), (13312, 512, 2048, 2)])
 def test_gemm_fp32(nat, M, N, K, flags):
     torch.manual_seed(0)
     A, W, b = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda") / K ** 0.5, torch.randn(N, device="cuda")
