@@ -483,11 +483,13 @@ def run_ours(args, w, shape, rank, local_rank, world):
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         peak_tf = sms * 128 * 2 * mhz * 1e6 / 1e12
         peak_src = f"computed: {sms} SMs x 128 FFMA lanes x 2 x {mhz:.0f} MHz (the fp32 path does not use tensor cores)"
-        gemm_kernel = "sgemm_kernel (fp32 FFMA, 128x128 tiles; reference-grade precision mode, not the headline path)"
+        gemm_kernel = "sgemm128_kernel (fp32 FFMA, 128x128x16 tiles, 8x8 outputs per thread; reference-grade precision mode, not the headline path)"
     ach_tf = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     fl_plan, fl_row = flops_per_plan(shape, n_total, w["guidance"], h)
     traffic, traffic_src = None, None
     try:
+        if args.precision != "bf16":
+            raise KeyError("the committed DRAM-traffic capture is of the bf16 GEMMs")
         tj = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json")))
         traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
     except Exception:

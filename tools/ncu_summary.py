@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Key counters of every launch in an ncu report: python tools/ncu_summary.py report.ncu-rep [out.json]
-Prints one block per launch and (optionally) writes the mean DRAM bytes per launch as JSON for bench.py."""
+Prints one block per launch and (optionally) writes the mean DRAM bytes per tensor-core GEMM launch as JSON for bench.py
+(profiles/gemm_traffic.json, the roofline.traffic figure)."""
 import csv, io, json, subprocess, sys
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -15,17 +16,22 @@ col = {h: i for i, h in enumerate(hdr)}
 def to_bytes(v, u):
     v = float(v.replace(",", ""))
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
-tot, n = 0.0, 0
+tot, n = 0.0, 0  # DRAM bytes of the tensor-core GEMM launches only (the kernels bench.py's roofline line is about)
 for r in body:
     print("---")
     for w in WANT:
         if w in col:
             print(f"  {w} [{units[col[w]]}] = {r[col[w]][:90]}")
     try:
+        name = r[col["Kernel Name"]]
+        if "gemm_bf16_2sm" not in name and "gemm_ln" not in name:
+            continue
         tot += to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]]) + to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
         n += 1
     except Exception:
         pass
 if len(sys.argv) > 2 and n:
-    json.dump({"report": rep, "launches": n, "dram_bytes_per_launch": tot / n}, open(sys.argv[2], "w"))
-    print("mean dram bytes per launch", tot / n)
+    json.dump({"source": "ncu --set full of one default step (tools/round_evidence.sh): dram__bytes_read.sum + dram__bytes_write.sum, mean over the "
+                         "gemm_bf16_2sm_kernel and gemm_ln_2sm_kernel launches of one 8-environment x 1024-candidate plan",
+               "report": rep, "launches": n, "dram_bytes_per_launch": tot / n}, open(sys.argv[2], "w"))
+    print("mean dram bytes per tensor-core GEMM launch", tot / n)

@@ -1,7 +1,6 @@
 # compute-sanitizer memcheck over representative parity tests (small shapes): fused GEMM + LayerNorm, env-batched plan, device ring,
 # zero-shot draws, checkpoint geometry, reference golden planners
 mkdir -p gpurun_out
-export M3PC_NO_GRAPHS=1
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 --print-limit 20 python -m pytest tests/test_gpu_parity.py -x -q -m gpu \
   -k "residual_layernorm_fused and (256 or 300 or 4000) or env_batched_plan_rows and bf16 or reference_format_checkpoints and bf16 or candidate_draws and bf16 or planners_match_reference_golden and bf16" \
   > gpurun_out/san_parity.txt 2>&1; echo "rc=$?" >> gpurun_out/san_parity.txt
