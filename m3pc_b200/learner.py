@@ -156,6 +156,56 @@ class PlannerMixin:
         ev, sm = self._plan_from_trajectory("rtg_guiding", trajectory, h, lmbda)
         return sm.clone()[None, :], ev.clone()
 
+    # -- validation loss (the forward half of SURVEY.md section 8(f) rank 4) ----------------------------------
+    @torch.no_grad()
+    def eval_mtm_loss(self, batch: Dict[str, torch.Tensor], data_shapes, discrete_map, entropy_reg, masks=None, eps=None):
+        """``compute_mtm_loss`` (finetune_omtm/learner.py:419-503) for logging: the masked-prediction loss of a validation batch
+        with the MTM forward on the B200 engine and NO autograd graph -- what ``finetune.py:346-369`` needs between training
+        steps.  Training itself (``mtm_update``: backward + optimiser) stays on the reference's module.
+
+        Same arguments and the same 5-tuple ``(loss, losses, masked_losses, masked_c_losses, entropy)``.  The reference returns
+        from inside its loop over modalities after the first continuous non-action key, so ``loss`` is the ``states`` MSE plus
+        the action negative log-likelihood and entropy terms, and the three dicts hold ``states`` (+ ``entropy``, ``nll``) only;
+        that behaviour is reproduced, not corrected.  ``masks`` (default: one draw of ``create_random_autoregressize_mask`` with
+        ``cfg.mask_ratio`` / ``cfg.p_weights`` from numpy's global generator, like the reference) and ``eps`` (the normal draws of
+        the single-sample entropy estimate, shape (1, B, T, 1, act)) can be injected for reproducible comparisons."""
+        from . import masks as M
+        model = self._planner_model()
+        self._engine()
+        dev = model.pos_embed.device
+        targets = self.tokenizer_manager.encode({k: v.to(dev) for k, v in batch.items()})
+        if masks is None:
+            masks = M.create_random_autoregressize_mask(data_shapes, self.cfg.mask_ratio, self.cfg.traj_length, dev, self.cfg.p_weights)
+        B = next(iter(targets.values())).shape[0]
+        step = int(model.config.max_batch)
+        parts = [model({k: v[b0:b0 + step] for k, v in targets.items()}, masks) for b0 in range(0, B, step)]
+        preds = {k: torch.cat([p[k] for p in parts]) for k in ("states", "rewards", "returns")}
+        from .mtm_model import SquashedNormal
+        preds["actions"] = SquashedNormal(torch.cat([p["actions"].loc for p in parts]), torch.cat([p["actions"].std for p in parts]))
+
+        key = next(k for k in targets if k != "actions")
+        if discrete_map[key]:
+            raise NotImplementedError("discrete modalities are not supported by the B200 engine")
+        target, pred = targets[key].to(torch.float32), preds[key]
+        mask = masks[key].to(dev)
+        if mask.dim() == 1:
+            mask = mask[:, None].repeat(1, target.shape[2])
+        raw = (pred - target) ** 2                                    # (B, T, P, d)
+        vis = mask[None, :, :, None].to(raw.dtype)
+        losses = {key: raw.mean(dim=(2, 3)).mean()}
+        masked_c_losses = {key: ((raw * vis).sum(dim=(1, 2, 3)) / mask.sum()).mean()}
+        masked_losses = {key: ((raw * (1 - vis)).sum(dim=(1, 2, 3)) / (1 - mask).sum()).mean()}
+        loss = torch.sum(torch.stack(list(losses.values())))
+        hidden = ~masks["actions"].to(dev).squeeze().to(torch.bool)
+        dist = preds["actions"]
+        a = targets["actions"].to(torch.float32).clip(-1 + 1e-6, 1 - 1e-6)
+        log_likelihood = dist.log_likelihood(a)[:, hidden, :].mean()
+        entropy = dist.entropy(eps=eps)[:, hidden, :].mean()
+        losses["entropy"] = entropy
+        losses["nll"] = -log_likelihood
+        loss = loss - (log_likelihood + entropy_reg * entropy)
+        return loss, losses, masked_losses, masked_c_losses, entropy
+
     # -- window builder (host) ------------------------------------------------------------------------------
     def _window_buffers(self, obs_dim: int, act_dim: int, n_env: int = 1):
         """Two pinned host staging buffers (alternating, each guarded by a CUDA event so a buffer is never rewritten while

@@ -10,6 +10,7 @@ Not provided (out of the planning path): ``forward_loss``, 
 from __future__ import annotations
 
 import dataclasses
+import math
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -47,6 +48,28 @@ class SquashedNormal:
     def sample(self, sample_shape=()) -> torch.Tensor:
         with torch.no_grad():
             return self.rsample(sample_shape)
+
+    # ---- densities (validation loss, finetune_omtm/learner.py:491-499) ----
+    def _log_prob_pre(self, u: torch.Tensor) -> torch.Tensor:
+        """log density of tanh(u), u ~ N(loc, std): Normal log-density minus log|d tanh / du| = 2 (log 2 - u - softplus(-2u))
+        (TanhTransform.log_abs_det_jacobian, mtm_model.py:247-251)."""
+        z = (u - self.loc) / self.std
+        normal = -0.5 * z * z - torch.log(self.std) - 0.5 * math.log(2.0 * math.pi)
+        return normal - 2.0 * (math.log(2.0) - u - torch.nn.functional.softplus(-2.0 * u))
+
+    def log_prob(self, x: torch.Tensor) -> torch.Tensor:
+        return self._log_prob_pre(0.5 * (torch.log1p(x) - torch.log1p(-x)))  # atanh as the reference writes it (mtm_model.py:234-236)
+
+    def log_likelihood(self, x: torch.Tensor) -> torch.Tensor:
+        """Summed over axis 2 like the reference (mtm_model.py:286-291): (B, T, 1, A) -> (B, T, A)."""
+        return self.log_prob(x).sum(dim=2)
+
+    def entropy(self, N: int = 1, eps: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Single-sample estimate -log p(x), x ~ self (mtm_model.py:277-284).  ``eps`` (N, *loc.shape) injects the normal draws
+        (test hook); the pre-tanh value is used directly, as the reference's cached transform does."""
+        if eps is None:
+            eps = torch.randn((N,) + tuple(self.loc.shape), dtype=self.loc.dtype, device=self.loc.device)
+        return -self._log_prob_pre(self.loc + self.std * eps).mean(dim=0).sum(dim=2)
 
 
 @dataclasses.dataclass
