@@ -32,6 +32,30 @@ def test_mask_creators_bit_exact_vs_reference(golden_dir):
         M.create_fd_mask(8, "cpu", 8)
 
 
+def test_random_autoregressive_masks_bit_exact_vs_reference(golden_dir):
+    """The validation-loss mask draw (finetune_omtm/masks.py:64-125) consumes numpy's global generator in the reference's order:
+    same seed, same masks (fixture written by the reference, tests/golden/gen_valloss_fixture.py)."""
+    import json
+    z = np.load(os.path.join(golden_dir, "valloss.npz"))
+    meta = json.loads(str(z["meta"]))
+    shapes = {"states": (1, 17), "actions": (1, 6), "rewards": (1, 1), "returns": (1, 1)}
+    n = 0
+    for ci, (ratios, pw) in enumerate(meta["mask_configs"]):
+        ratios = tuple(ratios) if isinstance(ratios, list) else ratios
+        for seed in range(meta["mask_seeds"]):
+            for T in (8, 16):
+                np.random.seed(seed)
+                m = M.create_random_autoregressize_mask(shapes, ratios, T, "cpu", tuple(pw))
+                assert list(m.keys()) == list(shapes) and all(v.dtype == torch.float64 and tuple(v.shape) == (T, 1) for v in m.values())
+                assert np.array_equal(np.stack([m[k].numpy()[:, 0] for k in m]), z[f"mask/{ci}/{T}/{seed}"]), (ci, T, seed)
+                assert not bool(m["actions"].eq(1).all())
+                n += 1
+    assert n == 360
+    rs = np.random.RandomState(5)
+    one = M.create_full_random_mask((1, 3), 10, 0.4, "cpu", rs)
+    assert tuple(one.shape) == (10, 1) and int(one.sum()) == 4
+
+
 def test_kept_token_counts():
     # SURVEY.md appendix: rcbc 17 / fd 13 / pi=gid 10 / fid 12 at idx=4; 9 / 9 / 8 / 8 at idx=0
     for idx, want in ((4, (17, 13, 10, 12)), (0, (9, 9, 8, 8))):
