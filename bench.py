@@ -541,6 +541,7 @@ def run_ours(args, w, shape, rank, local_rank, world):
                              "the whole step; dense_equivalent_speed_frac counts FLOPs the restricted decoder and the shared-history block do NOT "
                              "execute -- a speed in dense-plan units, not a roofline fraction"},
         "flops_per_plan_dense": fl_plan, "flops_per_candidate_row": fl_row,
+        "candidate_rollouts_per_sec": value * n_total,  # plans/s x candidates per plan
         "p50_ms": statistics.median(head.per_step_ms), "wall_s_resident_loop": wall_resident,
         "clocks": clocks,
     }
@@ -559,7 +560,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="walker2d_critic_1024", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="env", choices=["env", "cand"])
