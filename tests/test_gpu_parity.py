@@ -355,6 +355,39 @@ def test_plan_internals_vs_fp64_oracle(precision, env, guidance, temp, N, pl):
         assert rel(L.action_sample(hist, plan=True, eval=False, rtg=3.0)[0], ref["sample_action"][0]) < max(tol, 1e-4)
 
 
+def test_plan_internals_random_sweep():
+    """The same comparison over a seeded random sweep of ragged shapes: candidate counts around the tile / chunk / warp boundaries,
+    every horizon the window builder can produce (path_length 0 .. 3 -> h = 8 .. 5), the episode end, all three guidances."""
+    rs = np.random.RandomState(20260)
+    counts = [2, 3, 31, 33, 63, 65, 127, 129, 255, 257, 300, 511]
+    lengths = [0, 1, 2, 3, 4, 7, 50, 998]
+    guid = [("hopper", "rtg_guiding", 0.01), ("walker2d", "critic_lambda_guiding", 1.0), ("halfcheetah", "noise_adding_lambda", 1.0),
+            ("halfcheetah", "rtg_guiding", 0.01), ("hopper", "critic_lambda_guiding", 0.1)]  # temperatures of the reference's configs:
+    # the eval action is a softmax average over scores of magnitude ~1e3 (1000 x return-to-go), so at temperature x |dJ| >~ 1 it
+    # amplifies a 1e-3 relative score error beyond any fixed action tolerance (checked separately against the device scores in
+    # tests/test_gpu_bench_sizes.py)
+    for i in range(14):
+        env, g, temp = guid[rs.randint(len(guid))]
+        N, pl = counts[rs.randint(len(counts))], lengths[rs.randint(len(lengths))]
+        precision = "fp32" if i % 4 == 3 else "bf16"
+        try:
+            test_plan_internals_vs_fp64_oracle(precision, env, g, temp, N, pl)
+        except AssertionError as e:
+            raise AssertionError(f"sweep case {i}: {precision} {env} {g} temperature={temp} N={N} path_length={pl}: {e}") from e
+
+
+def test_plan_with_a_single_candidate():
+    """N = 1: the softmax is trivially 1, eval action = sampled action = the only candidate."""
+    shape, L = _learner("hopper", "rtg_guiding", 1, 0.01, "bf16")
+    L.debug_plans = True
+    hist = syn.make_history(shape, seed=2, path_length=30)
+    ev = L.action_sample(hist, plan=True, eval=True, rtg=3.0)
+    cand = L.last_plan_debug["candidates"]
+    assert tuple(ev.shape) == (shape.act_dim,) and torch.equal(ev, cand[0, 0])
+    sm = L.action_sample(hist, plan=True, eval=False, rtg=3.0)
+    assert tuple(sm.shape) == (1, shape.act_dim) and torch.isfinite(sm).all()
+
+
 def test_planner_method_signatures_and_shapes():
     """rtg_guiding / critic_lambda_guiding / noise_adding_lambda / mtm_sampling called directly, as the reference allows."""
     shape, L = _learner("walker2d", "critic_lambda_guiding", 64, 1.0, "bf16")
