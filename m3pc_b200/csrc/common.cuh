@@ -193,9 +193,9 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
 int gemm_bf16_tcgen05(const __nv_bfloat16* A, const __nv_bfloat16* W, void* C, int M, int N, int K,
                       const GemmEpilogue& epi, cudaStream_t st);
 int gemm_init_driver_api();
-// gemm_ln.cu: X (M,512) fp32 <- R + A W^T + bias (R = X in place, or table[row / rows_per_group]); Y (M,512) bf16 <- LayerNorm(X)
+// gemm_ln.cu: X (M,512) fp32 <- R + A W^T + bias (R = X in place, the fp32 rows `R`, or table[row / rows_per_group]); Y (M,512) bf16 <- LayerNorm(X)
 int gemm_ln_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, float* X, __nv_bfloat16* Y, const float* gamma,
-                 const float* beta, const float* table, int rows_per_group, int M, int K, cudaStream_t st);
+                 const float* beta, const float* table, int rows_per_group, int M, int K, cudaStream_t st, const float* R = nullptr);
 // mlp_fused.cu: X (M,512) fp32 += GELU(Y W1^T + b1) W2^T + b2, the 2048-wide hidden kept on chip
 int mlp_fused_bf16(const __nv_bfloat16* Y, const __nv_bfloat16* W1, const float* b1, const __nv_bfloat16* W2, const float* b2, float* X, int M,
                    cudaStream_t st);

@@ -145,6 +145,9 @@ struct m3pc_engine {
   bool fuse_ln = true;        // residual GEMM + LayerNorm in one kernel (gemm_ln.cu); M3PC_NO_FUSED_LN=1 disables
   int fuse_ln_min_rows = 1024;  // M3PC_FUSED_LN_MIN_ROWS overrides (the kernel-level parity tests call it at any size)
   bool restrict_deep = true;  // decoders with > 1 layer: last layer on the consumed rows only (M3PC_DEC_FULL=1 disables)
+  int split_residual_min_rows = 32768;  // restricted decoder, out-projection: from this many needed rows up one launch per residual
+                                        // source (no residual copy: -6 KB of HBM traffic per row); below, a copy + ONE launch (each
+                                        // extra launch costs ~7 us: break-even near 16 K rows).  Option "split_residual_min_rows".
   // planner buffers
   DevBuf p1_mu, p1_std, cand, pred_states, pred_rewards, pred_returns, sa, qa, qb1, qb2, qvals, J, filled, e_mu, e_std;
 
@@ -552,7 +555,8 @@ int gemm_group(m3pc_engine* e, const GemmJob* jobs, int n, cudaStream_t st) {
 // X += A W^T + bias (or, with `table`, X = table[row / rpg] + A W^T + bias) followed by Y = LayerNorm(X; g, b): ONE tensor-core
 // kernel whose epilogue owns whole rows (gemm_ln.cu) where it applies (bf16 mode, n_embd 512), else GEMM + LayerNorm kernel.
 int gemm_res_ln(m3pc_engine* e, const void* A, const float* w32, const __nv_bfloat16* w16, const float* bias, float* X, void* Y,
-                const float* g, const float* b, const float* table, int rpg, int M, int K, cudaStream_t st, bool allow_fused = true) {
+                const float* g, const float* b, const float* table, int rpg, int M, int K, cudaStream_t st, bool allow_fused = true,
+                const float* res_src = nullptr) {
   const int D = e->D;
   // one CTA pair per 256 rows: not for the few hundred rows of pass 1 of a multi-environment plan, where a single pair would do
   // the work of 4 .. 16.  (The switch is kept well below any pass-2 chunk or candidate shard, so the kernel choice -- and with it
@@ -571,10 +575,11 @@ int gemm_res_ln(m3pc_engine* e, const void* A, const float* w32, const __nv_bflo
       e->prof_flops[slot] = 2.0 * M * static_cast<double>(D) * K;
       M3PC_CHECK_CUDA(cudaEventRecord(e->prof_events[slot].first, st));
     }
-    M3PC_TRY(gemm_ln_bf16(reinterpret_cast<const __nv_bfloat16*>(A), w16, bias, X, reinterpret_cast<__nv_bfloat16*>(Y), g, b, table, rpg, M, K, st));
+    M3PC_TRY(gemm_ln_bf16(reinterpret_cast<const __nv_bfloat16*>(A), w16, bias, X, reinterpret_cast<__nv_bfloat16*>(Y), g, b, table, rpg, M, K, st, res_src));
     if (e->profile) M3PC_CHECK_CUDA(cudaEventRecord(e->prof_events[slot].second, st));
     return M3PC_OK;
   }
+  M3PC_REQUIRE(res_src == nullptr, "gemm_res_ln: a separate residual source needs the fused kernel");
   GemmEpilogue ep;
   ep.bias = bias;
   if (table != nullptr) {
@@ -908,24 +913,51 @@ int restricted_last_layer(m3pc_engine* e, const FwdIO& io, const LayerW& w, cons
     }
   if (ap.n_kv_batch == 4 * T) ap.n_kv_batch = 0;  // no constant keys (deeper decoders): plain kernel
   M3PC_TRY(launch_attention_gather(ap, e->bf16, st));
-  // (f) residual rows of the needed tokens -> XS, then out-projection accumulates into them
-  FillParams fp{};
-  fp.B = Bc;
-  for (int qi = 0; qi < need.n; ++qi) {
-    const int j = need.tok[qi];
-    if (src[j] < 0) {
-      fp.row[fp.n] = e->dec_maskrow + static_cast<size_t>(j) * D;
-      fp.bstride[fp.n] = 0;
-    } else {
-      fp.row[fp.n] = e->X.as<float>() + static_cast<size_t>(src[j]) * Bc * D;
-      fp.bstride[fp.n] = D;
-    }
-    fp.tok[fp.n++] = qi;
-  }
-  M3PC_TRY(launch_fill_rows(fp, D, e->XS.as<float>(), st));
+  // (f) out-projection + residual + norm2 of the needed tokens -> XS (compact, one row block per needed token) / Y.
+  // A run = needed tokens with consecutive row blocks whose residual comes from one place: masked tokens take the batch-constant
+  // row dec_maskrow[token] (consecutive tokens of a modality are consecutive table rows), kept tokens their own residual-stream rows.
   const int rows = need.n * Bc;
-  // out-projection + norm2 (fused: the 128-row-unit kernel hides its epilogue under the next unit's MMAs), then (g) the MLP
-  M3PC_TRY(gemm_res_ln(e, e->ATT.p, w.out_w, w.out_w16, w.out_b, e->XS.as<float>(), e->Y.p, w.n2_w, w.n2_b, nullptr, 1, rows, D, st));
+  struct Run { int q0, len; const float* table; const float* res; };
+  Run runs[MAX_TOK];
+  int n_runs = 0;
+  for (int qi = 0; qi < need.n;) {
+    const int j = need.tok[qi];
+    int len = 1;
+    if (src[j] < 0) {
+      while (qi + len < need.n && need.tok[qi + len] == j + len && src[j + len] < 0) ++len;
+      runs[n_runs++] = Run{qi, len, e->dec_maskrow + static_cast<size_t>(j) * D, nullptr};
+    } else {
+      while (qi + len < need.n && src[need.tok[qi + len]] == src[j] + len) ++len;
+      runs[n_runs++] = Run{qi, len, nullptr, e->X.as<float>() + static_cast<size_t>(src[j]) * Bc * D};
+    }
+    qi += len;
+  }
+  bool per_run = e->bf16 && e->fuse_ln && D == 512 && rows >= e->split_residual_min_rows;  // and every run large enough for the fused kernel
+  for (int r = 0; r < n_runs; ++r) per_run = per_run && static_cast<long>(runs[r].len) * Bc >= e->fuse_ln_min_rows;
+  if (per_run) {
+    for (int r = 0; r < n_runs; ++r) {
+      const size_t off = static_cast<size_t>(runs[r].q0) * Bc;
+      M3PC_TRY(gemm_res_ln(e, reinterpret_cast<const char*>(e->ATT.p) + off * D * ab, w.out_w, w.out_w16, w.out_b, e->XS.as<float>() + off * D,
+                           reinterpret_cast<char*>(e->Y.p) + off * D * ab, w.n2_w, w.n2_b, runs[r].table, Bc, runs[r].len * Bc, D, st, true, runs[r].res));
+    }
+  } else {
+    // small batches: residual rows -> XS by a copy kernel, then one out-projection accumulates into them (same arithmetic, same bits)
+    FillParams fp{};
+    fp.B = Bc;
+    for (int qi = 0; qi < need.n; ++qi) {
+      const int j = need.tok[qi];
+      if (src[j] < 0) {
+        fp.row[fp.n] = e->dec_maskrow + static_cast<size_t>(j) * D;
+        fp.bstride[fp.n] = 0;
+      } else {
+        fp.row[fp.n] = e->X.as<float>() + static_cast<size_t>(src[j]) * Bc * D;
+        fp.bstride[fp.n] = D;
+      }
+      fp.tok[fp.n++] = qi;
+    }
+    M3PC_TRY(launch_fill_rows(fp, D, e->XS.as<float>(), st));
+    M3PC_TRY(gemm_res_ln(e, e->ATT.p, w.out_w, w.out_w16, w.out_b, e->XS.as<float>(), e->Y.p, w.n2_w, w.n2_b, nullptr, 1, rows, D, st));
+  }
   bool fused_mlp_done = false;
   M3PC_TRY(mlp_fused(e, w, e->Y.p, e->XS.as<float>(), rows, st, &fused_mlp_done));
   if (!fused_mlp_done) {
@@ -1615,6 +1647,7 @@ int m3pc_set_option(m3pc_handle_t h, const char* name, int32_t value) {
   else if (n == "fused_mlp") h->fuse_mlp = value != 0;
   else if (n == "fused_ln_min_rows") h->fuse_ln_min_rows = std::max(129, static_cast<int>(value));
   else if (n == "restrict_deep_decoder") h->restrict_deep = value != 0;
+  else if (n == "split_residual_min_rows") h->split_residual_min_rows = std::max(0, static_cast<int>(value));
   else if (n == "dedupe_history") h->dedupe_history = value != 0;
   else if (n == "gemm_ln_unit_rows") {
     M3PC_REQUIRE(value == 0 || value == 128 || value == 256, "gemm_ln_unit_rows must be 0 (per launch), 128 or 256");

@@ -1,6 +1,6 @@
 // Tensor-core GEMM with a fused residual + LayerNorm epilogue (N = n_embd = 512):
 //
-//     X[M,512] (fp32)  <-  R + A[M,K] W[512,K]^T + bias          R = X (in place) or table[row / rows_per_group] (first block)
+//     X[M,512] (fp32)  <-  R + A[M,K] W[512,K]^T + bias          R = X (in place), other fp32 rows, or table[row / rows_per_group]
 //     Y[M,512] (bf16)  <-  LayerNorm(X; gamma, beta)             eps 1e-5, statistics in fp32
 //
 // Reference call sites: the out-projection / linear2 of nn.TransformerEncoderLayer followed by the next pre-LN norm
@@ -47,6 +47,8 @@ constexpr int LN_THREADS = 32 * (2 + LN_EPI_WARPS);
 
 struct LnGemmParams {
   CUtensorMap ta, tw, tx, ty;
+  CUtensorMap tr;  // residual source (fp32, same box shape as tx): X itself, or other rows (restricted decoder: the residual stream
+                   // rows of a kept token, read in place while the result goes to the compact needed-row block)
   const float* bias;
   const float* gamma;
   const float* beta;
@@ -118,6 +120,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
     prefetch_tmap(&P.tw);
     prefetch_tmap(&P.tx);
     prefetch_tmap(&P.ty);
+    prefetch_tmap(&P.tr);
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -242,7 +245,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
 #pragma unroll
         for (int b = 0; b < NPRE; ++b) {
           mbar_arrive_expect_tx(&rbar[b], L::kBoxBytes);
-          tma_load_2d(sbuf + b * L::kBoxBytes, &P.tx, &rbar[b], colw + b * 16, row0);
+          tma_load_2d(sbuf + b * L::kBoxBytes, &P.tr, &rbar[b], colw + b * 16, row0);
         }
       }
       mbar_wait(&acc_full[buf], static_cast<uint32_t>(it / NACC) & 1u);
@@ -296,7 +299,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
             if (from_x && ci + NBOX < NB1) {  // this buffer is needed again for a later residual box of the unit
               bulk_wait_read<0>();
               mbar_arrive_expect_tx(&rbar[b], L::kBoxBytes);
-              tma_load_2d(bx, &P.tx, &rbar[b], col0 + NBOX * 16, row0);
+              tma_load_2d(bx, &P.tr, &rbar[b], col0 + NBOX * 16, row0);
             }
           }
           ++ns;
@@ -419,7 +422,7 @@ int launch_ln(LnGemmParams& P, int M, cudaStream_t st) {
 //   K  > 512   256-row units feed the tensor pipe with 1/3 less operand traffic per FLOP (238 vs 264 us) -- unless the launch is so
 //              small that whole 256-row units quantise badly on the 74 CTA pairs (26 624 rows: 104 units = 2 rounds, vs 3 half rounds)
 int gemm_ln_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, float* X, __nv_bfloat16* Y, const float* gamma,
-                 const float* beta, const float* table, int rows_per_group, int M, int K, cudaStream_t st) {
+                 const float* beta, const float* table, int rows_per_group, int M, int K, cudaStream_t st, const float* R) {
   M3PC_REQUIRE(M > 0 && K > 0 && K % BK == 0, "gemm_ln: K must be a positive multiple of 64");
   M3PC_REQUIRE(A && W && X && Y && gamma && beta, "gemm_ln: null operand");
   M3PC_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) & 15) == 0,
@@ -436,6 +439,8 @@ int gemm_ln_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bi
   M3PC_TRY(make_tmap(&P.ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), rows / 2));
   M3PC_TRY(make_tmap(&P.tw, W, static_cast<uint64_t>(LN_N), static_cast<uint64_t>(K), 128));
   M3PC_TRY(make_tmap_out(&P.tx, X, static_cast<uint64_t>(M), LN_N, true));
+  M3PC_REQUIRE(R == nullptr || (table == nullptr && (reinterpret_cast<uintptr_t>(R) & 15) == 0), "gemm_ln: a residual source excludes a table and must be 16-byte aligned");
+  M3PC_TRY(make_tmap_out(&P.tr, const_cast<float*>(R != nullptr ? R : X), static_cast<uint64_t>(M), LN_N, true));
   M3PC_TRY(make_tmap_out(&P.ty, Y, static_cast<uint64_t>(M), LN_N, false));
   P.bias = bias; P.gamma = gamma; P.beta = beta; P.table = table;
   P.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;

@@ -875,3 +875,21 @@ def test_plan_with_the_fused_mlp_kernel(monkeypatch):
     monkeypatch.setitem(PlanEngine.default_options, "fused_ln_min_rows", 129)
     test_plan_internals_vs_fp64_oracle("bf16", "walker2d", "critic_lambda_guiding", 1.0, 130, 50)
     test_plan_internals_vs_fp64_oracle("bf16", "hopper", "rtg_guiding", 0.01, 200, 50)
+
+
+def test_restricted_decoder_residual_sources_are_bit_identical():
+    """The restricted decoder's out-projection takes its residual either from a copied row block (small batches) or, per run of
+    needed tokens, straight from the batch-constant mask-token table / the kept token's residual-stream rows (large batches:
+    option split_residual_min_rows).  Same arithmetic, same bits: scores and actions must be equal."""
+    outs = []
+    for split in (0, 1 << 30):
+        shape, L = _learner("walker2d", "critic_lambda_guiding", 1100, 1.0, "bf16")
+        L._engine().set_option("split_residual_min_rows", split)
+        rs = np.random.RandomState(5)
+        T, A = shape.traj_length, shape.act_dim
+        L.injected_noise = (torch.from_numpy(rs.randn(1100, 4, A)).float().cuda(), torch.from_numpy(rs.exponential(1.0, 1100)).float().cuda())
+        L.debug_plans = True
+        ev = L.action_sample(syn.make_history(shape, seed=3, path_length=60), plan=True, eval=True, rtg=3.0)
+        outs.append((ev.clone(), L.last_plan_debug["expect_return"].clone(), L._engine().last_launch_count()))
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][0], outs[1][0])
+    assert outs[0][2] == outs[1][2] + 1  # three launches (kept state, masked states, masked rewards) instead of a copy + one
