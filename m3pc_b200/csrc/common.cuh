@@ -196,6 +196,18 @@ int gemm_init_driver_api();
 // gemm_ln.cu: X (M,512) fp32 <- R + A W^T + bias (R = X in place, the fp32 rows `R`, or table[row / rows_per_group]); Y (M,512) bf16 <- LayerNorm(X)
 int gemm_ln_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, float* X, __nv_bfloat16* Y, const float* gamma,
                  const float* beta, const float* table, int rows_per_group, int M, int K, cudaStream_t st, const float* R = nullptr);
+// several such problems in ONE launch (at most 4; same K, bias, gamma, beta): own A / W / X / Y / residual source each
+struct LnJob {
+  const __nv_bfloat16* A;
+  const __nv_bfloat16* W;
+  float* X;
+  __nv_bfloat16* Y;
+  const float* table;   // residual = table[row / rows_per_group], or null
+  int rows_per_group;
+  int M;
+  const float* R;       // residual rows when they are not X itself (and table is null), or null
+};
+int gemm_ln_bf16_grouped(const LnJob* jobs, int n, const float* bias, const float* gamma, const float* beta, int K, cudaStream_t st);
 // mlp_fused.cu: X (M,512) fp32 += GELU(Y W1^T + b1) W2^T + b2, the 2048-wide hidden kept on chip
 int mlp_fused_bf16(const __nv_bfloat16* Y, const __nv_bfloat16* W1, const float* b1, const __nv_bfloat16* W2, const float* b2, float* X, int M,
                    cudaStream_t st);

@@ -142,12 +142,13 @@ struct m3pc_engine {
   bool use_fused_b1 = true;
   bool fuse_mlp = false;      // linear1 + GELU + linear2 + residual in one kernel, hidden on chip (mlp_fused.cu); option "fused_mlp".
                               // Off by default: measured 4 % slower per step than the two launches (profiles/r2l_fused_mlp.txt)
+  bool group_ln = true;       // several fused residual GEMM + LayerNorm problems per launch; option "grouped_ln" (0: one launch each)
   bool fuse_ln = true;        // residual GEMM + LayerNorm in one kernel (gemm_ln.cu); M3PC_NO_FUSED_LN=1 disables
   int fuse_ln_min_rows = 1024;  // M3PC_FUSED_LN_MIN_ROWS overrides (the kernel-level parity tests call it at any size)
   bool restrict_deep = true;  // decoders with > 1 layer: last layer on the consumed rows only (M3PC_DEC_FULL=1 disables)
-  int split_residual_min_rows = 32768;  // restricted decoder, out-projection: from this many needed rows up one launch per residual
-                                        // source (no residual copy: -6 KB of HBM traffic per row); below, a copy + ONE launch (each
-                                        // extra launch costs ~7 us: break-even near 16 K rows).  Option "split_residual_min_rows".
+  int split_residual_min_rows = 0;  // restricted decoder, out-projection: from this many needed rows up the residual is read in place, one
+                                    // problem per residual source in a grouped launch (no residual copy: -6 KB of HBM traffic per row);
+                                    // below, a copy kernel + one problem.  Option "split_residual_min_rows" (tests force either form).
   // planner buffers
   DevBuf p1_mu, p1_std, cand, pred_states, pred_rewards, pred_returns, sa, qa, qb1, qb2, qvals, J, filled, e_mu, e_std;
 
@@ -600,6 +601,57 @@ int gemm_res_ln(m3pc_engine* e, const void* A, const float* w32, const __nv_bflo
   return launch_layernorm(ln, D, e->bf16, st);
 }
 
+// Several residual GEMM + LayerNorm problems that share K, bias and the LayerNorm parameters: ONE launch of the fused kernel where
+// it applies to every problem (the ~10 us fixed cost of a launch is paid once), else one gemm_res_ln per problem.
+struct ResLnJob {
+  const void* A;
+  const float* w32;
+  const __nv_bfloat16* w16;
+  float* X;
+  void* Y;
+  const float* table;
+  int rpg;
+  int M;
+  const float* res_src;
+};
+int gemm_res_ln_group(m3pc_engine* e, const ResLnJob* jobs, int n, const float* bias, const float* g, const float* b, int K, cudaStream_t st) {
+  const int D = e->D;
+  bool fused = e->bf16 && e->fuse_ln && D == 512 && e->group_ln;
+  for (int i = 0; i < n; ++i) fused = fused && jobs[i].M >= e->fuse_ln_min_rows;
+  if (!fused || n == 1) {
+    for (int i = 0; i < n; ++i)
+      M3PC_TRY(gemm_res_ln(e, jobs[i].A, jobs[i].w32, jobs[i].w16, bias, jobs[i].X, jobs[i].Y, g, b, jobs[i].table, jobs[i].rpg, jobs[i].M, K, st, true,
+                           jobs[i].res_src));
+    return M3PC_OK;
+  }
+  for (int i0 = 0; i0 < n; i0 += 4) {
+    const int m = std::min(4, n - i0);
+    LnJob lj[4];
+    double flops = 0.0;
+    for (int i = 0; i < m; ++i) {
+      const ResLnJob& j = jobs[i0 + i];
+      lj[i] = LnJob{reinterpret_cast<const __nv_bfloat16*>(j.A), j.w16, j.X, reinterpret_cast<__nv_bfloat16*>(j.Y), j.table, j.rpg, j.M, j.res_src};
+      flops += 2.0 * j.M * static_cast<double>(D) * K;
+    }
+    size_t slot = 0;
+    if (e->profile) {
+      slot = e->prof_used++;
+      if (slot >= e->prof_events.size()) {
+        cudaEvent_t a, c;
+        M3PC_CHECK_CUDA(cudaEventCreate(&a));
+        M3PC_CHECK_CUDA(cudaEventCreate(&c));
+        e->prof_events.push_back({a, c});
+        e->prof_flops.push_back(0.0);
+      }
+      e->prof_flops[slot] = flops;
+      M3PC_CHECK_CUDA(cudaEventRecord(e->prof_events[slot].first, st));
+    }
+    M3PC_TRY(gemm_ln_bf16_grouped(lj, m, bias, g, b, K, st));
+    if (e->profile) M3PC_CHECK_CUDA(cudaEventRecord(e->prof_events[slot].second, st));
+  }
+  return M3PC_OK;
+}
+
 // LayerNorm applied to the residual stream right after a block: the next block's norm1 or a stack's final norm
 struct PostLn {
   const float* g = nullptr;
@@ -707,10 +759,11 @@ int block_shared_history(m3pc_engine* e, const LayerW& w, int Bc, int S, int n_s
   M3PC_TRY(launch_attention_gather(ap, e->bf16, st));
   // out-projection + norm2.  Shared tokens: X = table[token, group] + att W^T + b (row / grp = token * nG + group);
   // per-candidate tokens: X += att W^T + b.
-  M3PC_TRY(gemm_res_ln(e, e->ATT.p, w.out_w, w.out_w16, w.out_b, e->X.as<float>(), e->Y.p, w.n2_w, w.n2_b, e->XT.as<float>(), grp,
-                       static_cast<int>(off), D, st));
-  M3PC_TRY(gemm_res_ln(e, reinterpret_cast<const char*>(e->ATT.p) + off * D * ab, w.out_w, w.out_w16, w.out_b, e->X.as<float>() + off * D,
-                       reinterpret_cast<char*>(e->Y.p) + off * D * ab, w.n2_w, w.n2_b, nullptr, 1, (S - n_sh) * Bc, D, st));
+  const ResLnJob outp[2] = {
+      {e->ATT.p, w.out_w, w.out_w16, e->X.as<float>(), e->Y.p, e->XT.as<float>(), grp, static_cast<int>(off), nullptr},
+      {reinterpret_cast<const char*>(e->ATT.p) + off * D * ab, w.out_w, w.out_w16, e->X.as<float>() + off * D, reinterpret_cast<char*>(e->Y.p) + off * D * ab,
+       nullptr, 1, (S - n_sh) * Bc, nullptr}};
+  M3PC_TRY(gemm_res_ln_group(e, outp, 2, w.out_b, w.n2_w, w.n2_b, D, st));
   return mlp_half(e, w, S * Bc, st, post);
 }
 
@@ -935,11 +988,13 @@ int restricted_last_layer(m3pc_engine* e, const FwdIO& io, const LayerW& w, cons
   bool per_run = e->bf16 && e->fuse_ln && D == 512 && rows >= e->split_residual_min_rows;  // and every run large enough for the fused kernel
   for (int r = 0; r < n_runs; ++r) per_run = per_run && static_cast<long>(runs[r].len) * Bc >= e->fuse_ln_min_rows;
   if (per_run) {
+    ResLnJob jobs[MAX_TOK];
     for (int r = 0; r < n_runs; ++r) {
       const size_t off = static_cast<size_t>(runs[r].q0) * Bc;
-      M3PC_TRY(gemm_res_ln(e, reinterpret_cast<const char*>(e->ATT.p) + off * D * ab, w.out_w, w.out_w16, w.out_b, e->XS.as<float>() + off * D,
-                           reinterpret_cast<char*>(e->Y.p) + off * D * ab, w.n2_w, w.n2_b, runs[r].table, Bc, runs[r].len * Bc, D, st, true, runs[r].res));
+      jobs[r] = ResLnJob{reinterpret_cast<const char*>(e->ATT.p) + off * D * ab, w.out_w, w.out_w16, e->XS.as<float>() + off * D,
+                         reinterpret_cast<char*>(e->Y.p) + off * D * ab, runs[r].table, Bc, runs[r].len * Bc, runs[r].res};
     }
+    M3PC_TRY(gemm_res_ln_group(e, jobs, n_runs, w.out_b, w.n2_w, w.n2_b, D, st));
   } else {
     // small batches: residual rows -> XS by a copy kernel, then one out-projection accumulates into them (same arithmetic, same bits)
     FillParams fp{};
@@ -994,16 +1049,19 @@ int decode_restricted(m3pc_engine* e, const FwdIO& io, const void* enc_out, cons
     // (a) + (b) in one kernel per run of kept tokens of a modality: X = dec_cvec[token] + enc_out W_dec^T (compact, encoder order),
     // Y = LN1(X) -- the table-residual form of the fused residual GEMM + LayerNorm kernel (no residual traffic at all)
     const size_t ab = act_bytes(e);
+    ResLnJob jobs[MAX_TOK];
+    int nj = 0;
     for (int j = 0; j < 4 * T;) {
       if (dec_src[j] < 0) { ++j; continue; }
       const int k = j / T;
       int len = 1;
       while (j + len < (k + 1) * T && dec_src[j + len] == dec_src[j] + len) ++len;
       const size_t r0 = static_cast<size_t>(dec_src[j]) * Bc;
-      M3PC_TRY(gemm_res_ln(e, reinterpret_cast<const char*>(enc_out) + r0 * D * ab, e->dec_w[k], e->dec_w16[k], nullptr, e->X.as<float>() + r0 * D,
-                           reinterpret_cast<char*>(e->Y.p) + r0 * D * ab, w.n1_w, w.n1_b, e->dec_cvec + static_cast<size_t>(j) * D, Bc, len * Bc, D, st));
+      jobs[nj++] = ResLnJob{reinterpret_cast<const char*>(enc_out) + r0 * D * ab, e->dec_w[k], e->dec_w16[k], e->X.as<float>() + r0 * D,
+                            reinterpret_cast<char*>(e->Y.p) + r0 * D * ab, e->dec_cvec + static_cast<size_t>(j) * D, Bc, len * Bc, nullptr};
       j += len;
     }
+    M3PC_TRY(gemm_res_ln_group(e, jobs, nj, nullptr, w.n1_w, w.n1_b, D, st));
     return restricted_last_layer(e, io, w, dec_src, S, need, b0, Bc, st);
   }
   // (a) decoder embedding of the kept tokens, compact (encoder order) -> X[0 : S*Bc)
@@ -1645,6 +1703,7 @@ int m3pc_set_option(m3pc_handle_t h, const char* name, int32_t value) {
   else if (n == "fused_b1") h->use_fused_b1 = value != 0;
   else if (n == "fused_ln") h->fuse_ln = value != 0;
   else if (n == "fused_mlp") h->fuse_mlp = value != 0;
+  else if (n == "grouped_ln") h->group_ln = value != 0;
   else if (n == "fused_ln_min_rows") h->fuse_ln_min_rows = std::max(129, static_cast<int>(value));
   else if (n == "restrict_deep_decoder") h->restrict_deep = value != 0;
   else if (n == "split_residual_min_rows") h->split_residual_min_rows = std::max(0, static_cast<int>(value));

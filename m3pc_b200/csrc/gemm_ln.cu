@@ -45,19 +45,41 @@ constexpr int LN_N = 512;
 constexpr int LN_EPI_WARPS = 16;
 constexpr int LN_THREADS = 32 * (2 + LN_EPI_WARPS);
 
-struct LnGemmParams {
+constexpr int LN_MAX_GROUP = 4;
+
+// One problem of a launch: X[M,512] <- R + A W^T + bias, Y <- LayerNorm(X).  Several problems share a launch (same K, bias, gamma,
+// beta; own operands, outputs and residual source): the fixed cost of a launch -- barrier set-up, tensor-memory allocation,
+// cluster sync, pipeline fill and drain, ~10 us -- is paid once for e.g. the table part and the per-candidate part of the first
+// encoder block's out-projection, the decoder-embedding runs of the kept tokens, or the residual sources of the restricted decoder.
+struct LnProblem {
   CUtensorMap ta, tw, tx, ty;
-  CUtensorMap tr;  // residual source (fp32, same box shape as tx): X itself, or other rows (restricted decoder: the residual stream
-                   // rows of a kept token, read in place while the result goes to the compact needed-row block)
+  CUtensorMap tr;      // residual source (fp32, same box shape as tx): X itself, or other rows (restricted decoder: the residual-stream
+                       // rows of a kept token, read in place while the result goes to the compact needed-row block)
+  const float* table;  // null: residual through tr
+  int rows_per_group;
+  int M;
+  int unit0;           // first unit of this problem in the launch's unit order
+};
+
+struct LnGemmParams {
+  LnProblem p[LN_MAX_GROUP];
   const float* bias;
   const float* gamma;
   const float* beta;
-  const float* table;  // null: residual = X
-  int rows_per_group;
-  int M, num_kb, n_units;
+  int n, num_kb, n_units;
   int tune;  // tuning build only (timing experiments, results are garbage): bit 0 = no residual loads, bit 1 = no X store,
              // bit 2 = no Y store (pass 2 only drains TMEM), bit 3 = epilogue only hands the accumulator back
 };
+static_assert(sizeof(LnGemmParams) <= 4000, "kernel parameter space");
+
+// problem of unit u (a launch has at most LN_MAX_GROUP problems, ordered by unit0)
+__device__ __forceinline__ int ln_problem_of(const LnGemmParams& P, int u) {
+  int g = 0;
+#pragma unroll
+  for (int i = 1; i < LN_MAX_GROUP; ++i)
+    if (i < P.n && u >= P.p[i].unit0) g = i;
+  return g;
+}
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
   asm volatile(
@@ -116,11 +138,13 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&P.ta);
-    prefetch_tmap(&P.tw);
-    prefetch_tmap(&P.tx);
-    prefetch_tmap(&P.ty);
-    prefetch_tmap(&P.tr);
+    for (int g = 0; g < P.n; ++g) {
+      prefetch_tmap(&P.p[g].ta);
+      prefetch_tmap(&P.p[g].tw);
+      prefetch_tmap(&P.p[g].tx);
+      prefetch_tmap(&P.p[g].ty);
+      prefetch_tmap(&P.p[g].tr);
+    }
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -156,15 +180,16 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
       int s = 0;
       uint32_t ph = 0;
       for (int u = pair; u < P.n_units; u += n_pairs) {
-        const int m0 = (u * 2 + static_cast<int>(crank)) * (ROWS / 2);
+        const LnProblem& Q = P.p[ln_problem_of(P, u)];
+        const int m0 = ((u - Q.unit0) * 2 + static_cast<int>(crank)) * (ROWS / 2);
         for (int kb = 0; kb < P.num_kb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           if (leader) mbar_arrive_expect_tx(&full_bar[s], 2u * L::kStageBytes);
           uint8_t* dst = smem + s * L::kStageBytes;
           const uint32_t bar = full_leader + 8u * static_cast<uint32_t>(s);
-          tma_load_2d_2sm(dst, &P.ta, bar, kb * BK, m0);
-          tma_load_2d_2sm(dst + L::kABlk, &P.tw, bar, kb * BK, static_cast<int>(crank) * 128);
-          tma_load_2d_2sm(dst + L::kABlk + L::kBBlk, &P.tw, bar, kb * BK, 256 + static_cast<int>(crank) * 128);
+          tma_load_2d_2sm(dst, &Q.ta, bar, kb * BK, m0);
+          tma_load_2d_2sm(dst + L::kABlk, &Q.tw, bar, kb * BK, static_cast<int>(crank) * 128);
+          tma_load_2d_2sm(dst + L::kABlk + L::kBBlk, &Q.tw, bar, kb * BK, 256 + static_cast<int>(crank) * 128);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -220,7 +245,6 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
 #else
     constexpr int tune = 0;
 #endif
-    const bool from_x = P.table == nullptr && !(tune & 1);
     const float* sbias = sconst;
     const float* sgamma = sconst + LN_N;
     const float* sbeta = sconst + 2 * LN_N;
@@ -234,9 +258,11 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
     uint32_t ns = 0;
     for (int u = pair; u < P.n_units; u += n_pairs, ++it) {
       const uint32_t buf = static_cast<uint32_t>(it % NACC);
-      const int row0 = (u * 2 + static_cast<int>(crank)) * (ROWS / 2) + rowq * 32;
+      const LnProblem& Q = P.p[ln_problem_of(P, u)];
+      const bool from_x = Q.table == nullptr && !(tune & 1);
+      const int row0 = ((u - Q.unit0) * 2 + static_cast<int>(crank)) * (ROWS / 2) + rowq * 32;
       const int row = row0 + lane;
-      const bool live = row0 < P.M && !(tune & 8);
+      const bool live = row0 < Q.M && !(tune & 8);
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * ACC_COLS + tcol;
       // residual boxes travel to shared memory while the MMAs of this unit (and the epilogue of the previous one) still run
       if (from_x) ns = 0;
@@ -245,7 +271,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
 #pragma unroll
         for (int b = 0; b < NPRE; ++b) {
           mbar_arrive_expect_tx(&rbar[b], L::kBoxBytes);
-          tma_load_2d(sbuf + b * L::kBoxBytes, &P.tr, &rbar[b], colw + b * 16, row0);
+          tma_load_2d(sbuf + b * L::kBoxBytes, &Q.tr, &rbar[b], colw + b * 16, row0);
         }
       }
       mbar_wait(&acc_full[buf], static_cast<uint32_t>(it / NACC) & 1u);
@@ -269,7 +295,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
           }
           tmem_ld_wait();
           float v[16];
-          const float* trow = (from_x || P.table == nullptr) ? nullptr : P.table + static_cast<size_t>(min(row, P.M - 1) / P.rows_per_group) * LN_N + col0;
+          const float* trow = (from_x || Q.table == nullptr) ? nullptr : Q.table + static_cast<size_t>(min(row, Q.M - 1) / Q.rows_per_group) * LN_N + col0;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float4* slot = reinterpret_cast<float4*>(bx + lane * 64 + ((static_cast<uint32_t>(j) ^ sw) << 4));
@@ -294,12 +320,12 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            if (!(tune & 2)) tma_store_2d(&P.tx, bx, col0, row0);
+            if (!(tune & 2)) tma_store_2d(&Q.tx, bx, col0, row0);
             bulk_commit();
             if (from_x && ci + NBOX < NB1) {  // this buffer is needed again for a later residual box of the unit
               bulk_wait_read<0>();
               mbar_arrive_expect_tx(&rbar[b], L::kBoxBytes);
-              tma_load_2d(bx, &P.tr, &rbar[b], col0 + NBOX * 16, row0);
+              tma_load_2d(bx, &Q.tr, &rbar[b], col0 + NBOX * 16, row0);
             }
           }
           ++ns;
@@ -361,7 +387,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            if (!(tune & 4)) tma_store_2d(&P.ty, bx, col0, row0);
+            if (!(tune & 4)) tma_store_2d(&Q.ty, bx, col0, row0);
             bulk_commit();
           }
           ++ns;
@@ -383,7 +409,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
 }
 
 template <int ROWS, int STAGES, int NBOX>
-int launch_ln(LnGemmParams& P, int M, cudaStream_t st) {
+int launch_ln(LnGemmParams& P, cudaStream_t st) {
   using L = SmemLn<ROWS, STAGES, NBOX>;
   static_assert(L::kTotal <= 227 * 1024, "shared memory budget exceeded");
   static_assert(L::kStoreOffset % 1024 == 0, "operand stages must keep 1024-byte alignment");
@@ -392,7 +418,12 @@ int launch_ln(LnGemmParams& P, int M, cudaStream_t st) {
     M3PC_CHECK_CUDA(cudaFuncSetAttribute(gemm_ln_2sm_kernel<ROWS, STAGES, NBOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured.here() = true;
   }
-  P.n_units = ceil_div(M, ROWS);
+  int units = 0;
+  for (int g = 0; g < P.n; ++g) {
+    P.p[g].unit0 = units;
+    units += ceil_div(P.p[g].M, ROWS);
+  }
+  P.n_units = units;
   const int pairs = std::min(P.n_units, device_num_sms() / 2);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
@@ -415,39 +446,59 @@ int launch_ln(LnGemmParams& P, int M, cudaStream_t st) {
 
 }  // namespace
 
-// X (M, 512) fp32 in place (or table rows as the residual), Y (M, 512) bf16 = LayerNorm(X).  K % 64 == 0.
+// X (M, 512) fp32 in place (or other fp32 rows / table rows as the residual), Y (M, 512) bf16 = LayerNorm(X).  K % 64 == 0.
+// Up to LN_MAX_GROUP problems per launch (shared K, bias, gamma, beta).
 // Unit size (rows per CTA pair; bit-identical results, tests/test_gpu_parity.py::test_gemm_ln_unit_sizes_are_bit_identical):
 //   K <= 512   128-row units: the launch is bound by its epilogue traffic (6 KB per row), which then runs under the next unit's MMAs
 //              (measured at 106 496 rows: 125 us vs 135 us with 256-row units; profiles/r2g_gemm_ln_variants.txt)
 //   K  > 512   256-row units feed the tensor pipe with 1/3 less operand traffic per FLOP (238 vs 264 us) -- unless the launch is so
 //              small that whole 256-row units quantise badly on the 74 CTA pairs (26 624 rows: 104 units = 2 rounds, vs 3 half rounds)
-int gemm_ln_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, float* X, __nv_bfloat16* Y, const float* gamma,
-                 const float* beta, const float* table, int rows_per_group, int M, int K, cudaStream_t st, const float* R) {
-  M3PC_REQUIRE(M > 0 && K > 0 && K % BK == 0, "gemm_ln: K must be a positive multiple of 64");
-  M3PC_REQUIRE(A && W && X && Y && gamma && beta, "gemm_ln: null operand");
-  M3PC_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) & 15) == 0,
-               "gemm_ln: operands must be 16-byte aligned");
+int gemm_ln_bf16_grouped(const LnJob* jobs, int n, const float* bias, const float* gamma, const float* beta, int K, cudaStream_t st) {
+  M3PC_REQUIRE(n >= 1 && n <= LN_MAX_GROUP, "gemm_ln: 1 .. 4 problems per launch");
+  M3PC_REQUIRE(K > 0 && K % BK == 0, "gemm_ln: K must be a positive multiple of 64");
+  M3PC_REQUIRE(gamma && beta, "gemm_ln: null operand");
   M3PC_TRY(gemm_init_driver_api());
   int rows = g_ln_unit_rows;
   if (const char* t = tune_env("M3PC_LN_UNIT_ROWS")) rows = atoi(t);  // tuning build: A/B without a handle
   if (rows != 128 && rows != 256) {
     const int pairs = std::max(1, device_num_sms() / 2);
-    const double rounds256 = ceil_div(ceil_div(M, 256), pairs), rounds128 = 0.5 * ceil_div(ceil_div(M, 128), pairs);
+    int u256 = 0, u128 = 0;
+    for (int g = 0; g < n; ++g) {
+      u256 += ceil_div(jobs[g].M, 256);
+      u128 += ceil_div(jobs[g].M, 128);
+    }
+    const double rounds256 = ceil_div(u256, pairs), rounds128 = 0.5 * ceil_div(u128, pairs);
     rows = (K <= 512 || rounds128 + 0.25 < rounds256) ? 128 : 256;
   }
   LnGemmParams P{};
-  M3PC_TRY(make_tmap(&P.ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), rows / 2));
-  M3PC_TRY(make_tmap(&P.tw, W, static_cast<uint64_t>(LN_N), static_cast<uint64_t>(K), 128));
-  M3PC_TRY(make_tmap_out(&P.tx, X, static_cast<uint64_t>(M), LN_N, true));
-  M3PC_REQUIRE(R == nullptr || (table == nullptr && (reinterpret_cast<uintptr_t>(R) & 15) == 0), "gemm_ln: a residual source excludes a table and must be 16-byte aligned");
-  M3PC_TRY(make_tmap_out(&P.tr, const_cast<float*>(R != nullptr ? R : X), static_cast<uint64_t>(M), LN_N, true));
-  M3PC_TRY(make_tmap_out(&P.ty, Y, static_cast<uint64_t>(M), LN_N, false));
-  P.bias = bias; P.gamma = gamma; P.beta = beta; P.table = table;
-  P.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
-  P.M = M;
+  P.n = n;
+  for (int g = 0; g < n; ++g) {
+    const LnJob& j = jobs[g];
+    LnProblem& Q = P.p[g];
+    M3PC_REQUIRE(j.M > 0 && j.A && j.W && j.X && j.Y, "gemm_ln: null operand or empty problem");
+    M3PC_REQUIRE(((reinterpret_cast<uintptr_t>(j.A) | reinterpret_cast<uintptr_t>(j.W) | reinterpret_cast<uintptr_t>(j.X) | reinterpret_cast<uintptr_t>(j.Y)) & 15) == 0,
+                 "gemm_ln: operands must be 16-byte aligned");
+    M3PC_REQUIRE(j.R == nullptr || (j.table == nullptr && (reinterpret_cast<uintptr_t>(j.R) & 15) == 0),
+                 "gemm_ln: a residual source excludes a table and must be 16-byte aligned");
+    M3PC_TRY(make_tmap(&Q.ta, j.A, static_cast<uint64_t>(j.M), static_cast<uint64_t>(K), rows / 2));
+    M3PC_TRY(make_tmap(&Q.tw, j.W, static_cast<uint64_t>(LN_N), static_cast<uint64_t>(K), 128));
+    M3PC_TRY(make_tmap_out(&Q.tx, j.X, static_cast<uint64_t>(j.M), LN_N, true));
+    M3PC_TRY(make_tmap_out(&Q.tr, const_cast<float*>(j.R != nullptr ? j.R : j.X), static_cast<uint64_t>(j.M), LN_N, true));
+    M3PC_TRY(make_tmap_out(&Q.ty, j.Y, static_cast<uint64_t>(j.M), LN_N, false));
+    Q.table = j.table;
+    Q.rows_per_group = j.rows_per_group > 0 ? j.rows_per_group : 1;
+    Q.M = j.M;
+  }
+  P.bias = bias; P.gamma = gamma; P.beta = beta;
   P.num_kb = K / BK;
   if (const char* t = tune_env("M3PC_TUNE_LN")) P.tune = atoi(t);
-  return rows == 128 ? launch_ln<128, 3, 2>(P, M, st) : launch_ln<256, 3, 2>(P, M, st);
+  return rows == 128 ? launch_ln<128, 3, 2>(P, st) : launch_ln<256, 3, 2>(P, st);
+}
+
+int gemm_ln_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, float* X, __nv_bfloat16* Y, const float* gamma,
+                 const float* beta, const float* table, int rows_per_group, int M, int K, cudaStream_t st, const float* R) {
+  const LnJob job{A, W, X, Y, table, rows_per_group, M, R};
+  return gemm_ln_bf16_grouped(&job, 1, bias, gamma, beta, K, st);
 }
 
 }  // namespace m3pc

@@ -892,4 +892,24 @@ def test_restricted_decoder_residual_sources_are_bit_identical():
         ev = L.action_sample(syn.make_history(shape, seed=3, path_length=60), plan=True, eval=True, rtg=3.0)
         outs.append((ev.clone(), L.last_plan_debug["expect_return"].clone(), L._engine().last_launch_count()))
     assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][0], outs[1][0])
-    assert outs[0][2] == outs[1][2] + 1  # three launches (kept state, masked states, masked rewards) instead of a copy + one
+    assert outs[0][2] == outs[1][2] - 1  # one grouped launch (kept state, masked states, masked rewards) instead of a copy + one launch
+
+
+@pytest.mark.parametrize("env,guidance,temp,N,E", [("walker2d", "critic_lambda_guiding", 1.0, 600, 2), ("hopper", "rtg_guiding", 0.01, 1100, 1)])
+def test_grouped_residual_layernorm_launches_are_bit_identical(env, guidance, temp, N, E):
+    """Problems of the fused residual GEMM + LayerNorm kernel that share weights-independent parameters ride in one launch (first
+    encoder block: shared-history table part + per-candidate part; decoder embedding: one problem per run of kept tokens; restricted
+    out-projection: one per residual source).  Option grouped_ln = 0 launches them one by one: same units, same arithmetic, same bits."""
+    outs = []
+    for grouped in (1, 0):
+        shape, L = _learner(env, guidance, N, temp, "bf16", max_envs=E)
+        L._engine().set_option("grouped_ln", grouped)
+        rs = np.random.RandomState(11)
+        A = shape.act_dim
+        L.injected_noise = (torch.from_numpy(rs.randn(E * N, 4, A)).float().cuda(), torch.from_numpy(rs.exponential(1.0, E * N)).float().cuda())
+        L.debug_plans = True
+        hists = [syn.make_history(shape, seed=20 + i, path_length=40 + 7 * i) for i in range(E)]
+        ev = L.action_sample_batch(hists, plan=True, eval=True, rtg=3.0) if E > 1 else L.action_sample(hists[0], plan=True, eval=True, rtg=3.0)
+        outs.append((ev.clone(), L.last_plan_debug["expect_return"].clone(), L._engine().last_launch_count()))
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][0], outs[1][0])
+    assert outs[0][2] < outs[1][2]

@@ -23,6 +23,7 @@ def us(b):
 print(f"# HBM GB/s = (dram read + write) / duration, against MEASURED_PEAKS.json hbm_gbs {hbm:.0f}; tensor % = sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
 print(f"{'#':>2} {'kernel':<46} {'grid':>14} {'us':>8} {'tensor%':>7} {'dramR MB':>9} {'dramW MB':>9} {'GB/s':>6} {'of HBM':>6} {'L2hit%':>6}")
 tot = tt = tw = 0.0; nt = 0; traffic_t = 0.0
+per = []  # (index, name, us, tensor %)
 for i, b in enumerate(blocks):
     name = val(b, "Kernel Name")[1]
     name = re.sub(r"^void ", "", name); name = re.sub(r"unnamed>::", "", name); name = re.sub(r"\(.*", "", name)
@@ -33,6 +34,22 @@ for i, b in enumerate(blocks):
     gbs = (r + w) / t * 1e3 if t > 0 else 0.0
     print(f"{i:>2} {name[:46]:<46} {grid:>14} {t:8.1f} {tp:7.1f} {r:9.1f} {w:9.1f} {gbs:6.0f} {gbs / hbm:6.2f} {l2:6.1f}")
     tot += t
+    per.append((i, name, t, tp))
     if name.startswith("gemm_bf16_2sm") or name.startswith("gemm_ln"):
         tt += t; tw += t * tp; nt += 1; traffic_t += (r + w)
 print(f"# total {tot:.1f} us serialised; {nt} tensor-core GEMM launches (gemm_bf16_2sm + gemm_ln_2sm): {tt:.1f} us, mean DRAM bytes per launch {traffic_t / max(nt, 1):.1f} MB, time-weighted tensor pipe active {tw / max(tt, 1e-9):.1f} %")
+
+# the encoder / decoder GEMMs of pass 2 (between the candidate kernel and the critic / scoring tail): the north-star's ">= 50 % tensor pipe" set
+first = next((i for i, n, _, _ in per if n.startswith("candidates_kernel")), -1)
+last = next((i for i, n, _, _ in per if i > first and (n.startswith("critic_input") or n.startswith("score_kernel"))), len(per))
+def tw_of(sel):
+    t = sum(u for i, n, u, p in per if sel(i, n)); w = sum(u * p for i, n, u, p in per if sel(i, n))
+    return t, (w / t if t > 0 else 0.0)
+in2 = lambda i: first < i < last
+for label, sel in (("pass-2 encoder / decoder GEMMs", lambda i, n: in2(i) and (n.startswith("gemm_bf16_2sm") or n.startswith("gemm_ln"))),
+                   ("  of which plain gemm_bf16_2sm", lambda i, n: in2(i) and n.startswith("gemm_bf16_2sm")),
+                   ("  of which gemm_ln_2sm (residual + LayerNorm epilogue)", lambda i, n: in2(i) and n.startswith("gemm_ln")),
+                   ("pass-1 GEMMs (B = number of environments)", lambda i, n: i < first and (n.startswith("gemm_bf16") or n.startswith("gemm_ln"))),
+                   ("critic GEMMs", lambda i, n: i >= last and n.startswith("gemm_bf16"))):
+    t, p = tw_of(sel)
+    print(f"# {label}: {t:.1f} us, time-weighted tensor pipe active {p:.1f} %")
