@@ -160,13 +160,19 @@ __global__ void __launch_bounds__(256) fill_rows_kernel(const __grid_constant__ 
 // A warp owns R consecutive rows: every weight vector it loads is used for R dot products (at R = 1 the kernel re-read the
 // whole (d_out, D) weight matrix through L1 for every row, which bounded it at ~10 % of the HBM rate its inputs need).
 // Per row the arithmetic (per-lane FMA chain, then warp_sum) is the same for every R, so results do not depend on R.
+// A launch carries up to ROWDOT_MAX_JOBS projections (the heads of the consumed modalities): blocks [block0[j], block0[j + 1]) work on job j.
 template <int NJ, typename AT, int R>
-__global__ void __launch_bounds__(256) rowdot_kernel(const __grid_constant__ RowDotParams p) {
+__global__ void __launch_bounds__(256) rowdot_kernel(const __grid_constant__ RowDotGroup grp) {
   PDL_PROLOGUE();
   constexpr int D = NJ * 128;
   const int lane = threadIdx.x & 31;
+  int job = 0;
+#pragma unroll
+  for (int j = 1; j < ROWDOT_MAX_JOBS; ++j)
+    if (j < grp.n && static_cast<int>(blockIdx.x) >= grp.block0[j]) job = j;
+  const RowDotParams& p = grp.p[job];
   const int n_rows = p.n_t * p.B;
-  const int r0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * R;  // r = t * B + b
+  const int r0 = ((static_cast<int>(blockIdx.x) - grp.block0[job]) * 8 + (threadIdx.x >> 5)) * R;  // r = t * B + b
   if (r0 >= n_rows) return;
   float4 v[R][NJ];
 #pragma unroll
@@ -300,31 +306,43 @@ int launch_fill_rows(const FillParams& p, int D, float* x, cudaStream_t st) {
   });
 }
 
-int launch_rowdot(const RowDotParams& p, int D, bool y_bf16, cudaStream_t st) {
-  if (p.n_t <= 0) return M3PC_OK;
-  const int rows = p.n_t * p.B;
-  const bool wide = rows >= 4096 && D <= 512;  // 4 rows per warp once there are enough rows to fill the SMs (register budget: D <= 512)
-  dim3 grid(ceil_div(rows, 8 * (wide ? 4 : 1)));
+int launch_rowdot_group(const RowDotParams* jobs, int n, int D, bool y_bf16, cudaStream_t st) {
+  M3PC_REQUIRE(n >= 0 && n <= ROWDOT_MAX_JOBS, "rowdot: too many projections in one launch");
+  RowDotGroup g{};
+  int max_rows = 0;
+  for (int j = 0; j < n; ++j)
+    if (jobs[j].n_t > 0) max_rows = std::max(max_rows, jobs[j].n_t * jobs[j].B);
+  if (max_rows == 0) return M3PC_OK;
+  const bool wide = max_rows >= 4096 && D <= 512;  // 4 rows per warp once there are enough rows to fill the SMs (register budget: D <= 512)
+  int blocks = 0;
+  for (int j = 0; j < n; ++j) {
+    if (jobs[j].n_t <= 0) continue;
+    g.p[g.n] = jobs[j];
+    g.block0[g.n++] = blocks;
+    blocks += ceil_div(jobs[j].n_t * jobs[j].B, 8 * (wide ? 4 : 1));
+  }
+  dim3 grid(blocks);
   return dispatch_d(D, [&](auto nj) -> int {
     constexpr int NJ = decltype(nj)::value;
     if constexpr (NJ <= 4) {
       if (wide) {
         if (y_bf16)
-          M3PC_CHECK_CUDA(launch_k(rowdot_kernel<NJ, __nv_bfloat16, 4>, dim3(grid), dim3(256), 0, st, p));
+          M3PC_CHECK_CUDA(launch_k(rowdot_kernel<NJ, __nv_bfloat16, 4>, dim3(grid), dim3(256), 0, st, g));
         else
-          M3PC_CHECK_CUDA(launch_k(rowdot_kernel<NJ, float, 4>, dim3(grid), dim3(256), 0, st, p));
+          M3PC_CHECK_CUDA(launch_k(rowdot_kernel<NJ, float, 4>, dim3(grid), dim3(256), 0, st, g));
         M3PC_CHECK_LAUNCH();
         return M3PC_OK;
       }
     }
     if (y_bf16)
-      M3PC_CHECK_CUDA(launch_k(rowdot_kernel<NJ, __nv_bfloat16, 1>, dim3(grid), dim3(256), 0, st, p));
+      M3PC_CHECK_CUDA(launch_k(rowdot_kernel<NJ, __nv_bfloat16, 1>, dim3(grid), dim3(256), 0, st, g));
     else
-      M3PC_CHECK_CUDA(launch_k(rowdot_kernel<NJ, float, 1>, dim3(grid), dim3(256), 0, st, p));
+      M3PC_CHECK_CUDA(launch_k(rowdot_kernel<NJ, float, 1>, dim3(grid), dim3(256), 0, st, g));
     M3PC_CHECK_LAUNCH();
     return M3PC_OK;
   });
 }
+int launch_rowdot(const RowDotParams& p, int D, bool y_bf16, cudaStream_t st) { return launch_rowdot_group(&p, 1, D, y_bf16, st); }
 
 int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t st) {
   if (n == 0) return M3PC_OK;

@@ -820,7 +820,9 @@ int heads(m3pc_engine* e, const FwdIO& io, const NeedSet& need, const void* y1, 
     hid_rows += static_cast<size_t>(need.nt[k]) * Bc + 128;  // slack rows: tile tails of one problem never touch the next one's rows
   }
   if (nj > 0) M3PC_TRY(gemm_group(e, jobs, nj, st));
-  for (int k = 0; k < 4; ++k) {
+  RowDotParams rps[4];
+  int nr = 0;
+  for (int k = 0; k < 4; ++k) {  // the output projections of all consumed modalities in one launch
     if (hid[k] == nullptr) continue;
     const int d = e->dims[k];
     RowDotParams rp{};
@@ -829,8 +831,9 @@ int heads(m3pc_engine* e, const FwdIO& io, const NeedSet& need, const void* y1, 
     rp.w = e->head_w3[k];
     rp.b = e->head_b3[k];
     rp.out = outs[k] + static_cast<size_t>(b0) * T * d;
-    M3PC_TRY(launch_rowdot(rp, D, e->bf16, st));
+    rps[nr++] = rp;
   }
+  M3PC_TRY(launch_rowdot_group(rps, nr, D, e->bf16, st));
   if (io.out_mu != nullptr && need.nt[M3PC_ACTIONS] > 0) {
     RowDotParams rp{};
     rp.y = y1;
@@ -1465,9 +1468,8 @@ int plan_body(m3pc_engine* e, const m3pc_plan_args_t* a, cudaStream_t st) {
   sp.discount = a->discount; sp.lmbda = a->lmbda;
   sp.N = static_cast<int>(R); sp.h = h; sp.T = T;
   sp.J = e->J.as<float>();
-  M3PC_TRY(launch_score(sp, st));
-  if (a->dbg_expect_return) M3PC_CHECK_CUDA(cudaMemcpyAsync(a->dbg_expect_return, sp.J, sizeof(float) * R, cudaMemcpyDeviceToDevice, st));
   SelectParams sl{};
+  sl.score = sp;  // the score pass rides in the select launch
   sl.J = sp.J; sl.cand = cp.cand; sl.expq = a->expq;
   sl.n_env = E; sl.N = N; sl.h = h; sl.A = A;
   sl.temperature = a->temperature; sl.seed = a->seed; sl.cand_offset = a->cand_offset; sl.seed_ptr = e->seed_ptr_active;
@@ -1480,7 +1482,9 @@ int plan_body(m3pc_engine* e, const m3pc_plan_args_t* a, cudaStream_t st) {
     sl.xch.epoch = e->xch_epoch.as<unsigned long long>();
     sl.xch.timeout_ns = 2000000000ull;  // 2 s: a peer that never launches its plan must not hang this GPU
   }
-  return launch_select(sl, st);
+  M3PC_TRY(launch_select(sl, st));
+  if (a->dbg_expect_return) M3PC_CHECK_CUDA(cudaMemcpyAsync(a->dbg_expect_return, sp.J, sizeof(float) * R, cudaMemcpyDeviceToDevice, st));
+  return M3PC_OK;
 }
 
 // m3pc_plan: eager for parity / debug calls (injected noise, debug outputs, profiling); otherwise the launch sequence is

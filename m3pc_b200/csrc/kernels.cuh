@@ -113,6 +113,14 @@ struct RowDotParams {
   float* out2;      // std
 };
 int launch_rowdot(const RowDotParams& p, int D, bool y_bf16, cudaStream_t st);
+constexpr int ROWDOT_MAX_JOBS = 4;
+struct RowDotGroup {
+  RowDotParams p[ROWDOT_MAX_JOBS];
+  int block0[ROWDOT_MAX_JOBS];  // first block of each job
+  int n;
+};
+// several projections (the heads of the consumed modalities) in one launch; per-row arithmetic as in launch_rowdot
+int launch_rowdot_group(const RowDotParams* jobs, int n, int D, bool y_bf16, cudaStream_t st);
 
 // ---- K3: small-sequence bidirectional attention ----------------------------------------------------------
 // Token-gather form: every query / key / value token names its own source row block (row for batch b = ptr + b*bstride
@@ -212,6 +220,7 @@ struct SelectParams {
   float* partials;       // (M3PC_PARTIAL_FLOATS) or null
   int* indices;          // (2) or null
   ExchangeParams xch;    // xch.world > 0 (n_env == 1 only): exchange + merge inside the kernel; the outputs are the GLOBAL result
+  ScoreParams score;     // score.J == J: the TD(lambda) scores are computed by this launch first (one launch less per plan); null J: not
 };
 int launch_select(const SelectParams& p, cudaStream_t st);
 int launch_merge(const float* partials, int n_shards, int A, float temperature, float* eval_action, float* sample_action, int* indices,

@@ -96,10 +96,8 @@ __global__ void critic_out_kernel(const float* __restrict__ h1, const float* __r
   if (lane == 0) q[row] = fminf(s1, s2);
 }
 
-__global__ void score_kernel(const __grid_constant__ ScoreParams p) {
-  PDL_PROLOGUE();
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= p.N) return;
+// TD(lambda) return of candidate n, written as the reference's loop (learner.py:301-316)
+__device__ __forceinline__ float score_one(const ScoreParams& p, int n) {
   const int T = p.T, h = p.h;
   float disc[M3PC_MAX_T], r[M3PC_MAX_T];
   float d = 1.0f;
@@ -131,7 +129,14 @@ __global__ void score_kernel(const __grid_constant__ ScoreParams p) {
       J = __fadd_rn(J, __fmul_rn(s, lt));
     lam_t *= lam;
   }
-  p.J[n] = J;
+  return J;
+}
+
+__global__ void score_kernel(const __grid_constant__ ScoreParams p) {
+  PDL_PROLOGUE();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= p.N) return;
+  p.J[n] = score_one(p, n);
 }
 
 // ---- block reductions (1024 threads, deterministic order) ------------------------------------------------
@@ -221,11 +226,16 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const __grid_consta
   const unsigned long long seed = p.seed_ptr ? *p.seed_ptr : p.seed;
   // one block per environment: this block's slice of every per-candidate array
   const int env = blockIdx.x, row0 = env * p.N;
-  const float* __restrict__ Jv = p.J + row0;
+  const float* Jv = p.J + row0;
   const float* __restrict__ candv = p.cand + static_cast<size_t>(row0) * stride_a0;
   const float* __restrict__ expq = p.expq ? p.expq + row0 : nullptr;
   float* eval_action = p.eval_action + env * p.A;
   float* sample_action = p.sample_action + env * p.A;
+  // 0. scores of this environment's candidates, when the score pass rides in this launch (p.score.J == p.J)
+  if (p.score.J != nullptr) {
+    for (int n = tid; n < p.N; n += SEL_THREADS) p.score.J[row0 + n] = score_one(p.score, row0 + n);
+    __syncthreads();  // block-wide visibility of the global stores above
+  }
   // 1. max_n J_n (+ argmax)
   float m = -INFINITY;
   int mi = 0x7fffffff;
@@ -456,6 +466,8 @@ int launch_score(const ScoreParams& p, cudaStream_t st) {
 }
 int launch_select(const SelectParams& p, cudaStream_t st) {
   M3PC_REQUIRE(p.A <= M3PC_MAX_ACT && p.N >= 1 && p.n_env >= 1, "select: bad shape");
+  M3PC_REQUIRE(p.score.J == nullptr || (p.score.J == p.J && p.score.h >= 1 && p.score.h <= M3PC_MAX_T && p.score.N == p.N * p.n_env),
+               "select: the fused score pass must write the scores this launch selects from");
   M3PC_REQUIRE(p.n_env == 1 || (p.partials == nullptr && p.xch.world == 0), "select: per-shard records are single-environment only");
   M3PC_REQUIRE(p.xch.world >= 0 && p.xch.world <= XCH_MAX_RANKS, "select: too many ranks");
   M3PC_CHECK_CUDA(launch_k(select_kernel, dim3(p.n_env), dim3(SEL_THREADS), 0, st, p));
