@@ -162,7 +162,7 @@ inline const char* tune_env(const char*) { return nullptr; }
 // global-memory access and before it can exit (a grid that finished without waiting would release ITS dependents early).
 // The trigger is issued right after the wait, so at most one dependent grid is pre-staged at a time.
 extern int g_ln_unit_rows;  // gemm_ln.cu
-extern bool g_use_pdl;  // M3PC_NO_PDL=1 turns the attribute off (the device-side instructions are then no-ops)
+extern bool g_use_pdl;  // m3pc_set_option "pdl" = 0 turns the attribute off (the device-side instructions are then no-ops)
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -137,15 +137,15 @@ struct m3pc_engine {
   // workspaces (per chunk)
   DevBuf X, XS, Y, Y2, QKV, QSEL, ATT, HID, ENC;
   DevBuf XT, YT, QKVT;  // shared-history tables of the first encoder block (TAB_ROWS rows)
-  bool dedupe_history = true;  // M3PC_NO_DEDUPE=1 disables
+  bool dedupe_history = true;  // option "dedupe_history"
   DevBuf fb_xd, fb_bar;  // fused B = 1 path: decoder-embedding scratch, grid-barrier state
   bool use_fused_b1 = true;
   bool fuse_mlp = false;      // linear1 + GELU + linear2 + residual in one kernel, hidden on chip (mlp_fused.cu); option "fused_mlp".
                               // Off by default: measured 4 % slower per step than the two launches (profiles/r2l_fused_mlp.txt)
   bool group_ln = true;       // several fused residual GEMM + LayerNorm problems per launch; option "grouped_ln" (0: one launch each)
-  bool fuse_ln = true;        // residual GEMM + LayerNorm in one kernel (gemm_ln.cu); M3PC_NO_FUSED_LN=1 disables
-  int fuse_ln_min_rows = 1024;  // M3PC_FUSED_LN_MIN_ROWS overrides (the kernel-level parity tests call it at any size)
-  bool restrict_deep = true;  // decoders with > 1 layer: last layer on the consumed rows only (M3PC_DEC_FULL=1 disables)
+  bool fuse_ln = true;        // residual GEMM + LayerNorm in one kernel (gemm_ln.cu); option "fused_ln"
+  int fuse_ln_min_rows = 1024;  // option "fused_ln_min_rows" (the kernel-level parity tests call the kernel at any size)
+  bool restrict_deep = true;  // decoders with > 1 layer: last layer on the consumed rows only; option "restrict_deep_decoder"
   int split_residual_min_rows = 0;  // restricted decoder, out-projection: from this many needed rows up the residual is read in place, one
                                     // problem per residual source in a grouped launch (no residual copy: -6 KB of HBM traffic per row);
                                     // below, a copy kernel + one problem.  Option "split_residual_min_rows" (tests force either form).

@@ -42,7 +42,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode_tiled = nullptr;
-int g_force_bn = 0, g_force_cl = 0;  // M3PC_GEMM_CONFIG="<bn>x<cl>" pins one single-CTA configuration (tuning / tests)
+int g_force_bn = 0, g_force_cl = 0;  // tuning build: M3PC_GEMM_CONFIG="<bn>x<cl>" pins one single-CTA configuration (tuning / tests)
 #ifdef M3PC_TUNING
 int g_debug_skip_epi = 0;             // tuning build only, M3PC_GEMM_DEBUG_SKIP_EPI=1: the epilogue warps only hand the accumulator back (results are garbage)
 constexpr int EPI_DEBUG_SKIP = 1 << 30;
@@ -50,7 +50,7 @@ constexpr int EPI_DEBUG_SKIP = 1 << 30;
 constexpr int g_debug_skip_epi = 0;
 constexpr int EPI_DEBUG_SKIP = 0;     // the release library has no result-corrupting switch
 #endif
-int g_use_2sm = 1;                   // M3PC_GEMM_2SM=0 disables the CTA-pair kernel
+int g_use_2sm = 1;                   // tuning build: M3PC_GEMM_2SM=0 disables the CTA-pair kernel
 
 struct EpiParams {
   const float* bias;
@@ -688,8 +688,8 @@ int make_tmap_out(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t cols, boo
 }
 namespace {
 
-int g_use_strided = 1;  // M3PC_GEMM_STRIDED=0 restores contiguous unit ranges for every problem
-int g_use_splitk = 0;  // M3PC_GEMM_SPLITK=1 enables split-K (measured +0.4% plans/s at 1024 candidates; off by default: the reduce-add order of the two halves is not reproducible run to run)
+int g_use_strided = 1;  // tuning build: M3PC_GEMM_STRIDED=0 restores contiguous unit ranges for every problem
+int g_use_splitk = 0;  // tuning build: M3PC_GEMM_SPLITK=1 enables split-K (measured +0.4% plans/s at 1024 candidates; off by default: the reduce-add order of the two halves is not reproducible run to run)
 
 // One launch of the CTA-pair kernel over `n` problems (n <= MAX_GROUP; every N a multiple of 256).
 template <int STAGES>
