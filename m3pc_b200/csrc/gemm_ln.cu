@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) gemm_ln_2sm_kernel(const __grid
         if (lane == 0) mbar_arrive_remote(acc_empty_leader + 8u * buf);
       }
     }
-    if (lane == 0) bulk_wait_all();
+    if (lane == 0) bulk_wait_read<0>();  // shared memory may be released once the stores have been read; the writes complete with the grid
   }
 
   tc_fence_before();

@@ -606,7 +606,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_2SM, 1) gemm_bf16_2sm_kernel(cons
         if (lane == 0) mbar_arrive_remote(acc_empty_leader + 8u * static_cast<uint32_t>(a));
       }
     }
-    if (lane == 0) bulk_wait_all();  // all of this warp's stores have been written before the CTA exits
+    if (lane == 0) bulk_wait_read<0>();  // shared memory may be released once the stores have been READ; the writes complete with the grid
   }
 
   tc_fence_before();

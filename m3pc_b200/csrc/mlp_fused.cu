@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_2sm_kernel(const __gr
         if (lane == 0) mbar_arrive_remote(o_empty_leader);
       }
     }
-    if (lane == 0) bulk_wait_all();
+    if (lane == 0) bulk_wait_read<0>();  // shared memory may be released once the stores have been read; the writes complete with the grid
   }
 
   tc_fence_before();
